@@ -1,0 +1,119 @@
+/* videoswap_b200 -- C ABI of the B200-native denoising hot path of showlab/VideoSwap.
+ *
+ * The reference has no FFI boundary (it is pure Python on PyTorch/diffusers); its seam for this path is the Python
+ * call  AnimateDiffUNet3DModel.forward  (videoswap/models/animatediff_models/unet.py:328-481)  plus the CFG combine and
+ * scheduler step of the denoising loop  (videoswap/pipelines/pipeline_videoswap.py:568-587).  This header is the
+ * C-ABI a Python binding (ctypes) calls instead; every entry point cites what it replaces.
+ *
+ * Conventions: every function returns 0 on success, non-zero on error (message: vs_last_error()).  All pointers
+ * named d_* are DEVICE pointers owned by the caller (e.g. torch tensors' data_ptr()); `stream` is a cudaStream_t
+ * passed as void*.  Calls are asynchronous on that stream; the library never synchronises the device.  The handle
+ * owns the packed weights and the activation workspace; nothing is allocated after the first forward of a given
+ * shape (CUDA-graph capturable).  One host thread per handle.
+ */
+#ifndef VIDEOSWAP_B200_H
+#define VIDEOSWAP_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* vs_last_error(void);
+int vs_version(void);
+
+/* ---- model handle ---------------------------------------------------------------------------------------------
+ * Mirrors the constructor arguments of AnimateDiffUNet3DModel that the SD-1.5 + AnimateDiff configuration uses
+ * (unet.py:36-100; options/model_cfg/inference.yml of the reference). */
+typedef struct vs_unet_config {
+  int in_channels, out_channels;
+  int block_out_channels[4];
+  int layers_per_block;
+  int num_heads;                 /* `attention_head_dim` of the SD-1.5 config == number of heads (unet.py:158) */
+  int cross_attention_dim;
+  int norm_num_groups;
+  float norm_eps;
+  int use_motion_module;
+  int motion_down[4];            /* motion modules present in down block i / up block i */
+  int motion_up[4];
+  int motion_mid;
+  int motion_num_heads;
+  int pe_max_len;                /* temporal_position_encoding_max_len */
+} vs_unet_config;
+
+typedef struct vs_unet vs_unet;
+
+int vs_unet_create(const vs_unet_config* cfg, vs_unet** out);
+void vs_unet_destroy(vs_unet* h);
+
+/* Replaces  unet.load_state_dict(...)  (pipeline_videoswap.py:303,418; convert_edlora_to_diffusers.py:94-96):
+ * takes n tensors by diffusers state_dict key name (fp16 device pointers, shapes implied by the config) and re-packs
+ * them into kernel layouts (conv [Co,tap,Ci]; fused QKV; GEGLU-interleaved FF).  May be called repeatedly (LoRA merge
+ * / restore between editing prompts).  Unknown names are an error; missing names keep their previous value. */
+int vs_unet_load_weights(vs_unet* h, void* stream, int n, const char* const* names, const void* const* d_ptrs,
+                         const int64_t* numels);
+/* Number of parameter tensors the handle expects and the i-th name (for completeness checks). */
+int vs_unet_num_params(const vs_unet* h);
+const char* vs_unet_param_name(const vs_unet* h, int i);
+
+/* Replaces  AnimateDiffUNet3DModel.forward  (unet.py:328-481).
+ *   d_sample   [B, C_in, F, H, W]  (fp16 if !io_f32 else fp32), NCFHW exactly as the reference passes it
+ *   d_timesteps DEVICE array of B floats (the reference broadcasts a scalar timestep to B, unet.py:389); a device
+ *              pointer keeps the call CUDA-graph replayable with a new timestep
+ *   d_ehs      encoder hidden states fp16: [B, 77, D] (ehs_layers == 0) or ED-LoRA [B, L, 77, D] (ehs_layers == L;
+ *              layer i of the 16 cross-attention layers reads slice i, utils/edlora_util.py:40-41,96-98)
+ *   d_residuals 4 adapter maps (or NULL): NHWC fp16 [(B F), H_l, W_l, C_l] if residuals_nhwc else NCHW fp16
+ *              [(B F), C_l, H_l, W_l] as the reference passes them (down_block_additional_residuals, unet.py:336);
+ *              residual_scale multiplies them (t2i_guidance_scale, pipeline_videoswap.py:544-545)
+ *   d_out      [B, C_out, F, H, W] same dtype as d_sample */
+int vs_unet_forward(vs_unet* h, void* stream, const void* d_sample, int io_f32, int B, int F, int H, int W,
+                    const float* d_timesteps, const void* d_ehs, int ehs_tokens, int ehs_layers,
+                    const void* const* d_residuals, int residuals_nhwc, float residual_scale, void* d_out);
+size_t vs_unet_workspace_bytes(const vs_unet* h);
+/* Debug taps: after the next forward, copies of named intermediate activations (NHWC fp16) can be fetched. */
+int vs_unet_enable_taps(vs_unet* h, int enable);
+int vs_unet_num_taps(const vs_unet* h);
+int vs_unet_get_tap(const vs_unet* h, int i, const char** name, const void** d_ptr, int* nimg, int* hh, int* ww, int* c);
+
+/* Replaces the CFG combine + DDIMScheduler.step of the loop body (pipeline_videoswap.py:578-587; diffusers
+ * DDIMScheduler.step, eta = 0):  eps = eps_u + g (eps_c - eps_u);  x' = sqrt(a_p) (x - sqrt(1-a_t) eps)/sqrt(a_t)
+ * + sqrt(1-a_p) eps.   d_eps2: [2, n] (uncond first) when cfg != 0 else [1, n]; d_latents/d_out: [n]. */
+int vs_cfg_ddim_step(void* stream, const void* d_eps2, const void* d_latents, int io_f32, size_t n, int cfg,
+                     float guidance, float alpha_t, float alpha_prev, void* d_out);
+
+/* Replaces  SparsePointAdapter.forward  (models/adapter_model.py:97-136): MLP_l(point_embedding) then bilinear splat.
+ *   d_w0 [mid, E], d_b0 [mid], d_w1 [C, mid], d_b1 [C] fp16; d_point_embedding [P, E] fp32; d_tracks [F, P, 2] fp32
+ *   (x, y; negative = invisible); d_point_mask [P] int32 or NULL (index_list); d_ws: >= P*(mid + C) floats scratch.
+ *   d_map: NHWC fp16 [F, h, w, C] with h = img_h / rate, w = img_w / rate; values multiplied by `scale`. */
+int vs_adapter_level(void* stream, const void* d_w0, const void* d_b0, const void* d_w1, const void* d_b1, int E, int mid,
+                     int C, const float* d_point_embedding, const float* d_tracks, const int* d_point_mask, int F, int P,
+                     int h, int w, float rate, int coord_fp16, float scale, float* d_ws, void* d_map);
+
+/* ---- per-kernel entry points (used by the parity tests; same kernels the forward uses) -------------------------- */
+int vs_gemm(void* stream, const void* d_A, int K1, const void* d_A2, int K2, const void* d_W, int M, int N,
+            const float* d_bias, const float* d_rowvec, int pix_per_batch, const void* d_residual, void* d_out, int mode,
+            int force_bn);
+int vs_conv3x3(void* stream, const void* d_x, int C1, const void* d_x2, int C2, const void* d_w_packed, int nimg, int H,
+               int W, int Cout, const float* d_bias, const float* d_rowvec, int imgs_per_batch, const void* d_residual,
+               void* d_out);
+int vs_pack_conv3x3(void* stream, const void* d_w, int cout, int cin, void* d_out);
+int vs_pack_geglu(void* stream, const void* d_w, const void* d_b, int hidden, int K, void* d_wout, float* d_bout);
+int vs_groupnorm(void* stream, const void* d_x1, int c1, const void* d_x2, int c2, int nimg, int hw, int imgs_per_set,
+                 int groups, float eps, const float* d_gamma, const float* d_beta, int silu, float* d_sums, void* d_out);
+int vs_layernorm(void* stream, const void* d_x, int rows, int C, const float* d_gamma, const float* d_beta,
+                 const float* d_pe, int hw, int F, void* d_out);
+int vs_attention(void* stream, const void* d_q, int ldq, const void* d_k, int ldk, const void* d_v, int ldv, void* d_o,
+                 int ldo, int batch, int nq, int nk, int heads, int d, long long q_bstride, long long kv_bstride,
+                 long long o_bstride, int kv_div);
+int vs_temporal_attention(void* stream, const void* d_qkv, void* d_o, int B, int F, int HW, int C, int heads);
+int vs_conv_in(void* stream, const void* d_x, int nimg, int H, int W, int cin, const void* d_w, const float* d_bias,
+               int cout, void* d_out);
+int vs_upsample2x(void* stream, const void* d_x, int nimg, int H, int W, int C, void* d_out);
+int vs_conv3x3_s2(void* stream, const void* d_x, int nimg, int H, int W, int C, const void* d_w_packed, int Cout,
+                  const float* d_bias, void* d_scratch, void* d_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

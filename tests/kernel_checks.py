@@ -1,0 +1,269 @@
+"""Per-kernel parity checks: every CUDA kernel (called through the C-ABI) against a plain PyTorch fp32 restatement
+of the same op on the same seeded inputs.  Each check returns {"err": max abs error, "ref": max |ref|, "tol": ...}.
+Used by tests/test_kernels_gpu.py (pytest -m gpu) and tools/gpu_kernel_check.py (subprocess-isolated diagnostics)."""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+from videoswap_b200 import ops
+
+DEV = "cuda"
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(DEV)
+
+
+def _res(out, ref, rel=2 ** -8, abs_=2e-3):
+    out, ref = out.float(), ref.float()
+    err = (out - ref).abs().max().item()
+    mx = ref.abs().max().item()
+    tol = rel * mx + abs_
+    bad = not (err <= tol) or not torch.isfinite(out).all().item()
+    return {"err": err, "ref": mx, "tol": tol, "ok": not bad}
+
+
+# ---------------------------------------------------------------------------------------------------- GEMM
+def check_gemm(M=512, N=320, K=320, bias=True, residual=False, bn=0, seed=0):
+    A = _rand((M, K), seed).half()
+    W = _rand((N, K), seed + 1, 1 / math.sqrt(K)).half()
+    b = _rand((N,), seed + 2).float() if bias else None
+    R = _rand((M, N), seed + 3).half() if residual else None
+    out = ops.gemm(A, W, bias=b, residual=R, force_bn=bn)
+    ref = A.float() @ W.float().t()
+    if bias:
+        ref = ref + b
+    if residual:
+        ref = ref + R.float()
+    return _res(out, ref)
+
+
+def check_gemm_concat(M=300, N=640, K1=640, K2=320, seed=10):
+    A = _rand((M, K1), seed).half()
+    A2 = _rand((M, K2), seed + 1).half()
+    W = _rand((N, K1 + K2), seed + 2, 1 / math.sqrt(K1 + K2)).half()
+    b = _rand((N,), seed + 3).float()
+    out = ops.gemm(A, W, bias=b, A2=A2)
+    ref = torch.cat([A, A2], 1).float() @ W.float().t() + b
+    return _res(out, ref)
+
+
+def check_gemm_rowvec(M=256, N=320, K=64, seed=20):
+    A = _rand((M, K), seed).half()
+    W = _rand((N, K), seed + 1, 1 / math.sqrt(K)).half()
+    rv = _rand((4, N), seed + 2).float()
+    out = ops.gemm(A, W, rowvec=rv, pix_per_batch=64)
+    ref = A.float() @ W.float().t() + rv.repeat_interleave(64, 0)
+    return _res(out, ref)
+
+
+def check_geglu(M=384, C=320, seed=30):
+    A = _rand((M, C), seed).half()
+    W = _rand((8 * C, C), seed + 1, 1 / math.sqrt(C)).half()
+    b = _rand((8 * C,), seed + 2, 0.1).half()
+    wp, bp = ops.pack_geglu(W, b)
+    out = ops.gemm(A, wp, bias=bp, mode=ops.EPI_GEGLU)
+    h = A.float() @ W.float().t() + b.float()
+    v, g = h.chunk(2, -1)
+    ref = v * F.gelu(g)
+    return _res(out, ref)
+
+
+# ---------------------------------------------------------------------------------------------------- conv
+def _conv_ref(x_nhwc, w, b, stride=1):
+    y = F.conv2d(x_nhwc.float().permute(0, 3, 1, 2), w.float(), None if b is None else b.float(), stride=stride, padding=1)
+    return y.permute(0, 2, 3, 1)
+
+
+def check_conv3x3(n=4, H=16, W=16, ci=320, co=320, rowvec=False, residual=False, seed=40):
+    x = _rand((n, H, W, ci), seed).half()
+    w = _rand((co, ci, 3, 3), seed + 1, 1 / math.sqrt(9 * ci)).half()
+    b = _rand((co,), seed + 2).float()
+    rv = _rand((n // 2, co), seed + 3).float() if rowvec else None
+    R = _rand((n, H, W, co), seed + 4).half() if residual else None
+    out = ops.conv3x3(x, ops.pack_conv3x3(w), bias=b, rowvec=rv, imgs_per_batch=2, residual=R)
+    ref = _conv_ref(x, w, b)
+    if rowvec:
+        ref = ref + rv.repeat_interleave(2, 0)[:, None, None, :]
+    if residual:
+        ref = ref + R.float()
+    return _res(out, ref)
+
+
+def check_conv3x3_concat(n=2, H=8, W=8, c1=640, c2=320, co=640, seed=50):
+    x1 = _rand((n, H, W, c1), seed).half()
+    x2 = _rand((n, H, W, c2), seed + 1).half()
+    w = _rand((co, c1 + c2, 3, 3), seed + 2, 1 / math.sqrt(9 * (c1 + c2))).half()
+    b = _rand((co,), seed + 3).float()
+    out = ops.conv3x3(x1, ops.pack_conv3x3(w), bias=b, x2=x2)
+    ref = _conv_ref(torch.cat([x1, x2], -1), w, b)
+    return _res(out, ref)
+
+
+def check_conv3x3_odd_shape(n=3, H=7, W=12, ci=320, co=320, seed=55):
+    return check_conv3x3(n=n, H=H, W=W, ci=ci, co=co, seed=seed) if n % 2 == 0 else _conv_odd(n, H, W, ci, co, seed)
+
+
+def _conv_odd(n, H, W, ci, co, seed):
+    x = _rand((n, H, W, ci), seed).half()
+    w = _rand((co, ci, 3, 3), seed + 1, 1 / math.sqrt(9 * ci)).half()
+    b = _rand((co,), seed + 2).float()
+    out = ops.conv3x3(x, ops.pack_conv3x3(w), bias=b)
+    return _res(out, _conv_ref(x, w, b))
+
+
+def check_conv_out(n=2, H=16, W=16, ci=320, co=4, seed=60):
+    return _conv_odd(n, H, W, ci, co, seed)
+
+
+def check_conv_s2(n=2, H=16, W=16, ci=320, co=320, seed=70):
+    x = _rand((n, H, W, ci), seed).half()
+    w = _rand((co, ci, 3, 3), seed + 1, 1 / math.sqrt(9 * ci)).half()
+    b = _rand((co,), seed + 2).float()
+    out = ops.conv3x3_s2(x, ops.pack_conv3x3(w), bias=b)
+    return _res(out, _conv_ref(x, w, b, stride=2))
+
+
+def check_conv_in(n=4, H=16, W=16, seed=80):
+    x = _rand((n, H, W, 4), seed).half()
+    w = _rand((320, 4, 3, 3), seed + 1, 1 / 6).half()
+    b = _rand((320,), seed + 2).float()
+    out = ops.conv_in(x, w, b)
+    return _res(out, _conv_ref(x, w, b))
+
+
+def check_upsample(n=2, H=5, W=6, c=640, seed=90):
+    x = _rand((n, H, W, c), seed).half()
+    out = ops.upsample2x(x)
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+    return _res(out, ref, rel=0, abs_=0)
+
+
+# ---------------------------------------------------------------------------------------------------- norms
+def check_groupnorm(B=2, Fr=3, H=8, W=8, c1=320, c2=0, per_frame=False, silu=True, eps=1e-5, seed=100):
+    n = B * Fr
+    x1 = (_rand((n, H, W, c1), seed) * 1.5 + 0.3).half()
+    x2 = (_rand((n, H, W, c2), seed + 1) * 0.7 - 0.2).half() if c2 else None
+    C = c1 + c2
+    gamma = (1 + 0.1 * _rand((C,), seed + 2)).float()
+    beta = (0.1 * _rand((C,), seed + 3)).float()
+    out = ops.groupnorm(x1, gamma, beta, 32, eps, imgs_per_set=1 if per_frame else Fr, silu=silu, x2=x2)
+    x = x1 if x2 is None else torch.cat([x1, x2], -1)
+    x = x.float().permute(0, 3, 1, 2)                                # [n, C, H, W]
+    if per_frame:
+        ref = F.group_norm(x, 32, gamma, beta, eps)
+    else:                                                            # 5-D GroupNorm: stats over (C/32, F, H, W)
+        x5 = x.reshape(B, Fr, C, H, W).permute(0, 2, 1, 3, 4)
+        ref = F.group_norm(x5, 32, gamma, beta, eps).permute(0, 2, 1, 3, 4).reshape(n, C, H, W)
+    if silu:
+        ref = F.silu(ref)
+    return _res(out, ref.permute(0, 2, 3, 1))
+
+
+def check_layernorm(rows=1000, C=320, pe=False, seed=110):
+    x = (_rand((rows, C), seed) * 2 + 0.5).half()
+    gamma = (1 + 0.1 * _rand((C,), seed + 1)).float()
+    beta = (0.1 * _rand((C,), seed + 2)).float()
+    Fr, hw = 5, 8
+    table = _rand((24, C), seed + 3).float() if pe else None
+    rows = (rows // (Fr * hw)) * Fr * hw if pe else rows
+    x = x[:rows].contiguous()
+    out = ops.layernorm(x, gamma, beta, pe=table, hw=hw, F=Fr)
+    ref = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
+    if pe:
+        f_idx = (torch.arange(rows, device=DEV) // hw) % Fr
+        ref = ref + table[f_idx]
+    return _res(out, ref)
+
+
+# ---------------------------------------------------------------------------------------------------- attention
+def _mha_ref(q, k, v, heads):
+    B, nq, C = q.shape
+    d = C // heads
+    qh = q.float().reshape(B, nq, heads, d).transpose(1, 2)
+    kh = k.float().reshape(k.shape[0], -1, heads, d).transpose(1, 2)
+    vh = v.float().reshape(v.shape[0], -1, heads, d).transpose(1, 2)
+    s = qh @ kh.transpose(-1, -2) * d ** -0.5
+    return (s.softmax(-1) @ vh).transpose(1, 2).reshape(B, nq, C)
+
+
+def check_self_attention(B=3, N=200, C=320, seed=120):
+    qkv = _rand((B, N, 3 * C), seed).half()
+    q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    out = ops.attention(q, k, v, 8)
+    return _res(out, _mha_ref(q, k, v, 8))
+
+
+def check_cross_attention(B=2, Fr=3, N=100, C=640, nk=77, seed=130):
+    q = _rand((B * Fr, N, C), seed).half()
+    kv = _rand((B, nk, 2 * C), seed + 1).half()
+    k, v = kv[..., :C], kv[..., C:]
+    out = ops.attention(q, k, v, 8, kv_div=Fr)
+    ref = _mha_ref(q, k.repeat_interleave(Fr, 0), v.repeat_interleave(Fr, 0), 8)
+    return _res(out, ref)
+
+
+def check_temporal_attention(B=2, Fr=16, HW=20, C=320, seed=140):
+    qkv = _rand((B, Fr, HW, 3 * C), seed).half()
+    out = ops.temporal_attention(qkv, 8)
+    t = qkv.permute(0, 2, 1, 3).reshape(B * HW, Fr, 3 * C)
+    ref = _mha_ref(t[..., :C], t[..., C:2 * C], t[..., 2 * C:], 8)
+    ref = ref.reshape(B, HW, Fr, C).permute(0, 2, 1, 3)
+    return _res(out, ref)
+
+
+# ---------------------------------------------------------------------------------------------------- step
+def check_cfg_ddim(dtype=torch.float16, seed=150):
+    eps2 = _rand((2, 4, 4, 8, 8), seed).to(dtype)
+    x = _rand((1, 4, 4, 8, 8), seed + 1).to(dtype)
+    a_t, a_p, g = 0.0047, 0.0058, 7.5
+    out = ops.cfg_ddim_step(eps2, x, g, a_t, a_p)
+    e = eps2[0:1].float() + g * (eps2[1:2].float() - eps2[0:1].float())
+    x0 = (x.float() - math.sqrt(1 - a_t) * e) / math.sqrt(a_t)
+    ref = math.sqrt(a_p) * x0 + math.sqrt(1 - a_p) * e
+    return _res(out, ref, rel=2 ** -9, abs_=1e-3)
+
+
+CHECKS = {
+    "gemm_bn160": lambda: check_gemm(512, 320, 320),
+    "gemm_bn128_tail": lambda: check_gemm(300, 768, 320, bn=128),
+    "gemm_bn64": lambda: check_gemm(130, 64, 128, bn=64),
+    "gemm_residual": lambda: check_gemm(1024, 1280, 1280, residual=True),
+    "gemm_small_m": lambda: check_gemm(77, 640, 768),
+    "gemm_big_k": lambda: check_gemm(256, 320, 5120),
+    "gemm_many_tiles": lambda: check_gemm(128 * 150 + 5, 320, 64),
+    "gemm_concat": check_gemm_concat,
+    "gemm_rowvec": check_gemm_rowvec,
+    "geglu": check_geglu,
+    "conv3x3": lambda: check_conv3x3(),
+    "conv3x3_epi": lambda: check_conv3x3(rowvec=True, residual=True),
+    "conv3x3_w64": lambda: check_conv3x3(n=2, H=64, W=64, ci=64, co=160),
+    "conv3x3_small": lambda: check_conv3x3(n=2, H=2, W=2, ci=1280, co=1280),
+    "conv3x3_1x1": lambda: check_conv3x3(n=4, H=1, W=1, ci=1280, co=1280),
+    "conv3x3_odd": lambda: _conv_odd(3, 7, 12, 320, 320, 55),
+    "conv3x3_concat": check_conv3x3_concat,
+    "conv_out": check_conv_out,
+    "conv_s2": check_conv_s2,
+    "conv_in": check_conv_in,
+    "upsample": check_upsample,
+    "gn5d_silu": lambda: check_groupnorm(),
+    "gn5d_concat": lambda: check_groupnorm(c1=640, c2=320),
+    "gn_frame": lambda: check_groupnorm(per_frame=True, silu=False, eps=1e-6),
+    "gn5d_1280": lambda: check_groupnorm(B=1, Fr=2, H=4, W=4, c1=1280, c2=1280),
+    "ln_320": lambda: check_layernorm(C=320),
+    "ln_1280_pe": lambda: check_layernorm(rows=640, C=1280, pe=True),
+    "self_attn_d40": lambda: check_self_attention(C=320),
+    "self_attn_d80": lambda: check_self_attention(B=2, N=64, C=640),
+    "self_attn_d160": lambda: check_self_attention(B=2, N=130, C=1280),
+    "self_attn_tiny": lambda: check_self_attention(B=2, N=4, C=320),
+    "cross_attn": check_cross_attention,
+    "temporal_attn_d40": lambda: check_temporal_attention(C=320),
+    "temporal_attn_d160_f3": lambda: check_temporal_attention(B=1, Fr=3, HW=7, C=1280),
+    "temporal_attn_f24": lambda: check_temporal_attention(B=1, Fr=24, HW=5, C=640),
+    "cfg_ddim_f16": lambda: check_cfg_ddim(torch.float16),
+    "cfg_ddim_f32": lambda: check_cfg_ddim(torch.float32),
+}

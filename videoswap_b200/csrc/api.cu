@@ -1,0 +1,103 @@
+// extern "C" entry points declared in include/videoswap_b200.h (the model-handle functions live in unet.cu).
+#include "../../include/videoswap_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace vs;
+
+extern "C" const char* vs_last_error(void) { return vs::last_error(); }
+extern "C" int vs_version(void) { return 100; }
+
+extern "C" int vs_cfg_ddim_step(void* stream, const void* d_eps2, const void* d_latents, int io_f32, size_t n, int cfg,
+                                float guidance, float alpha_t, float alpha_prev, void* d_out) {
+  VS_REQUIRE(d_eps2 && d_latents && d_out, "vs_cfg_ddim_step: null pointer");
+  VS_REQUIRE(alpha_t > 0.f && alpha_t <= 1.f && alpha_prev > 0.f && alpha_prev <= 1.f, "vs_cfg_ddim_step: alphas must be in (0,1]");
+  return cfg_ddim_step((cudaStream_t)stream, d_eps2, d_latents, io_f32, n, cfg, guidance, alpha_t, alpha_prev, d_out);
+}
+
+extern "C" int vs_adapter_level(void* stream, const void* d_w0, const void* d_b0, const void* d_w1, const void* d_b1, int E,
+                                int mid, int C, const float* d_pe, const float* d_tracks, const int* d_mask, int F, int P,
+                                int h, int w, float rate, int coord_fp16, float scale, float* d_ws, void* d_map) {
+  cudaStream_t st = (cudaStream_t)stream;
+  VS_REQUIRE(d_w0 && d_b0 && d_w1 && d_b1 && d_pe && d_tracks && d_ws && d_map, "vs_adapter_level: null pointer");
+  // d_ws: [mid] b0 f32 | [C] b1 f32 | [P, mid] hidden | [P, C] feat
+  float* b0 = d_ws;
+  float* b1 = b0 + mid;
+  float* hid = b1 + C;
+  float* feat = hid + (size_t)P * mid;
+  if (int e = f16_to_f32(st, (const __half*)d_b0, mid, b0)) return e;
+  if (int e = f16_to_f32(st, (const __half*)d_b1, C, b1)) return e;
+  if (int e = small_linear(st, d_pe, P, E, (const __half*)d_w0, b0, mid, false, true, hid)) return e;   // Linear + SiLU
+  if (int e = small_linear(st, hid, P, mid, (const __half*)d_w1, b1, C, false, false, feat)) return e;
+  return adapter_splat(st, feat, d_tracks, d_mask, F, P, C, h, w, rate, coord_fp16, scale, (__half*)d_map);
+}
+
+extern "C" int vs_gemm(void* stream, const void* d_A, int K1, const void* d_A2, int K2, const void* d_W, int M, int N,
+                       const float* d_bias, const float* d_rowvec, int pix_per_batch, const void* d_residual, void* d_out,
+                       int mode, int force_bn) {
+  GemmArgs g;
+  g.A = (const __half*)d_A; g.K1 = K1; g.lda1 = K1; g.A2 = (const __half*)d_A2; g.K2 = K2; g.lda2 = K2;
+  g.Bw = (const __half*)d_W; g.M = M; g.N = N; g.bias = d_bias; g.rowvec = d_rowvec; g.pix_per_batch = pix_per_batch;
+  g.residual = (const __half*)d_residual; g.ldr = (mode == EPI_GEGLU) ? N / 2 : N;
+  g.out = (__half*)d_out; g.ldc = (mode == EPI_GEGLU) ? N / 2 : N; g.mode = mode; g.force_bn = force_bn;
+  return gemm_tc((cudaStream_t)stream, g);
+}
+
+extern "C" int vs_conv3x3(void* stream, const void* d_x, int C1, const void* d_x2, int C2, const void* d_w, int nimg, int H,
+                          int W, int Cout, const float* d_bias, const float* d_rowvec, int imgs_per_batch,
+                          const void* d_residual, void* d_out) {
+  GemmArgs g;
+  g.A = (const __half*)d_x; g.K1 = C1; g.lda1 = C1; g.A2 = (const __half*)d_x2; g.K2 = C2; g.lda2 = C2;
+  g.Bw = (const __half*)d_w; g.taps = 9; g.nimg = nimg; g.H = H; g.W = W; g.M = nimg * H * W; g.N = Cout; g.bias = d_bias;
+  g.rowvec = d_rowvec; g.pix_per_batch = imgs_per_batch * H * W; g.residual = (const __half*)d_residual; g.ldr = Cout;
+  g.out = (__half*)d_out; g.ldc = Cout;
+  return gemm_tc((cudaStream_t)stream, g);
+}
+
+extern "C" int vs_pack_conv3x3(void* stream, const void* d_w, int cout, int cin, void* d_out) {
+  return pack_conv3x3((cudaStream_t)stream, (const __half*)d_w, cout, cin, (__half*)d_out);
+}
+extern "C" int vs_pack_geglu(void* stream, const void* d_w, const void* d_b, int hidden, int K, void* d_wout, float* d_bout) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int e = pack_geglu(st, (const __half*)d_w, nullptr, hidden, K, kGegluGranule, (__half*)d_wout, nullptr)) return e;
+  return pack_geglu(st, nullptr, (const __half*)d_b, hidden, 1, kGegluGranule, nullptr, d_bout);
+}
+
+extern "C" int vs_groupnorm(void* stream, const void* d_x1, int c1, const void* d_x2, int c2, int nimg, int hw,
+                            int imgs_per_set, int groups, float eps, const float* d_gamma, const float* d_beta, int silu,
+                            float* d_sums, void* d_out) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int e = groupnorm_stats(st, (const __half*)d_x1, c1, (const __half*)d_x2, c2, nimg, hw, imgs_per_set, groups, d_sums)) return e;
+  return groupnorm_apply(st, (const __half*)d_x1, c1, (const __half*)d_x2, c2, nimg, hw, imgs_per_set, groups, d_sums, eps,
+                         d_gamma, d_beta, silu != 0, (__half*)d_out);
+}
+extern "C" int vs_layernorm(void* stream, const void* d_x, int rows, int C, const float* d_gamma, const float* d_beta,
+                            const float* d_pe, int hw, int F, void* d_out) {
+  return layernorm((cudaStream_t)stream, (const __half*)d_x, rows, C, d_gamma, d_beta, d_pe, hw, F, (__half*)d_out);
+}
+extern "C" int vs_attention(void* stream, const void* d_q, int ldq, const void* d_k, int ldk, const void* d_v, int ldv,
+                            void* d_o, int ldo, int batch, int nq, int nk, int heads, int d, long long q_bstride,
+                            long long kv_bstride, long long o_bstride, int kv_div) {
+  return attention((cudaStream_t)stream, (const __half*)d_q, ldq, (const __half*)d_k, ldk, (const __half*)d_v, ldv,
+                   (__half*)d_o, ldo, batch, nq, nk, heads, d, q_bstride, kv_bstride, o_bstride, kv_div);
+}
+extern "C" int vs_temporal_attention(void* stream, const void* d_qkv, void* d_o, int B, int F, int HW, int C, int heads) {
+  return temporal_attention((cudaStream_t)stream, (const __half*)d_qkv, (__half*)d_o, B, F, HW, C, heads);
+}
+extern "C" int vs_conv_in(void* stream, const void* d_x, int nimg, int H, int W, int cin, const void* d_w, const float* d_bias,
+                          int cout, void* d_out) {
+  return conv_in_3x3((cudaStream_t)stream, (const __half*)d_x, nimg, H, W, cin, (const __half*)d_w, d_bias, cout, (__half*)d_out);
+}
+extern "C" int vs_upsample2x(void* stream, const void* d_x, int nimg, int H, int W, int C, void* d_out) {
+  return upsample_nearest2x((cudaStream_t)stream, (const __half*)d_x, nimg, H, W, C, (__half*)d_out);
+}
+extern "C" int vs_conv3x3_s2(void* stream, const void* d_x, int nimg, int H, int W, int C, const void* d_w, int Cout,
+                             const float* d_bias, void* d_scratch, void* d_out) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int e = im2col_s2(st, (const __half*)d_x, nimg, H, W, C, (__half*)d_scratch)) return e;
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  GemmArgs g;
+  g.A = (const __half*)d_scratch; g.K1 = 9 * C; g.lda1 = 9 * C; g.Bw = (const __half*)d_w; g.M = nimg * Ho * Wo; g.N = Cout;
+  g.bias = d_bias; g.out = (__half*)d_out; g.ldc = Cout;
+  return gemm_tc(st, g);
+}

@@ -1,0 +1,358 @@
+// Attention kernels, v1: flash-attention-2 style streaming softmax on mma.sync.m16n8k16 (fp16 in, fp32 accumulate).
+//  * attention():           spatial self-attention (N x N, d = 40/80/160) and cross-attention (N x 77) --
+//                           replaces diffusers AttnProcessor2_0 / EDLoRA_AttnProcessor.__call__
+//                           (reference utils/edlora_util.py:47-65, models/animatediff_models/attention.py:229-241).
+//  * temporal_attention():  attention across the F frames of every pixel (motion_module.py:305-335), one warp per
+//                           (batch, pixel, head); probabilities never touch HBM and no '(b f) d c <-> (b d) f c'
+//                           transposes are materialised.
+// These are the legacy-tensor-path (HMMA) baseline kernels; the tcgen05/TMEM version replaces the spatial one.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vs {
+namespace {
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool pred) {
+  const int sz = pred ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// One warp: S[16 x 8*NT] = Q[16 x DP] K[8*NT x DP]^T.  q_s / k_s: shared addresses of row 0, row stride LDS bytes.
+template <int DP, int NT>
+__device__ __forceinline__ void warp_qk(float (*s)[4], uint32_t q_s, uint32_t k_s, int lds_bytes, int lane) {
+#pragma unroll
+  for (int n = 0; n < NT; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+#pragma unroll
+  for (int kk = 0; kk < DP / 16; ++kk) {
+    uint32_t a[4];
+    ldsm_x4(q_s + (lane & 15) * lds_bytes + (kk * 16 + (lane >> 4) * 8) * 2, a[0], a[1], a[2], a[3]);
+#pragma unroll
+    for (int n = 0; n < NT; n += 2) {
+      uint32_t b0, b1, b2, b3;
+      const int key = n * 8 + (lane & 7) + ((lane >> 4) ? 8 : 0);
+      const int ch = kk * 16 + (((lane >> 3) & 1) ? 8 : 0);
+      ldsm_x4(k_s + key * lds_bytes + ch * 2, b0, b1, b2, b3);
+      mma16816(s[n], a, b0, b1);
+      mma16816(s[n + 1], a, b2, b3);
+    }
+  }
+}
+
+// One warp: O[16 x 8*ON] += P[16 x 8*NT] V[8*NT x 8*ON]; P comes from the S accumulators (already exponentiated).
+template <int NT, int ON>
+__device__ __forceinline__ void warp_pv(float (*o)[4], const float (*s)[4], uint32_t v_s, int lds_bytes, int lane) {
+#pragma unroll
+  for (int kt = 0; kt < NT / 2; ++kt) {
+    uint32_t a[4];
+    a[0] = pack_h2(s[2 * kt][0], s[2 * kt][1]);
+    a[1] = pack_h2(s[2 * kt][2], s[2 * kt][3]);
+    a[2] = pack_h2(s[2 * kt + 1][0], s[2 * kt + 1][1]);
+    a[3] = pack_h2(s[2 * kt + 1][2], s[2 * kt + 1][3]);
+#pragma unroll
+    for (int n = 0; n < ON; n += 2) {
+      uint32_t b0, b1, b2, b3;
+      const int key = kt * 16 + (lane & 7) + (((lane >> 3) & 1) ? 8 : 0);
+      const int ch = n * 8 + ((lane >> 4) ? 8 : 0);
+      ldsm_x4_t(v_s + key * lds_bytes + ch * 2, b0, b1, b2, b3);
+      mma16816(o[n], a, b0, b1);
+      mma16816(o[n + 1], a, b2, b3);
+    }
+  }
+}
+
+// ================================================================================================ spatial / cross
+struct AttnParams {
+  const __half* q; const __half* k; const __half* v; __half* o;
+  int ldq, ldk, ldv, ldo;
+  long long q_bs, kv_bs, o_bs;
+  int nq, nk, kv_div;
+  float scale_log2;
+};
+
+template <int D>
+struct ACfg {
+  static constexpr int DP = (D + 15) / 16 * 16;
+  static constexpr int LDS = DP + 8;           // halves per smem row (conflict-free ldmatrix)
+  static constexpr int BQ = 64, BKV = 64;
+  static constexpr int SMEM = (BQ + 4 * BKV) * LDS * 2;
+};
+
+template <int D>
+__device__ __forceinline__ void load_rows(uint32_t dst, const __half* src, int ld, int row0, int nrows_valid, int tid,
+                                          int nthreads) {
+  using C = ACfg<D>;
+  constexpr int CH = C::DP / 8;  // 16-byte chunks per row
+  for (int i = tid; i < 64 * CH; i += nthreads) {
+    const int r = i / CH, c = i % CH;
+    const bool ok = (row0 + r < nrows_valid) && (c * 8 < D);
+    const __half* s = ok ? src + (long long)(row0 + r) * ld + c * 8 : src;
+    cp_async16(dst + (r * C::LDS + c * 8) * 2, s, ok);
+  }
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) attn_kernel(const AttnParams p) {
+  using C = ACfg<D>;
+  constexpr int DP = C::DP, LDSB = C::LDS * 2, NT = C::BKV / 8, ON = DP / 8;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const uint32_t q_s = smem_u32(smem);
+  const uint32_t k_s0 = q_s + C::BQ * LDSB;
+  const uint32_t v_s0 = k_s0 + 2 * C::BKV * LDSB;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const __half* qp = p.q + b * p.q_bs + h * D;
+  const __half* kp = p.k + (b / p.kv_div) * p.kv_bs + h * D;
+  const __half* vp = p.v + (b / p.kv_div) * p.kv_bs + h * D;
+  const int nkt = (p.nk + C::BKV - 1) / C::BKV;
+
+  load_rows<D>(q_s, qp, p.ldq, qt * C::BQ, p.nq, tid, 128);
+  load_rows<D>(k_s0, kp, p.ldk, 0, p.nk, tid, 128);
+  load_rows<D>(v_s0, vp, p.ldv, 0, p.nk, tid, 128);
+  cp_async_commit();
+
+  float o[ON][4];
+#pragma unroll
+  for (int n = 0; n < ON; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+  for (int j = 0; j < nkt; ++j) {
+    cp_async_wait<0>();
+    __syncthreads();
+    if (j + 1 < nkt) {  // prefetch the next K/V tile into the other buffer (free: every warp is past tile j-1)
+      const int nb = (j + 1) & 1;
+      load_rows<D>(k_s0 + nb * C::BKV * LDSB, kp, p.ldk, (j + 1) * C::BKV, p.nk, tid, 128);
+      load_rows<D>(v_s0 + nb * C::BKV * LDSB, vp, p.ldv, (j + 1) * C::BKV, p.nk, tid, 128);
+      cp_async_commit();
+    }
+    const uint32_t k_s = k_s0 + (j & 1) * C::BKV * LDSB;
+    const uint32_t v_s = v_s0 + (j & 1) * C::BKV * LDSB;
+    float s[NT][4];
+    warp_qk<DP, NT>(s, q_s + warp * 16 * LDSB, k_s, LDSB, lane);
+    // mask keys beyond nk (last tile only)
+    const int kbase = j * C::BKV;
+    if (kbase + C::BKV > p.nk) {
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        const int c = kbase + n * 8 + (lane & 3) * 2;
+        if (c >= p.nk) s[n][0] = s[n][2] = -INFINITY;
+        if (c + 1 >= p.nk) s[n][1] = s[n][3] = -INFINITY;
+      }
+    }
+    float mx0 = m0, mx1 = m1;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      mx0 = fmaxf(mx0, fmaxf(s[n][0], s[n][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[n][2], s[n][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float c0 = exp2f((m0 - mx0) * p.scale_log2), c1 = exp2f((m1 - mx1) * p.scale_log2);
+    m0 = mx0; m1 = mx1;
+    const float ms0 = mx0 * p.scale_log2, ms1 = mx1 * p.scale_log2;
+    float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      s[n][0] = exp2f(s[n][0] * p.scale_log2 - ms0);
+      s[n][1] = exp2f(s[n][1] * p.scale_log2 - ms0);
+      s[n][2] = exp2f(s[n][2] * p.scale_log2 - ms1);
+      s[n][3] = exp2f(s[n][3] * p.scale_log2 - ms1);
+      rs0 += s[n][0] + s[n][1];
+      rs1 += s[n][2] + s[n][3];
+    }
+    l0 = l0 * c0 + rs0;
+    l1 = l1 * c1 + rs1;
+#pragma unroll
+    for (int n = 0; n < ON; ++n) {
+      o[n][0] *= c0; o[n][1] *= c0; o[n][2] *= c1; o[n][3] *= c1;
+    }
+    warp_pv<NT, ON>(o, s, v_s, LDSB, lane);
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  const int r0 = qt * C::BQ + warp * 16 + (lane >> 2), r1 = r0 + 8;
+  __half* op = p.o + b * p.o_bs + h * D;
+#pragma unroll
+  for (int n = 0; n < ON; ++n) {
+    const int c = n * 8 + (lane & 3) * 2;
+    if (c < D) {
+      if (r0 < p.nq) *reinterpret_cast<__half2*>(op + (long long)r0 * p.ldo + c) = __floats2half2_rn(o[n][0] * i0, o[n][1] * i0);
+      if (r1 < p.nq) *reinterpret_cast<__half2*>(op + (long long)r1 * p.ldo + c) = __floats2half2_rn(o[n][2] * i1, o[n][3] * i1);
+    }
+  }
+}
+
+template <int D>
+int launch_attn(cudaStream_t st, const AttnParams& p, int batch, int heads) {
+  using C = ACfg<D>;
+  static bool configured = false;
+  if (!configured) {
+    VS_CHECK_CUDA(cudaFuncSetAttribute(attn_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    configured = true;
+  }
+  dim3 grid((p.nq + C::BQ - 1) / C::BQ, heads, batch);
+  attn_kernel<D><<<grid, 128, C::SMEM, st>>>(p);
+  VS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ================================================================================================ temporal
+struct TAttnParams {
+  const __half* qkv; __half* o;
+  int B, F, HW, C, heads;
+  float scale_log2;
+  long long items;
+};
+
+template <int D, int FP>   // FP = frames padded to 16 or 32
+__global__ void __launch_bounds__(128) tattn_kernel(const TAttnParams p) {
+  constexpr int DP = (D + 15) / 16 * 16, LDS = DP + 8, LDSB = LDS * 2, CH = DP / 8;
+  constexpr int MT = FP / 16, NT = FP / 8, ON = DP / 8;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long item = (long long)blockIdx.x * 4 + warp;
+  if (item >= p.items) return;   // whole warp exits together; no block-level sync below
+  const int head = item % p.heads;
+  const long long bp = item / p.heads;
+  const int pix = bp % p.HW;
+  const int b = bp / p.HW;
+  const uint32_t base = smem_u32(smem) + warp * (3 * FP * LDSB);
+  const uint32_t q_s = base, k_s = base + FP * LDSB, v_s = base + 2 * FP * LDSB;
+  const long long row_stride = (long long)p.HW * 3 * p.C;   // between frames
+  const __half* src = p.qkv + ((long long)b * p.F * p.HW + pix) * 3 * p.C + head * D;
+  for (int i = lane; i < 3 * FP * CH; i += 32) {
+    const int sec = i / (FP * CH), rem = i % (FP * CH), f = rem / CH, c = rem % CH;
+    const bool ok = (f < p.F) && (c * 8 < D);
+    const __half* s = ok ? src + f * row_stride + sec * p.C + c * 8 : src;
+    cp_async16(base + sec * FP * LDSB + (f * LDS + c * 8) * 2, s, ok);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncwarp();
+  __half* dst = p.o + ((long long)b * p.F * p.HW + pix) * p.C + head * D;
+  const long long orow = (long long)p.HW * p.C;
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    float s[NT][4];
+    warp_qk<DP, NT>(s, q_s + mt * 16 * LDSB, k_s, LDSB, lane);
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      const int c = n * 8 + (lane & 3) * 2;
+      if (c >= p.F) s[n][0] = s[n][2] = -INFINITY;
+      if (c + 1 >= p.F) s[n][1] = s[n][3] = -INFINITY;
+      mx0 = fmaxf(mx0, fmaxf(s[n][0], s[n][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[n][2], s[n][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float ms0 = mx0 * p.scale_log2, ms1 = mx1 * p.scale_log2;
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      s[n][0] = exp2f(s[n][0] * p.scale_log2 - ms0);
+      s[n][1] = exp2f(s[n][1] * p.scale_log2 - ms0);
+      s[n][2] = exp2f(s[n][2] * p.scale_log2 - ms1);
+      s[n][3] = exp2f(s[n][3] * p.scale_log2 - ms1);
+      l0 += s[n][0] + s[n][1];
+      l1 += s[n][2] + s[n][3];
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    float o[ON][4];
+#pragma unroll
+    for (int n = 0; n < ON; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+    warp_pv<NT, ON>(o, s, v_s, LDSB, lane);
+    const float i0 = 1.f / l0, i1 = 1.f / l1;
+    const int f0 = mt * 16 + (lane >> 2), f1 = f0 + 8;
+#pragma unroll
+    for (int n = 0; n < ON; ++n) {
+      const int c = n * 8 + (lane & 3) * 2;
+      if (c < D) {
+        if (f0 < p.F) *reinterpret_cast<__half2*>(dst + f0 * orow + c) = __floats2half2_rn(o[n][0] * i0, o[n][1] * i0);
+        if (f1 < p.F) *reinterpret_cast<__half2*>(dst + f1 * orow + c) = __floats2half2_rn(o[n][2] * i1, o[n][3] * i1);
+      }
+    }
+  }
+}
+
+template <int D, int FP>
+int launch_tattn(cudaStream_t st, const TAttnParams& p) {
+  constexpr int DP = (D + 15) / 16 * 16;
+  constexpr int SMEM = 4 * 3 * FP * (DP + 8) * 2;
+  static bool configured = false;
+  if (!configured) {
+    VS_CHECK_CUDA(cudaFuncSetAttribute(tattn_kernel<D, FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  const long long blocks = (p.items + 3) / 4;
+  tattn_kernel<D, FP><<<(unsigned)blocks, 128, SMEM, st>>>(p);
+  VS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+int attention(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv, __half* o,
+              int ldo, int batch, int nq, int nk, int heads, int d, long long q_bstride, long long kv_bstride,
+              long long o_bstride, int kv_div) {
+  VS_REQUIRE(nq > 0 && nk > 0 && batch > 0, "attention: empty problem");
+  VS_REQUIRE((ldq % 8 | ldk % 8 | ldv % 8 | ldo % 2) == 0 && d % 8 == 0, "attention: unaligned leading dims");
+  AttnParams p{q, k, v, o, ldq, ldk, ldv, ldo, q_bstride, kv_bstride, o_bstride, nq, nk, kv_div > 0 ? kv_div : 1,
+               1.4426950408889634f / sqrtf((float)d)};
+  switch (d) {
+    case 40: return launch_attn<40>(st, p, batch, heads);
+    case 80: return launch_attn<80>(st, p, batch, heads);
+    case 160: return launch_attn<160>(st, p, batch, heads);
+    default: VS_REQUIRE(false, "attention: unsupported head dim %d (supported: 40, 80, 160)", d);
+  }
+}
+
+int temporal_attention(cudaStream_t st, const __half* qkv, __half* o, int B, int F, int HW, int C, int heads) {
+  VS_REQUIRE(F >= 1 && F <= 32, "temporal_attention: F=%d out of range (1..32)", F);
+  VS_REQUIRE(C % heads == 0, "temporal_attention: C %% heads != 0");
+  const int d = C / heads;
+  TAttnParams p{qkv, o, B, F, HW, C, heads, 1.4426950408889634f / sqrtf((float)d), (long long)B * HW * heads};
+  const bool big = F > 16;
+  switch (d) {
+    case 40: return big ? launch_tattn<40, 32>(st, p) : launch_tattn<40, 16>(st, p);
+    case 80: return big ? launch_tattn<80, 32>(st, p) : launch_tattn<80, 16>(st, p);
+    case 160: return big ? launch_tattn<160, 32>(st, p) : launch_tattn<160, 16>(st, p);
+    default: VS_REQUIRE(false, "temporal_attention: unsupported head dim %d", d);
+  }
+}
+
+}  // namespace vs

@@ -1,0 +1,84 @@
+// Host-side launchers of the sm_100a kernels (all asynchronous on `st`, no hidden allocation, return 0 on success).
+// Activation layout everywhere: NHWC fp16, i.e. tokens [(b f), h*w, C] with C innermost.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vs {
+
+enum EpiMode { EPI_LINEAR = 0, EPI_GEGLU = 1 };
+
+// out[pix, n] = epilogue( sum_k A[pix(+tap shift), k] * Bw[n, k] )
+//   * plain GEMM (taps == 1): A is [M, K1] (lda1) optionally followed along K by A2 [M, K2] (channel concat).
+//   * 3x3 conv (taps == 9): A is NHWC [nimg, H, W, C1] (+ A2 [.., C2]); Bw is [N, 9*(C1+C2)], tap-major;
+//     zero padding comes from TMA out-of-bounds fill.
+//   epilogue: + bias[n] + rowvec[pix / pix_per_batch, n] + residual[pix, n]; EPI_GEGLU: value*gelu(gate) on
+//   column-interleaved weights (see pack_geglu) -> N/2 output columns.
+struct GemmArgs {
+  const __half* A = nullptr;  int K1 = 0;  int lda1 = 0;
+  const __half* A2 = nullptr; int K2 = 0;  int lda2 = 0;
+  const __half* Bw = nullptr;                 // [N, taps*(K1+K2)] fp16, K contiguous
+  int M = 0, N = 0;
+  int taps = 1;                               // 1 or 9
+  int nimg = 0, H = 0, W = 0;                 // conv geometry (taps == 9)
+  const float* bias = nullptr;                // [N] fp32
+  const float* rowvec = nullptr;              // [M / pix_per_batch, ldrv] fp32 (time-embedding add)
+  int ldrv = 0;                               // row stride of rowvec (0 = N)
+  int pix_per_batch = 1;
+  const __half* residual = nullptr; int ldr = 0;
+  __half* out = nullptr; int ldc = 0;
+  int mode = EPI_LINEAR;
+  int force_bn = 0;                           // 0 = auto
+};
+int gemm_tc(cudaStream_t st, const GemmArgs& a);
+constexpr int kGegluGranule = 80;             // value/gate column interleave granule (= BLOCK_N/2 of the GEGLU GEMM)
+
+// ---- normalisation -------------------------------------------------------------------------------------------
+// GroupNorm over `nstat` statistics sets; set s covers `imgs_per_set` consecutive images (5-D GroupNorm of the
+// reference: imgs_per_set = F; per-frame GroupNorm: imgs_per_set = 1).  Input may be a virtual channel concat.
+// sums: [nstat, groups, 2] fp32 (sum, sum of squares); zeroed inside groupnorm_stats.
+int groupnorm_stats(cudaStream_t st, const __half* x1, int c1, const __half* x2, int c2, int nimg, int hw,
+                    int imgs_per_set, int groups, float* sums);
+int groupnorm_apply(cudaStream_t st, const __half* x1, int c1, const __half* x2, int c2, int nimg, int hw,
+                    int imgs_per_set, int groups, const float* sums, float eps, const float* gamma,
+                    const float* beta, bool silu, __half* out);
+// LayerNorm over the last dim of [rows, C]; optional temporal positional encoding pe[(row / hw) % F, :] added after.
+int layernorm(cudaStream_t st, const __half* x, int rows, int C, const float* gamma, const float* beta,
+              const float* pe, int hw, int F, __half* out);
+
+// ---- attention -----------------------------------------------------------------------------------------------
+// Spatial self/cross attention, all heads: q[b, nq, h, d] (row stride ldq), k/v[b, nk, h, d] (ldk/ldv) -> o (ldo).
+int attention(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv,
+              __half* o, int ldo, int batch, int nq, int nk, int heads, int d, long long q_bstride,
+              long long kv_bstride, long long o_bstride, int kv_div);   // k/v batch index = batch / kv_div
+// Temporal attention across F frames per pixel: qkv [B, F, HW, 3C] -> o [B, F, HW, C].
+int temporal_attention(cudaStream_t st, const __half* qkv, __half* o, int B, int F, int HW, int C, int heads);
+
+// ---- pointwise / small -----------------------------------------------------------------------------------------
+int small_linear(cudaStream_t st, const float* x, int rows, int K, const __half* W, const float* bias, int N,
+                 bool silu_in, bool silu_out, float* out);     // out[r,n] = act(sum_k f(x[r,k]) W[n,k] + b[n]), fp32
+int timestep_embedding(cudaStream_t st, const float* t, int B, int dim, float* out);   // cat(cos, sin)
+int conv_in_3x3(cudaStream_t st, const __half* x, int nimg, int H, int W, int cin, const __half* w, const float* bias,
+                int cout, __half* out);                        // direct conv for tiny Cin (conv_in)
+int upsample_nearest2x(cudaStream_t st, const __half* x, int nimg, int H, int W, int C, __half* out);
+int im2col_s2(cudaStream_t st, const __half* x, int nimg, int H, int W, int C, __half* out);  // [nimg*Ho*Wo, 9*C]
+int add_inplace(cudaStream_t st, __half* x, const __half* r, size_t n, float scale);   // x += scale * r
+int ncfhw_to_nhwc(cudaStream_t st, const void* src, int src_is_f32, int B, int C, int F, int H, int W, __half* dst);
+int nhwc_to_ncfhw(cudaStream_t st, const __half* src, int B, int C, int F, int H, int W, void* dst, int dst_is_f32);
+int nchw_to_nhwc(cudaStream_t st, const __half* src, int n, int C, int H, int W, float scale, __half* dst);
+// eps = u + s (c - u); x_prev = sqrt(a_p) (x - sqrt(1-a_t) eps)/sqrt(a_t) + sqrt(1-a_p) eps.  eps2: [2, n] (uncond
+// first) or [1, n] when guidance is disabled (cfg == 0).
+int cfg_ddim_step(cudaStream_t st, const void* eps2, const void* latents, int is_f32, size_t n, int cfg,
+                  float guidance, float a_t, float a_prev, void* out);
+// SparsePointAdapter splat: feat [P, C] fp32, tracks [F, P, 2] fp32 -> maps NHWC [F, h, w, C] fp16 (zeroed inside)
+int adapter_splat(cudaStream_t st, const float* feat, const float* tracks, const int* point_mask, int F, int P, int C,
+                  int h, int w, float rate, int coord_fp16, float scale, __half* maps);
+
+// ---- weight packing --------------------------------------------------------------------------------------------
+int pack_conv3x3(cudaStream_t st, const __half* w, int cout, int cin, __half* out);   // [co,ci,3,3] -> [co,tap,ci]
+int pack_geglu(cudaStream_t st, const __half* w, const __half* b, int hidden, int K, int granule, __half* wout,
+               float* bout);   // rows interleaved value/gate in `granule` blocks; w or b may be null (pack one only)
+int f16_to_f32(cudaStream_t st, const __half* x, size_t n, float* out);
+
+}  // namespace vs

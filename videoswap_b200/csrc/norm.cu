@@ -1,0 +1,241 @@
+// HBM-bound normalisation kernels (NHWC fp16 in/out, fp32 statistics):
+//  * GroupNorm(32) statistics + apply(+SiLU).  A "statistics set" is `imgs_per_set` consecutive images: the
+//    reference's ResnetBlock3D / conv_norm_out GroupNorm runs on the 5-D [B,C,F,H,W] tensor, so its statistics
+//    span all F frames of a batch element (resnet.py:166,177; unet.py:474), whereas Transformer3DModel.norm and the
+//    motion-module norm are per frame (attention.py:108, motion_module.py:146).  The input may be a *virtual*
+//    channel concat of two tensors (skip connections, unet_blocks.py:618,720): the concat is never materialised
+//    un-normalised.
+//  * LayerNorm over C with an optional temporal sinusoidal positional encoding added after the norm
+//    (motion_module.py:224-228,294).
+// Every thread owns a fixed 8-channel vector (16-byte loads) and walks pixels, so per-channel parameters stay in
+// registers; reductions are warp shuffle -> shared atomics -> one global atomic per (block, group).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vs {
+namespace {
+
+struct GnParams {
+  const __half* x1; const __half* x2; int c1, c2;
+  int C, CV;                 // total channels, 8-channel vectors per pixel
+  int hw, imgs_per_set, groups, cpg;
+  long long pix_per_set;     // imgs_per_set * hw
+  float* sums;               // [nstat, groups, 2]
+  const float* gamma; const float* beta; float eps; int silu;
+  __half* out;
+  int rows_per_block;        // pixel rows in flight per block (blockDim.x = CV * rows_per_block)
+  int pix_per_block;
+};
+
+__device__ __forceinline__ uint4 gn_load(const GnParams& p, long long pix, int cv) {
+  const int c = cv * 8;
+  if (c < p.c1) return *reinterpret_cast<const uint4*>(p.x1 + pix * p.c1 + c);
+  return *reinterpret_cast<const uint4*>(p.x2 + pix * p.c2 + (c - p.c1));
+}
+
+__global__ void gn_stats_kernel(const GnParams p) {
+  extern __shared__ float sh[];   // [groups][2]
+  for (int i = threadIdx.x; i < p.groups * 2; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int set = blockIdx.y;
+  const int cv = threadIdx.x % p.CV, r = threadIdx.x / p.CV;
+  const int ga = (cv * 8) / p.cpg, gb = (cv * 8 + 7) / p.cpg;
+  const int split = (ga == gb) ? 8 : (gb * p.cpg - cv * 8);   // first `split` channels belong to group ga
+  float sa = 0.f, qa = 0.f, sb = 0.f, qb = 0.f;
+  const long long p0 = (long long)blockIdx.x * p.pix_per_block;
+  const long long p1 = min(p0 + p.pix_per_block, p.pix_per_set);
+  const long long base = (long long)set * p.pix_per_set;
+  for (long long i = p0 + r; i < p1; i += p.rows_per_block) {
+    const uint4 v = gn_load(p, base + i, cv);
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      if (2 * j < split) { sa += f.x; qa += f.x * f.x; } else { sb += f.x; qb += f.x * f.x; }
+      if (2 * j + 1 < split) { sa += f.y; qa += f.y * f.y; } else { sb += f.y; qb += f.y * f.y; }
+    }
+  }
+  atomicAdd(&sh[ga * 2], sa);
+  atomicAdd(&sh[ga * 2 + 1], qa);
+  if (gb != ga) {
+    atomicAdd(&sh[gb * 2], sb);
+    atomicAdd(&sh[gb * 2 + 1], qb);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < p.groups * 2; i += blockDim.x) atomicAdd(&p.sums[(long long)set * p.groups * 2 + i], sh[i]);
+}
+
+__global__ void gn_apply_kernel(const GnParams p) {
+  const int set = blockIdx.y;
+  const int cv = threadIdx.x % p.CV, r = threadIdx.x / p.CV;
+  float a[8], b[8];
+  const float inv_n = 1.f / ((float)p.pix_per_set * p.cpg);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cv * 8 + j;
+    const int g = c / p.cpg;
+    const float s = p.sums[((long long)set * p.groups + g) * 2], q = p.sums[((long long)set * p.groups + g) * 2 + 1];
+    const float mean = s * inv_n;
+    const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + p.eps);
+    a[j] = rstd * p.gamma[c];
+    b[j] = p.beta[c] - mean * a[j];
+  }
+  const long long p0 = (long long)blockIdx.x * p.pix_per_block;
+  const long long p1 = min(p0 + p.pix_per_block, p.pix_per_set);
+  const long long base = (long long)set * p.pix_per_set;
+  for (long long i = p0 + r; i < p1; i += p.rows_per_block) {
+    const uint4 v = gn_load(p, base + i, cv);
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      float y0 = f.x * a[2 * j] + b[2 * j], y1 = f.y * a[2 * j + 1] + b[2 * j + 1];
+      if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
+      oh[j] = __floats2half2_rn(y0, y1);
+    }
+    *reinterpret_cast<uint4*>(p.out + (base + i) * p.C + cv * 8) = o;
+  }
+}
+
+int gn_fill(GnParams& p, dim3& grid, int& threads, const __half* x1, int c1, const __half* x2, int c2, int nimg, int hw,
+            int imgs_per_set, int groups) {
+  const int C = c1 + c2;
+  VS_REQUIRE(x1 && c1 > 0 && (c2 == 0 || x2), "groupnorm: bad inputs");
+  VS_REQUIRE(c1 % 8 == 0 && c2 % 8 == 0, "groupnorm: channel counts must be multiples of 8 (got %d, %d)", c1, c2);
+  VS_REQUIRE(C % groups == 0 && (C / groups) >= 8, "groupnorm: needs >= 8 channels per group (C=%d groups=%d)", C, groups);
+  VS_REQUIRE(nimg % imgs_per_set == 0, "groupnorm: nimg %% imgs_per_set != 0");
+  VS_REQUIRE(C / 8 <= 1024, "groupnorm: too many channels");
+  p.x1 = x1; p.x2 = x2; p.c1 = c1; p.c2 = c2; p.C = C; p.CV = C / 8;
+  p.hw = hw; p.imgs_per_set = imgs_per_set; p.groups = groups; p.cpg = C / groups;
+  p.pix_per_set = (long long)imgs_per_set * hw;
+  int rows = 512 / p.CV;
+  if (rows < 1) rows = 1;
+  p.rows_per_block = rows;
+  threads = p.CV * rows;
+  const int nstat = nimg / imgs_per_set;
+  // enough blocks to cover the machine ~4x, at least 8 pixel rows per thread
+  long long want = (4LL * num_sms() + nstat - 1) / nstat;
+  long long ppb = (p.pix_per_set + want - 1) / want;
+  const long long min_ppb = (long long)rows * 8;
+  if (ppb < min_ppb) ppb = min_ppb;
+  p.pix_per_block = (int)ppb;
+  grid = dim3((unsigned)((p.pix_per_set + ppb - 1) / ppb), nstat, 1);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+template <int VPL>   // uint4 vectors per lane; C = 8 * (number of vectors), vectors strided by 32 over the warp
+__global__ void ln_kernel(const __half* __restrict__ x, int rows, int C, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, const float* __restrict__ pe, int hw, int F,
+                          __half* __restrict__ out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const int nvec = C / 8;
+  const __half* xr = x + (long long)warp * C;
+  uint4 v[VPL];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      v[i] = *reinterpret_cast<const uint4*>(xr + vi * 8);
+      const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); s += f.x + f.y; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        q += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / C + 1e-5f);
+  const float* per = pe ? pe + (long long)((warp / hw) % F) * C : nullptr;
+  __half* orow = out + (long long)warp * C;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
+      uint4 o;
+      __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = vi * 8 + 2 * j;
+        const float2 f = __half22float2(h[j]);
+        float y0 = (f.x - mean) * rstd * gamma[c] + beta[c];
+        float y1 = (f.y - mean) * rstd * gamma[c + 1] + beta[c + 1];
+        if (per) { y0 += per[c]; y1 += per[c + 1]; }
+        oh[j] = __floats2half2_rn(y0, y1);
+      }
+      *reinterpret_cast<uint4*>(orow + vi * 8) = o;
+    }
+  }
+}
+
+}  // namespace
+
+int groupnorm_stats(cudaStream_t st, const __half* x1, int c1, const __half* x2, int c2, int nimg, int hw,
+                    int imgs_per_set, int groups, float* sums) {
+  GnParams p{};
+  dim3 grid;
+  int threads;
+  if (int e = gn_fill(p, grid, threads, x1, c1, x2, c2, nimg, hw, imgs_per_set, groups)) return e;
+  p.sums = sums;
+  VS_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * groups * (nimg / imgs_per_set), st));
+  gn_stats_kernel<<<grid, threads, groups * 2 * sizeof(float), st>>>(p);
+  VS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int groupnorm_apply(cudaStream_t st, const __half* x1, int c1, const __half* x2, int c2, int nimg, int hw,
+                    int imgs_per_set, int groups, const float* sums, float eps, const float* gamma, const float* beta,
+                    bool silu, __half* out) {
+  GnParams p{};
+  dim3 grid;
+  int threads;
+  if (int e = gn_fill(p, grid, threads, x1, c1, x2, c2, nimg, hw, imgs_per_set, groups)) return e;
+  p.sums = const_cast<float*>(sums);
+  p.gamma = gamma; p.beta = beta; p.eps = eps; p.silu = silu ? 1 : 0; p.out = out;
+  gn_apply_kernel<<<grid, threads, 0, st>>>(p);
+  VS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int layernorm(cudaStream_t st, const __half* x, int rows, int C, const float* gamma, const float* beta, const float* pe,
+              int hw, int F, __half* out) {
+  VS_REQUIRE(C % 8 == 0 && C <= 8 * 32 * 8, "layernorm: unsupported C=%d", C);
+  const int nvec = C / 8, vpl = (nvec + 31) / 32;
+  const int threads = 256, wpb = threads / 32;
+  const int blocks = (rows + wpb - 1) / wpb;
+  if (hw <= 0) hw = 1;
+  if (F <= 0) F = 1;
+  switch (vpl) {
+    case 1: ln_kernel<1><<<blocks, threads, 0, st>>>(x, rows, C, gamma, beta, pe, hw, F, out); break;
+    case 2: ln_kernel<2><<<blocks, threads, 0, st>>>(x, rows, C, gamma, beta, pe, hw, F, out); break;
+    case 3: ln_kernel<3><<<blocks, threads, 0, st>>>(x, rows, C, gamma, beta, pe, hw, F, out); break;
+    case 4: ln_kernel<4><<<blocks, threads, 0, st>>>(x, rows, C, gamma, beta, pe, hw, F, out); break;
+    case 5: ln_kernel<5><<<blocks, threads, 0, st>>>(x, rows, C, gamma, beta, pe, hw, F, out); break;
+    default: ln_kernel<8><<<blocks, threads, 0, st>>>(x, rows, C, gamma, beta, pe, hw, F, out); break;
+  }
+  VS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace vs

@@ -1,0 +1,375 @@
+// Small / pointwise kernels of the denoising step: timestep embedding + tiny linears, conv_in (Cin=4), nearest 2x
+// up-sampling, stride-2 im2col, layout conversion at the API boundary, the fused classifier-free-guidance + DDIM
+// update (reference pipelines/pipeline_videoswap.py:578-587 + diffusers DDIMScheduler.step), the sparse-point
+// adapter splat (models/adapter_model.py:25-47,121-130) and weight re-packing.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vs {
+namespace {
+
+constexpr int TPB = 256;
+inline unsigned blocks_for(size_t n, int per = TPB) { return (unsigned)((n + per - 1) / per); }
+
+// ---------------------------------------------------------------------------------------------- tiny linears
+__global__ void small_linear_kernel(const float* __restrict__ x, int rows, int K, const __half* __restrict__ W,
+                                    const float* __restrict__ bias, int N, int silu_in, int silu_out,
+                                    float* __restrict__ out) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const __half* w = W + (long long)n * K;
+  for (int r0 = 0; r0 < rows; r0 += 8) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int k = lane * 2; k < K; k += 64) {
+      const float2 wv = __half22float2(*reinterpret_cast<const __half2*>(w + k));
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        if (r0 + r < rows) {
+          float a = x[(long long)(r0 + r) * K + k], b = x[(long long)(r0 + r) * K + k + 1];
+          if (silu_in) { a = silu_f(a); b = silu_f(b); }
+          acc[r] += a * wv.x + b * wv.y;
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], o);
+      if (lane == 0 && r0 + r < rows) {
+        float v = acc[r] + (bias ? bias[n] : 0.f);
+        if (silu_out) v = silu_f(v);
+        out[(long long)(r0 + r) * N + n] = v;
+      }
+    }
+  }
+}
+
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, int B, int dim, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int half = dim / 2;
+  if (i >= B * half) return;
+  const int b = i / half, j = i % half;
+  const float freq = expf(-9.210340371976184f * (float)j / (float)half);   // ln(1e4)
+  const float arg = t[b] * freq;
+  out[b * dim + j] = cosf(arg);            // flip_sin_to_cos=True -> cos first
+  out[b * dim + half + j] = sinf(arg);
+}
+
+// ---------------------------------------------------------------------------------------------- conv_in (tiny Cin)
+__global__ void conv_in_kernel(const __half* __restrict__ x, int nimg, int H, int W, int cin, const __half* __restrict__ w,
+                               const float* __restrict__ bias, int cout, __half* __restrict__ out) {
+  extern __shared__ float ws[];   // [9*cin][cout]
+  const int K = 9 * cin;
+  for (int i = threadIdx.x; i < K * cout; i += blockDim.x) {
+    const int co = i % cout, k = i / cout;           // k = tap*cin + ci
+    const int tap = k / cin, ci = k % cin;
+    ws[i] = __half2float(w[((long long)co * cin + ci) * 9 + tap]);   // [co][ci][3][3]
+  }
+  __syncthreads();
+  const int cg = cout / 8;
+  const long long total = (long long)nimg * H * W * cg;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int g = i % cg;
+    const long long pix = i / cg;
+    const int xq = pix % W, yq = (pix / W) % H;
+    const long long img = pix / ((long long)W * H);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bias ? bias[g * 8 + j] : 0.f;
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = yq + tap / 3 - 1, xx = xq + tap % 3 - 1;
+      if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+      const __half* px = x + ((img * H + yy) * W + xx) * cin;
+      for (int ci = 0; ci < cin; ++ci) {
+        const float v = __half2float(px[ci]);
+        const float* wr = ws + (tap * cin + ci) * cout + g * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += v * wr[j];
+      }
+    }
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]);
+    *reinterpret_cast<uint4*>(out + pix * cout + g * 8) = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- data movement
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, int nimg, int H, int W, int CV, uint4* __restrict__ out) {
+  const long long total = (long long)nimg * 4 * H * W * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = i % CV;
+    const long long pix = i / CV;
+    const int xo = pix % (2 * W), yo = (pix / (2 * W)) % (2 * H);
+    const long long img = pix / (4LL * W * H);
+    out[i] = x[((img * H + yo / 2) * W + xo / 2) * CV + cv];
+  }
+}
+
+__global__ void im2col_s2_kernel(const uint4* __restrict__ x, int nimg, int H, int W, int CV, int Ho, int Wo,
+                                 uint4* __restrict__ out) {
+  const long long total = (long long)nimg * Ho * Wo * 9 * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = i % CV;
+    const int tap = (i / CV) % 9;
+    const long long opix = i / (9LL * CV);
+    const int xo = opix % Wo, yo = (opix / Wo) % Ho;
+    const long long img = opix / ((long long)Wo * Ho);
+    const int yy = 2 * yo + tap / 3 - 1, xx = 2 * xo + tap % 3 - 1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = x[((img * H + yy) * W + xx) * CV + cv];
+    out[i] = v;
+  }
+}
+
+__global__ void add_kernel(__half* __restrict__ x, const __half* __restrict__ r, size_t n, float scale) {
+  const size_t nv = n / 8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += (size_t)gridDim.x * blockDim.x) {
+    uint4 a = reinterpret_cast<uint4*>(x)[i];
+    const uint4 b = reinterpret_cast<const uint4*>(r)[i];
+    __half2* ah = reinterpret_cast<__half2*>(&a);
+    const __half2* bh = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 fa = __half22float2(ah[j]), fb = __half22float2(bh[j]);
+      ah[j] = __floats2half2_rn(fa.x + scale * fb.x, fa.y + scale * fb.y);
+    }
+    reinterpret_cast<uint4*>(x)[i] = a;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (size_t i = nv * 8; i < n; ++i) x[i] = __float2half_rn(__half2float(x[i]) + scale * __half2float(r[i]));
+}
+
+template <typename T>
+__global__ void ncfhw_to_nhwc_kernel(const T* __restrict__ src, int B, int C, int F, int H, int W, __half* __restrict__ dst) {
+  const long long total = (long long)B * F * H * W * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = i % C;
+    long long r = i / C;
+    const int x = r % W; r /= W;
+    const int y = r % H; r /= H;
+    const int f = r % F;
+    const int b = r / F;
+    dst[i] = __float2half_rn((float)src[((((long long)b * C + c) * F + f) * H + y) * W + x]);
+  }
+}
+template <typename T>
+__global__ void nhwc_to_ncfhw_kernel(const __half* __restrict__ src, int B, int C, int F, int H, int W, T* __restrict__ dst) {
+  const long long total = (long long)B * F * H * W * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int x = r % W; r /= W;
+    const int y = r % H; r /= H;
+    const int f = r % F; r /= F;
+    const int c = r % C;
+    const int b = r / C;
+    dst[i] = (T)__half2float(src[((((long long)b * F + f) * H + y) * W + x) * C + c]);
+  }
+}
+
+__global__ void nchw_to_nhwc_kernel(const __half* __restrict__ src, int C, int HW, float scale, __half* __restrict__ dst) {
+  __shared__ __half tile[32][33];
+  const long long img = blockIdx.z;
+  const int c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int c = c0 + j, p = p0 + threadIdx.x;
+    if (c < C && p < HW) tile[j][threadIdx.x] = src[(img * C + c) * HW + p];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int p = p0 + j, c = c0 + threadIdx.x;
+    if (c < C && p < HW) dst[(img * HW + p) * C + c] = __float2half_rn(__half2float(tile[threadIdx.x][j]) * scale);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- CFG + DDIM
+template <typename T>
+__global__ void cfg_ddim_kernel(const T* __restrict__ eps2, const T* __restrict__ x, size_t n, int cfg, float g,
+                                float c_x, float c_e, T* __restrict__ out) {
+  // x_prev = sqrt(a_p)/sqrt(a_t) * x + (sqrt(1-a_p) - sqrt(a_p) sqrt(1-a_t)/sqrt(a_t)) * eps   (eta = 0)
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float e = (float)eps2[i];
+    if (cfg) {
+      const float ec = (float)eps2[n + i];
+      e = e + g * (ec - e);
+    }
+    out[i] = (T)(c_x * (float)x[i] + c_e * e);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- adapter splat
+__device__ __forceinline__ float r16(float v, int on) { return on ? __half2float(__float2half_rn(v)) : v; }
+
+__global__ void adapter_splat_kernel(const float* __restrict__ feat, const float* __restrict__ tracks,
+                                     const int* __restrict__ mask, int F, int P, int C, int h, int w, float rate,
+                                     int c16, float scale, __half* __restrict__ maps) {
+  const int CV = C / 8;
+  const long long total = (long long)F * h * w * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = i % CV;
+    const long long cell = i / CV;
+    const int x = cell % w, y = (cell / w) % h, f = cell / ((long long)w * h);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int pt = 0; pt < P; ++pt) {
+      if (mask && !mask[pt]) continue;
+      const float px = r16(tracks[(f * P + pt) * 2], c16), py = r16(tracks[(f * P + pt) * 2 + 1], c16);
+      if (px < 0.f || py < 0.f) continue;
+      const float fx = r16(px / rate, c16), fy = r16(py / rate, c16);
+      int x1 = (int)fx, y1 = (int)fy;
+      const float xf = r16(fx - (float)x1, c16), yf = r16(fy - (float)y1, c16);
+      int x2 = x1 + 1, y2 = y1 + 1;
+      x1 = max(min(x1, w - 1), 0); x2 = max(min(x2, w - 1), 0);
+      y1 = max(min(y1, h - 1), 0); y2 = max(min(y2, h - 1), 0);
+      const float ox = r16(1.f - xf, c16), oy = r16(1.f - yf, c16);
+      float wsum = 0.f;
+      if (y == y1 && x == x1) wsum += r16(ox * oy, c16);
+      if (y == y1 && x == x2) wsum += r16(xf * oy, c16);
+      if (y == y2 && x == x1) wsum += r16(ox * yf, c16);
+      if (y == y2 && x == x2) wsum += r16(xf * yf, c16);
+      if (wsum != 0.f) {
+        const float* fr = feat + (long long)pt * C + cv * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += r16(fr[j], c16) * wsum;
+      }
+    }
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oh[j] = __floats2half2_rn(r16(acc[2 * j], c16) * scale, r16(acc[2 * j + 1], c16) * scale);
+    *reinterpret_cast<uint4*>(maps + cell * C + cv * 8) = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- packing
+__global__ void pack_conv3x3_kernel(const __half* __restrict__ w, int cout, int cin, __half* __restrict__ out) {
+  const long long total = (long long)cout * 9 * cin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = i % cin, tap = (i / cin) % 9;
+    const long long co = i / (9LL * cin);
+    out[i] = w[(co * cin + ci) * 9 + tap];
+  }
+}
+__global__ void pack_geglu_kernel(const __half* __restrict__ w, const __half* __restrict__ b, int hidden, int K,
+                                  int gran, __half* __restrict__ wout, float* __restrict__ bout) {
+  const long long total = (long long)2 * hidden * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = i % K;
+    const long long pr = i / K;                       // packed row
+    const long long tile = pr / (2 * gran);
+    const int within = pr % (2 * gran);
+    const long long srow = within < gran ? tile * gran + within : (long long)hidden + tile * gran + (within - gran);
+    if (w) wout[i] = w[srow * K + k];
+    if (b && k == 0) bout[pr] = __half2float(b[srow]);
+  }
+}
+__global__ void f16_to_f32_kernel(const __half* __restrict__ x, size_t n, float* __restrict__ out) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = __half2float(x[i]);
+}
+
+inline unsigned capped(size_t n) {
+  size_t b = (n + TPB - 1) / TPB;
+  const size_t cap = (size_t)num_sms() * 16;
+  return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+int small_linear(cudaStream_t st, const float* x, int rows, int K, const __half* W, const float* bias, int N, bool silu_in,
+                 bool silu_out, float* out) {
+  VS_REQUIRE(K % 2 == 0, "small_linear: K must be even");
+  small_linear_kernel<<<blocks_for((size_t)N * 32), TPB, 0, st>>>(x, rows, K, W, bias, N, silu_in, silu_out, out);
+  VS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int timestep_embedding(cudaStream_t st, const float* t, int B, int dim, float* out) {
+  timestep_embedding_kernel<<<blocks_for((size_t)B * dim / 2), TPB, 0, st>>>(t, B, dim, out);
+  VS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int conv_in_3x3(cudaStream_t st, const __half* x, int nimg, int H, int W, int cin, const __half* w, const float* bias,
+                int cout, __half* out) {
+  VS_REQUIRE(cout % 8 == 0 && cin <= 8, "conv_in_3x3: needs cout %% 8 == 0 and cin <= 8");
+  const size_t smem = (size_t)9 * cin * cout * sizeof(float);
+  VS_REQUIRE(smem <= 48 * 1024, "conv_in_3x3: weights do not fit shared memory");
+  conv_in_kernel<<<capped((size_t)nimg * H * W * (cout / 8)), TPB, smem, st>>>(x, nimg, H, W, cin, w, bias, cout, out);
+  VS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int upsample_nearest2x(cudaStream_t st, const __half* x, int nimg, int H, int W, int C, __half* out) {
+  VS_REQUIRE(C % 8 == 0, "upsample: C %% 8 != 0");
+  upsample2x_kernel<<<capped((size_t)nimg * 4 * H * W * (C / 8)), TPB, 0, st>>>(
+      reinterpret_cast<const uint4*>(x), nimg, H, W, C / 8, reinterpret_cast<uint4*>(out));
+  VS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int im2col_s2(cudaStream_t st, const __half* x, int nimg, int H, int W, int C, __half* out) {
+  VS_REQUIRE(C % 8 == 0, "im2col: C %% 8 != 0");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  im2col_s2_kernel<<<capped((size_t)nimg * Ho * Wo * 9 * (C / 8)), TPB, 0, st>>>(
+      reinterpret_cast<const uint4*>(x), nimg, H, W, C / 8, Ho, Wo, reinterpret_cast<uint4*>(out));
+  VS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int add_inplace(cudaStream_t st, __half* x, const __half* r, size_t n, float scale) {
+  add_kernel<<<capped(n / 8 + 1), TPB, 0, st>>>(x, r, n, scale);
+  VS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int ncfhw_to_nhwc(cudaStream_t st, const void* src, int src_is_f32, int B, int C, int F, int H, int W, __half* dst) {
+  const size_t n = (size_t)B * C * F * H * W;
+  if (src_is_f32) ncfhw_to_nhwc_kernel<float><<<capped(n), TPB, 0, st>>>((const float*)src, B, C, F, H, W, dst);
+  else ncfhw_to_nhwc_kernel<__half><<<capped(n), TPB, 0, st>>>((const __half*)src, B, C, F, H, W, dst);
+  VS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int nhwc_to_ncfhw(cudaStream_t st, const __half* src, int B, int C, int F, int H, int W, void* dst, int dst_is_f32) {
+  const size_t n = (size_t)B * C * F * H * W;
+  if (dst_is_f32) nhwc_to_ncfhw_kernel<float><<<capped(n), TPB, 0, st>>>(src, B, C, F, H, W, (float*)dst);
+  else nhwc_to_ncfhw_kernel<__half><<<capped(n), TPB, 0, st>>>(src, B, C, F, H, W, (__half*)dst);
+  VS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int nchw_to_nhwc(cudaStream_t st, const __half* src, int n, int C, int H, int W, float scale, __half* dst) {
+  const int HW = H * W;
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, n), block(32, 8);
+  nchw_to_nhwc_kernel<<<grid, block, 0, st>>>(src, C, HW, scale, dst);
+  VS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int cfg_ddim_step(cudaStream_t st, const void* eps2, const void* latents, int is_f32, size_t n, int cfg, float guidance,
+                  float a_t, float a_prev, void* out) {
+  const float c_x = sqrtf(a_prev) / sqrtf(a_t);
+  const float c_e = sqrtf(1.f - a_prev) - sqrtf(a_prev) * sqrtf(1.f - a_t) / sqrtf(a_t);
+  if (is_f32) cfg_ddim_kernel<float><<<capped(n), TPB, 0, st>>>((const float*)eps2, (const float*)latents, n, cfg, guidance, c_x, c_e, (float*)out);
+  else cfg_ddim_kernel<__half><<<capped(n), TPB, 0, st>>>((const __half*)eps2, (const __half*)latents, n, cfg, guidance, c_x, c_e, (__half*)out);
+  VS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int adapter_splat(cudaStream_t st, const float* feat, const float* tracks, const int* point_mask, int F, int P, int C,
+                  int h, int w, float rate, int coord_fp16, float scale, __half* maps) {
+  VS_REQUIRE(C % 8 == 0, "adapter_splat: C %% 8 != 0");
+  adapter_splat_kernel<<<capped((size_t)F * h * w * (C / 8)), TPB, 0, st>>>(feat, tracks, point_mask, F, P, C, h, w, rate,
+                                                                            coord_fp16, scale, maps);
+  VS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int pack_conv3x3(cudaStream_t st, const __half* w, int cout, int cin, __half* out) {
+  pack_conv3x3_kernel<<<capped((size_t)cout * 9 * cin), TPB, 0, st>>>(w, cout, cin, out);
+  VS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int pack_geglu(cudaStream_t st, const __half* w, const __half* b, int hidden, int K, int granule, __half* wout, float* bout) {
+  VS_REQUIRE(hidden % granule == 0, "pack_geglu: hidden %% granule != 0");
+  pack_geglu_kernel<<<capped((size_t)2 * hidden * K), TPB, 0, st>>>(w, b, hidden, K, granule, wout, bout);
+  VS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int f16_to_f32(cudaStream_t st, const __half* x, size_t n, float* out) {
+  f16_to_f32_kernel<<<capped(n), TPB, 0, st>>>(x, n, out);
+  VS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace vs

@@ -1,0 +1,644 @@
+// Host-side executor of the reference's AnimateDiffUNet3DModel.forward (videoswap/models/animatediff_models/unet.py:
+// 328-481 and unet_blocks.py) on top of the sm_100a kernels.  Owns the packed weights and a static activation
+// workspace; activations are NHWC fp16 ([(b f), h*w, C] tokens), so none of the reference's rearrange/permute/concat
+// copies exist.  Weight names are the reference's state_dict keys.
+#include <math.h>
+#include <string.h>
+
+#include <functional>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/videoswap_b200.h"
+#include "common.cuh"
+#include "kernels.h"
+
+using namespace vs;
+
+namespace {
+
+enum LoadKind { LK_COPY_F16, LK_TO_F32, LK_CONV3, LK_GEGLU_W, LK_GEGLU_B, LK_IGNORE };
+
+struct Loader {
+  LoadKind kind;
+  void* dst;
+  int64_t numel;
+  int a, b;   // conv: co, ci; geglu: hidden, K
+};
+
+struct Lin { __half* w = nullptr; float* b = nullptr; int N = 0, K = 0; };
+struct Conv3 { __half* w = nullptr; float* b = nullptr; int co = 0, ci = 0; };
+struct Norm { float* g = nullptr; float* b = nullptr; int C = 0; };
+struct Resnet {
+  Norm n1, n2; Conv3 c1, c2; Lin sc; bool has_sc = false; int cin = 0, cout = 0; int temb_off = 0;
+};
+struct Transformer {
+  int C = 0, layer = 0;
+  Norm norm, ln1, ln2, ln3; Lin proj_in, proj_out, out1, out2, ff2;
+  __half* wqkv = nullptr; __half* wq = nullptr; __half* wkv = nullptr; __half* ff1w = nullptr; float* ff1b = nullptr;
+};
+struct Motion {
+  int C = 0;
+  Norm norm, ln[2], ff_norm; Lin proj_in, proj_out, out[2], ff2;
+  __half* wqkv[2] = {nullptr, nullptr}; __half* ff1w = nullptr; float* ff1b = nullptr;
+};
+struct Layer { Resnet res; bool has_tr = false; Transformer tr; bool has_mo = false; Motion mo; };
+struct Block { std::vector<Layer> layers; bool has_sampler = false; Conv3 sampler; };
+
+struct Act { __half* p; int c; };   // NHWC activation view at the current resolution
+
+}  // namespace
+
+struct vs_unet {
+  vs_unet_config cfg;
+  std::vector<void*> allocs;
+  std::unordered_map<std::string, Loader> loaders;
+  std::vector<std::string> names;
+
+  // parameters
+  __half* conv_in_w = nullptr; float* conv_in_b = nullptr;
+  Lin te1, te2;                         // time_embedding.linear_1/2
+  __half* tproj_w = nullptr; float* tproj_b = nullptr; int tproj_n = 0;   // all resnets' time_emb_proj, stacked
+  Block down[4], up[4];
+  Layer mid0; Resnet mid1;              // mid: resnet0 + transformer, then resnet1
+  Norm norm_out; Conv3 conv_out;
+  float* pe[4] = {nullptr, nullptr, nullptr, nullptr};   // [pe_max_len, C_l] fp32 per level
+
+  // workspace
+  size_t ws_bytes = 0; void* ws = nullptr;
+  int wsB = 0, wsF = 0, wsH = 0, wsW = 0;
+  __half *XIN, *XN, *T, *TN, *QKV, *ATT, *HH, *SC, *P0, *P1, *SCR, *KV, *RES, *OUT;
+  std::vector<__half*> skip;            // 12 skip buffers
+  float *F_T, *F_TE0, *F_TE1, *F_EMB, *F_TPROJ, *F_SUMS;
+
+  // debug taps
+  bool taps_on = false;
+  struct Tap { std::string name; void* p; int n, h, w, c; };
+  std::vector<Tap> taps;
+
+  ~vs_unet() {
+    for (void* p : allocs) cudaFree(p);
+    if (ws) cudaFree(ws);
+    for (auto& t : taps) cudaFree(t.p);
+  }
+
+  template <typename T>
+  T* alloc(size_t n) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) { set_error("cudaMalloc of %zu bytes failed", n * sizeof(T)); return nullptr; }
+    cudaMemset(p, 0, n * sizeof(T));
+    allocs.push_back(p);
+    return reinterpret_cast<T*>(p);
+  }
+  void reg(const std::string& name, LoadKind k, void* dst, int64_t numel, int a = 0, int b = 0) {
+    loaders[name] = Loader{k, dst, numel, a, b};
+    names.push_back(name);
+  }
+  float* f32(const std::string& name, int64_t n) { float* p = alloc<float>(n); reg(name, LK_TO_F32, p, n); return p; }
+  __half* f16(const std::string& name, int64_t n) { __half* p = alloc<__half>(n); reg(name, LK_COPY_F16, p, n); return p; }
+  Norm norm(const std::string& p, int C) { Norm n; n.C = C; n.g = f32(p + ".weight", C); n.b = f32(p + ".bias", C); return n; }
+  Lin lin(const std::string& p, int N, int K, bool bias = true) {
+    Lin l; l.N = N; l.K = K; l.w = f16(p + ".weight", (int64_t)N * K); if (bias) l.b = f32(p + ".bias", N); return l;
+  }
+  Conv3 conv3(const std::string& p, int co, int ci) {
+    Conv3 c; c.co = co; c.ci = ci;
+    const int co_pad = co < 64 ? 64 : co;             // tiny-N convs (conv_out) read a zero-padded weight panel
+    c.w = alloc<__half>((int64_t)co_pad * 9 * ci);
+    reg(p + ".weight", LK_CONV3, c.w, (int64_t)co * ci * 9, co, ci);
+    c.b = f32(p + ".bias", co);
+    return c;
+  }
+};
+
+namespace {
+
+void build_resnet(vs_unet* h, Resnet& r, const std::string& p, int cin, int cout, int temb, int& toff) {
+  r.cin = cin; r.cout = cout;
+  r.n1 = h->norm(p + ".norm1", cin);
+  r.c1 = h->conv3(p + ".conv1", cout, cin);
+  r.temb_off = toff;
+  h->reg(p + ".time_emb_proj.weight", LK_COPY_F16, h->tproj_w + (int64_t)toff * temb, (int64_t)cout * temb);
+  h->reg(p + ".time_emb_proj.bias", LK_TO_F32, h->tproj_b + toff, cout);
+  toff += cout;
+  r.n2 = h->norm(p + ".norm2", cout);
+  r.c2 = h->conv3(p + ".conv2", cout, cout);
+  r.has_sc = cin != cout;
+  if (r.has_sc) r.sc = h->lin(p + ".conv_shortcut", cout, cin);
+}
+
+void build_attn_fused(vs_unet* h, const std::string& p, int C, __half*& wqkv, Lin& out) {
+  wqkv = h->alloc<__half>((int64_t)3 * C * C);
+  h->reg(p + ".to_q.weight", LK_COPY_F16, wqkv, (int64_t)C * C);
+  h->reg(p + ".to_k.weight", LK_COPY_F16, wqkv + (int64_t)C * C, (int64_t)C * C);
+  h->reg(p + ".to_v.weight", LK_COPY_F16, wqkv + (int64_t)2 * C * C, (int64_t)C * C);
+  out = h->lin(p + ".to_out.0", C, C);
+}
+
+void build_ff(vs_unet* h, const std::string& p, int C, __half*& w1, float*& b1, Lin& ff2) {
+  w1 = h->alloc<__half>((int64_t)8 * C * C);
+  b1 = h->alloc<float>(8 * C);
+  h->reg(p + ".net.0.proj.weight", LK_GEGLU_W, w1, (int64_t)8 * C * C, 4 * C, C);
+  h->reg(p + ".net.0.proj.bias", LK_GEGLU_B, b1, 8 * C, 4 * C, 1);
+  ff2 = h->lin(p + ".net.2", C, 4 * C);
+}
+
+void build_transformer(vs_unet* h, Transformer& t, const std::string& p, int C, int ctx, int layer) {
+  t.C = C; t.layer = layer;
+  t.norm = h->norm(p + ".norm", C);
+  t.proj_in = h->lin(p + ".proj_in", C, C);
+  const std::string q = p + ".transformer_blocks.0";
+  build_attn_fused(h, q + ".attn1", C, t.wqkv, t.out1);
+  t.ln1 = h->norm(q + ".norm1", C);
+  t.wq = h->f16(q + ".attn2.to_q.weight", (int64_t)C * C);
+  t.wkv = h->alloc<__half>((int64_t)2 * C * ctx);
+  h->reg(q + ".attn2.to_k.weight", LK_COPY_F16, t.wkv, (int64_t)C * ctx);
+  h->reg(q + ".attn2.to_v.weight", LK_COPY_F16, t.wkv + (int64_t)C * ctx, (int64_t)C * ctx);
+  t.out2 = h->lin(q + ".attn2.to_out.0", C, C);
+  t.ln2 = h->norm(q + ".norm2", C);
+  build_ff(h, q + ".ff", C, t.ff1w, t.ff1b, t.ff2);
+  t.ln3 = h->norm(q + ".norm3", C);
+  t.proj_out = h->lin(p + ".proj_out", C, C);
+}
+
+void build_motion(vs_unet* h, Motion& m, const std::string& p0, int C) {
+  const std::string p = p0 + ".temporal_transformer";
+  m.C = C;
+  m.norm = h->norm(p + ".norm", C);
+  m.proj_in = h->lin(p + ".proj_in", C, C);
+  const std::string q = p + ".transformer_blocks.0";
+  for (int i = 0; i < 2; ++i) {
+    const std::string a = q + ".attention_blocks." + std::to_string(i);
+    build_attn_fused(h, a, C, m.wqkv[i], m.out[i]);
+    h->reg(a + ".processor.pos_encoder.pe", LK_IGNORE, nullptr, 0);   // closed-form table, rebuilt internally
+  }
+  for (int i = 0; i < 2; ++i) m.ln[i] = h->norm(q + ".norms." + std::to_string(i), C);
+  build_ff(h, q + ".ff", C, m.ff1w, m.ff1b, m.ff2);
+  m.ff_norm = h->norm(q + ".ff_norm", C);
+  m.proj_out = h->lin(p + ".proj_out", C, C);
+}
+
+int up_in_channels(const vs_unet_config& c, int i, int j, int* skip) {
+  const int n = 4;
+  int rev[4];
+  for (int k = 0; k < n; ++k) rev[k] = c.block_out_channels[n - 1 - k];
+  const int out_c = rev[i];
+  const int prev = rev[i > 0 ? i - 1 : 0];
+  const int in_c = rev[i + 1 < n ? i + 1 : n - 1];
+  const int nl = c.layers_per_block + 1;
+  *skip = (j == nl - 1) ? in_c : out_c;
+  return (j == 0) ? prev : out_c;
+}
+
+}  // namespace
+
+// =================================================================================================== create
+extern "C" int vs_unet_create(const vs_unet_config* cfg, vs_unet** out) {
+  VS_REQUIRE(cfg && out, "vs_unet_create: null argument");
+  VS_REQUIRE(cfg->layers_per_block >= 1 && cfg->layers_per_block <= 4, "bad layers_per_block");
+  for (int i = 0; i < 4; ++i)
+    VS_REQUIRE(cfg->block_out_channels[i] % 64 == 0 && (cfg->block_out_channels[i] / cfg->num_heads == 40 ||
+               cfg->block_out_channels[i] / cfg->num_heads == 80 || cfg->block_out_channels[i] / cfg->num_heads == 160),
+               "block_out_channels[%d]=%d unsupported (need C %% 64 == 0 and head dim in {40,80,160})", i,
+               cfg->block_out_channels[i]);
+  VS_REQUIRE(cfg->cross_attention_dim % 64 == 0, "cross_attention_dim must be a multiple of 64");
+  vs_unet* h = new vs_unet();
+  h->cfg = *cfg;
+  const int* boc = cfg->block_out_channels;
+  const int temb = boc[0] * 4, ctx = cfg->cross_attention_dim, lpb = cfg->layers_per_block;
+  h->conv_in_w = h->f16("conv_in.weight", (int64_t)boc[0] * cfg->in_channels * 9);
+  h->conv_in_b = h->f32("conv_in.bias", boc[0]);
+  h->te1 = h->lin("time_embedding.linear_1", temb, boc[0]);
+  h->te2 = h->lin("time_embedding.linear_2", temb, temb);
+  // total stacked time_emb_proj rows
+  int tn = 0;
+  {
+    int cout = boc[0];
+    for (int i = 0; i < 4; ++i) { cout = boc[i]; tn += lpb * cout; }
+    tn += 2 * boc[3];
+    for (int i = 0; i < 4; ++i) tn += (lpb + 1) * boc[3 - i];
+  }
+  h->tproj_n = tn;
+  h->tproj_w = h->alloc<__half>((int64_t)tn * temb);
+  h->tproj_b = h->alloc<float>(tn);
+  int toff = 0, layer = 0;
+  int cout = boc[0];
+  for (int i = 0; i < 4; ++i) {
+    const int cin = cout;
+    cout = boc[i];
+    const std::string p = "down_blocks." + std::to_string(i);
+    Block& b = h->down[i];
+    b.layers.resize(lpb);
+    for (int j = 0; j < lpb; ++j) {
+      Layer& L = b.layers[j];
+      build_resnet(h, L.res, p + ".resnets." + std::to_string(j), j == 0 ? cin : cout, cout, temb, toff);
+      if (i < 3) { L.has_tr = true; build_transformer(h, L.tr, p + ".attentions." + std::to_string(j), cout, ctx, layer++); }
+      if (cfg->use_motion_module && cfg->motion_down[i]) { L.has_mo = true; build_motion(h, L.mo, p + ".motion_modules." + std::to_string(j), cout); }
+    }
+    if (i < 3) { b.has_sampler = true; b.sampler = h->conv3(p + ".downsamplers.0.conv", cout, cout); }
+  }
+  build_resnet(h, h->mid0.res, "mid_block.resnets.0", boc[3], boc[3], temb, toff);
+  h->mid0.has_tr = true;
+  build_transformer(h, h->mid0.tr, "mid_block.attentions.0", boc[3], ctx, layer++);
+  if (cfg->use_motion_module && cfg->motion_mid) { h->mid0.has_mo = true; build_motion(h, h->mid0.mo, "mid_block.motion_modules.0", boc[3]); }
+  build_resnet(h, h->mid1, "mid_block.resnets.1", boc[3], boc[3], temb, toff);
+  for (int i = 0; i < 4; ++i) {
+    const std::string p = "up_blocks." + std::to_string(i);
+    Block& b = h->up[i];
+    const int oc = boc[3 - i];
+    b.layers.resize(lpb + 1);
+    for (int j = 0; j <= lpb; ++j) {
+      Layer& L = b.layers[j];
+      int skipc;
+      const int run = up_in_channels(*cfg, i, j, &skipc);
+      build_resnet(h, L.res, p + ".resnets." + std::to_string(j), run + skipc, oc, temb, toff);
+      if (i > 0) { L.has_tr = true; build_transformer(h, L.tr, p + ".attentions." + std::to_string(j), oc, ctx, layer++); }
+      if (cfg->use_motion_module && cfg->motion_up[i]) { L.has_mo = true; build_motion(h, L.mo, p + ".motion_modules." + std::to_string(j), oc); }
+    }
+    if (i < 3) { b.has_sampler = true; b.sampler = h->conv3(p + ".upsamplers.0.conv", oc, oc); }
+  }
+  h->norm_out = h->norm("conv_norm_out", boc[0]);
+  h->conv_out = h->conv3("conv_out", cfg->out_channels, boc[0]);
+  VS_REQUIRE(toff == tn, "internal: time_emb_proj stacking mismatch (%d vs %d)", toff, tn);
+  // temporal positional-encoding tables (closed form of motion_module.py:242-251)
+  for (int l = 0; l < 4; ++l) {
+    const int C = boc[l], L = cfg->pe_max_len;
+    std::vector<float> t((size_t)L * C);
+    for (int pos = 0; pos < L; ++pos)
+      for (int i2 = 0; i2 < C; i2 += 2) {
+        const float div = expf((float)i2 * (-logf(10000.0f) / (float)C));
+        t[(size_t)pos * C + i2] = sinf((float)pos * div);
+        if (i2 + 1 < C) t[(size_t)pos * C + i2 + 1] = cosf((float)pos * div);
+      }
+    h->pe[l] = h->alloc<float>((size_t)L * C);
+    if (!h->pe[l]) { delete h; return 1; }
+    cudaMemcpy(h->pe[l], t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice);
+  }
+  for (void* p : h->allocs) if (!p) { delete h; return 1; }
+  VS_CHECK_CUDA(cudaGetLastError());
+  *out = h;
+  return 0;
+}
+
+extern "C" void vs_unet_destroy(vs_unet* h) { delete h; }
+extern "C" int vs_unet_num_params(const vs_unet* h) { return (int)h->names.size(); }
+extern "C" const char* vs_unet_param_name(const vs_unet* h, int i) { return h->names[i].c_str(); }
+extern "C" size_t vs_unet_workspace_bytes(const vs_unet* h) { return h->ws_bytes; }
+
+extern "C" int vs_unet_load_weights(vs_unet* h, void* stream, int n, const char* const* names, const void* const* ptrs,
+                                    const int64_t* numels) {
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int i = 0; i < n; ++i) {
+    auto it = h->loaders.find(names[i]);
+    VS_REQUIRE(it != h->loaders.end(), "vs_unet_load_weights: unknown parameter '%s'", names[i]);
+    const Loader& L = it->second;
+    if (L.kind == LK_IGNORE) continue;
+    VS_REQUIRE(numels[i] == L.numel, "vs_unet_load_weights: '%s' has %lld elements, expected %lld", names[i],
+               (long long)numels[i], (long long)L.numel);
+    const __half* src = (const __half*)ptrs[i];
+    int e = 0;
+    switch (L.kind) {
+      case LK_COPY_F16:
+        VS_CHECK_CUDA(cudaMemcpyAsync(L.dst, src, (size_t)L.numel * 2, cudaMemcpyDeviceToDevice, st));
+        break;
+      case LK_TO_F32: e = f16_to_f32(st, src, (size_t)L.numel, (float*)L.dst); break;
+      case LK_CONV3: e = pack_conv3x3(st, src, L.a, L.b, (__half*)L.dst); break;
+      case LK_GEGLU_W: e = pack_geglu(st, src, nullptr, L.a, L.b, kGegluGranule, (__half*)L.dst, nullptr); break;
+      case LK_GEGLU_B: e = pack_geglu(st, nullptr, src, L.a, 1, kGegluGranule, nullptr, (float*)L.dst); break;
+      default: break;
+    }
+    if (e) return e;
+  }
+  return 0;
+}
+
+// =================================================================================================== forward
+namespace {
+
+struct Ctx {
+  vs_unet* h; cudaStream_t st;
+  int B, F, NI, H, W;      // W/H are the CURRENT resolution during the walk
+  const __half* ehs; int ehs_tokens, ehs_layers;
+};
+
+#define RUN(expr) do { if (int _e = (expr)) return _e; } while (0)
+
+int tap(Ctx& c, const std::string& name, const __half* p, int C) {
+  vs_unet* h = c.h;
+  if (!h->taps_on) return 0;
+  const size_t bytes = (size_t)c.NI * c.H * c.W * C * 2;
+  void* d = nullptr;
+  VS_CHECK_CUDA(cudaMalloc(&d, bytes));
+  VS_CHECK_CUDA(cudaMemcpyAsync(d, p, bytes, cudaMemcpyDeviceToDevice, c.st));
+  h->taps.push_back({name, d, c.NI, c.H, c.W, C});
+  return 0;
+}
+
+int linear(Ctx& c, const __half* A, int M, const Lin& l, const __half* residual, __half* out) {
+  GemmArgs g;
+  g.A = A; g.K1 = l.K; g.lda1 = l.K; g.Bw = l.w; g.M = M; g.N = l.N; g.bias = l.b;
+  g.residual = residual; g.ldr = l.N; g.out = out; g.ldc = l.N;
+  return gemm_tc(c.st, g);
+}
+
+int conv(Ctx& c, const __half* x, int C1, const Conv3& w, const float* rowvec, const __half* residual, __half* out) {
+  GemmArgs g;
+  g.A = x; g.K1 = C1; g.lda1 = C1; g.Bw = w.w; g.taps = 9; g.nimg = c.NI; g.H = c.H; g.W = c.W;
+  g.M = c.NI * c.H * c.W; g.N = w.co; g.bias = w.b; g.rowvec = rowvec; g.ldrv = c.h->tproj_n; g.pix_per_batch = c.F * c.H * c.W;
+  g.residual = residual; g.ldr = w.co; g.out = out; g.ldc = w.co;
+  return gemm_tc(c.st, g);
+}
+
+int resnet(Ctx& c, const Resnet& r, const __half* in1, int C1, const __half* in2, int C2, __half* out) {
+  vs_unet* h = c.h;
+  const int hw = c.H * c.W, G = h->cfg.norm_num_groups;
+  const float eps = h->cfg.norm_eps;
+  VS_REQUIRE(C1 + C2 == r.cin, "internal: resnet input channels %d+%d != %d", C1, C2, r.cin);
+  RUN(groupnorm_stats(c.st, in1, C1, in2, C2, c.NI, hw, c.F, G, h->F_SUMS));
+  RUN(groupnorm_apply(c.st, in1, C1, in2, C2, c.NI, hw, c.F, G, h->F_SUMS, eps, r.n1.g, r.n1.b, true, h->XN));
+  RUN(conv(c, h->XN, r.cin, r.c1, h->F_TPROJ + r.temb_off, nullptr, h->T));
+  RUN(groupnorm_stats(c.st, h->T, r.cout, nullptr, 0, c.NI, hw, c.F, G, h->F_SUMS));
+  RUN(groupnorm_apply(c.st, h->T, r.cout, nullptr, 0, c.NI, hw, c.F, G, h->F_SUMS, eps, r.n2.g, r.n2.b, true, h->XN));
+  const __half* residual = in1;
+  if (r.has_sc) {
+    GemmArgs g;
+    g.A = in1; g.K1 = C1; g.lda1 = C1; g.A2 = in2; g.K2 = C2; g.lda2 = C2; g.Bw = r.sc.w; g.M = c.NI * hw; g.N = r.cout;
+    g.bias = r.sc.b; g.out = h->SC; g.ldc = r.cout;
+    RUN(gemm_tc(c.st, g));
+    residual = h->SC;
+  } else {
+    VS_REQUIRE(in2 == nullptr, "internal: concat input without shortcut conv");
+  }
+  RUN(conv(c, h->XN, r.cout, r.c2, nullptr, residual, out));
+  return 0;
+}
+
+int geglu_ff(Ctx& c, const __half* tn, int M, int C, const __half* w1, const float* b1, const Lin& ff2, __half* t) {
+  vs_unet* h = c.h;
+  GemmArgs g;
+  g.A = tn; g.K1 = C; g.lda1 = C; g.Bw = w1; g.M = M; g.N = 8 * C; g.bias = b1; g.out = h->HH; g.ldc = 4 * C; g.mode = EPI_GEGLU;
+  RUN(gemm_tc(c.st, g));
+  return linear(c, h->HH, M, ff2, t, t);
+}
+
+int transformer(Ctx& c, const Transformer& t, __half* x) {
+  vs_unet* h = c.h;
+  const int hw = c.H * c.W, C = t.C, M = c.NI * hw, heads = h->cfg.num_heads, d = C / heads;
+  RUN(groupnorm_stats(c.st, x, C, nullptr, 0, c.NI, hw, 1, h->cfg.norm_num_groups, h->F_SUMS));
+  RUN(groupnorm_apply(c.st, x, C, nullptr, 0, c.NI, hw, 1, h->cfg.norm_num_groups, h->F_SUMS, 1e-6f, t.norm.g, t.norm.b, false, h->XN));
+  RUN(linear(c, h->XN, M, t.proj_in, nullptr, h->T));
+  // self-attention
+  RUN(layernorm(c.st, h->T, M, C, t.ln1.g, t.ln1.b, nullptr, 1, 1, h->TN));
+  { GemmArgs g; g.A = h->TN; g.K1 = C; g.lda1 = C; g.Bw = t.wqkv; g.M = M; g.N = 3 * C; g.out = h->QKV; g.ldc = 3 * C; RUN(gemm_tc(c.st, g)); }
+  RUN(attention(c.st, h->QKV, 3 * C, h->QKV + C, 3 * C, h->QKV + 2 * C, 3 * C, h->ATT, C, c.NI, hw, hw, heads, d,
+                (long long)hw * 3 * C, (long long)hw * 3 * C, (long long)hw * C, 1));
+  RUN(linear(c, h->ATT, M, t.out1, h->T, h->T));
+  // cross-attention to the (ED-LoRA layer-selected) text embeddings; K/V were projected once per (batch, layer)
+  RUN(layernorm(c.st, h->T, M, C, t.ln2.g, t.ln2.b, nullptr, 1, 1, h->TN));
+  { GemmArgs g; g.A = h->TN; g.K1 = C; g.lda1 = C; g.Bw = t.wq; g.M = M; g.N = C; g.out = h->QKV; g.ldc = C; RUN(gemm_tc(c.st, g)); }
+  {
+    const int nk = c.ehs_tokens;
+    const int ctx = h->cfg.cross_attention_dim;
+    const int L = c.ehs_layers > 0 ? c.ehs_layers : 1;
+    const int li = c.ehs_layers > 0 ? t.layer : 0;
+    VS_REQUIRE(li < L, "ED-LoRA embeddings have %d layers but layer %d was requested", L, li);
+    for (int b = 0; b < c.B; ++b) {
+      GemmArgs g;
+      g.A = c.ehs + ((long long)(b * L + li) * nk) * ctx; g.K1 = ctx; g.lda1 = ctx; g.Bw = t.wkv; g.M = nk; g.N = 2 * C;
+      g.out = h->KV + (long long)b * nk * 2 * C; g.ldc = 2 * C;
+      RUN(gemm_tc(c.st, g));
+    }
+    RUN(attention(c.st, h->QKV, C, h->KV, 2 * C, h->KV + C, 2 * C, h->ATT, C, c.NI, hw, nk, heads, d, (long long)hw * C,
+                  (long long)nk * 2 * C, (long long)hw * C, c.F));
+  }
+  RUN(linear(c, h->ATT, M, t.out2, h->T, h->T));
+  // feed-forward
+  RUN(layernorm(c.st, h->T, M, C, t.ln3.g, t.ln3.b, nullptr, 1, 1, h->TN));
+  RUN(geglu_ff(c, h->TN, M, C, t.ff1w, t.ff1b, t.ff2, h->T));
+  RUN(linear(c, h->T, M, t.proj_out, x, x));
+  return 0;
+}
+
+int motion(Ctx& c, const Motion& m, int level, __half* x) {
+  vs_unet* h = c.h;
+  const int hw = c.H * c.W, C = m.C, M = c.NI * hw;
+  VS_REQUIRE(c.F <= h->cfg.pe_max_len, "video_length %d exceeds temporal_position_encoding_max_len %d", c.F, h->cfg.pe_max_len);
+  RUN(groupnorm_stats(c.st, x, C, nullptr, 0, c.NI, hw, 1, 32, h->F_SUMS));
+  RUN(groupnorm_apply(c.st, x, C, nullptr, 0, c.NI, hw, 1, 32, h->F_SUMS, 1e-6f, m.norm.g, m.norm.b, false, h->XN));
+  RUN(linear(c, h->XN, M, m.proj_in, nullptr, h->T));
+  for (int i = 0; i < 2; ++i) {
+    RUN(layernorm(c.st, h->T, M, C, m.ln[i].g, m.ln[i].b, h->pe[level], hw, c.F, h->TN));
+    { GemmArgs g; g.A = h->TN; g.K1 = C; g.lda1 = C; g.Bw = m.wqkv[i]; g.M = M; g.N = 3 * C; g.out = h->QKV; g.ldc = 3 * C; RUN(gemm_tc(c.st, g)); }
+    RUN(temporal_attention(c.st, h->QKV, h->ATT, c.B, c.F, hw, C, h->cfg.motion_num_heads));
+    RUN(linear(c, h->ATT, M, m.out[i], h->T, h->T));
+  }
+  RUN(layernorm(c.st, h->T, M, C, m.ff_norm.g, m.ff_norm.b, nullptr, 1, 1, h->TN));
+  RUN(geglu_ff(c, h->TN, M, C, m.ff1w, m.ff1b, m.ff2, h->T));
+  RUN(linear(c, h->T, M, m.proj_out, x, x));
+  return 0;
+}
+
+size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+int ensure_workspace(vs_unet* h, int B, int F, int H, int W) {
+  if (h->ws && h->wsB == B && h->wsF == F && h->wsH == H && h->wsW == W) return 0;
+  if (h->ws) { cudaFree(h->ws); h->ws = nullptr; }
+  const int* boc = h->cfg.block_out_channels;
+  const size_t NI = (size_t)B * F;
+  // per-level pixel counts
+  size_t hw[4]; int hh = H, ww = W;
+  for (int l = 0; l < 4; ++l) { hw[l] = (size_t)hh * ww; hh = (hh - 1) / 2 + 1; ww = (ww - 1) / 2 + 1; }
+  size_t maxC = 0, maxCat = 0;
+  for (int l = 0; l < 4; ++l) {
+    maxC = std::max(maxC, NI * hw[l] * boc[l]);
+    maxCat = std::max(maxCat, NI * hw[l] * (size_t)(boc[l] + boc[std::min(l + 1, 3)]) );
+    maxCat = std::max(maxCat, NI * hw[l] * (size_t)(2 * boc[l]));
+  }
+  std::vector<std::pair<__half**, size_t>> req;
+  auto want = [&](__half** p, size_t elems) { req.push_back({p, elems}); };
+  want(&h->XIN, NI * hw[0] * 8);
+  want(&h->XN, maxCat);
+  want(&h->T, maxC); want(&h->TN, maxC); want(&h->QKV, 3 * maxC); want(&h->ATT, maxC); want(&h->HH, 4 * maxC);
+  want(&h->SC, maxC); want(&h->P0, maxC); want(&h->P1, maxC);
+  want(&h->SCR, std::max(NI * hw[1] * 9 * boc[0], 4 * maxC));     // im2col (stride-2) / nearest-upsample scratch
+  want(&h->KV, (size_t)B * 128 * 2 * boc[3]);
+  want(&h->RES, maxC);
+  want(&h->OUT, NI * hw[0] * 8);
+  // skips: conv_in, then per down block lpb layers (+ down-sampler output)
+  h->skip.assign(0, nullptr);
+  std::vector<size_t> skip_elems;
+  skip_elems.push_back(NI * hw[0] * boc[0]);
+  for (int i = 0; i < 4; ++i) {
+    for (int j = 0; j < h->cfg.layers_per_block; ++j) skip_elems.push_back(NI * hw[i] * boc[i]);
+    if (i < 3) skip_elems.push_back(NI * hw[i + 1] * boc[i]);
+  }
+  h->skip.resize(skip_elems.size());
+  for (size_t i = 0; i < skip_elems.size(); ++i) want(&h->skip[i], skip_elems[i]);
+  size_t total = 0;
+  for (auto& r : req) total += align_up(r.second * 2);
+  const int temb = boc[0] * 4;
+  const size_t fl = align_up(4 * 64) + align_up((size_t)B * boc[0] * 4) + 2 * align_up((size_t)B * temb * 4) +
+                    align_up((size_t)B * h->tproj_n * 4) + align_up((size_t)NI * 64 * 2 * 4);
+  total += fl;
+  VS_CHECK_CUDA(cudaMalloc(&h->ws, total));
+  h->ws_bytes = total;
+  char* p = (char*)h->ws;
+  for (auto& r : req) { *r.first = (__half*)p; p += align_up(r.second * 2); }
+  h->F_T = (float*)p; p += align_up(4 * 64);
+  h->F_TE0 = (float*)p; p += align_up((size_t)B * boc[0] * 4);
+  h->F_TE1 = (float*)p; p += align_up((size_t)B * temb * 4);
+  h->F_EMB = (float*)p; p += align_up((size_t)B * temb * 4);
+  h->F_TPROJ = (float*)p; p += align_up((size_t)B * h->tproj_n * 4);
+  h->F_SUMS = (float*)p;
+  h->wsB = B; h->wsF = F; h->wsH = H; h->wsW = W;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int vs_unet_enable_taps(vs_unet* h, int enable) {
+  for (auto& t : h->taps) cudaFree(t.p);
+  h->taps.clear();
+  h->taps_on = enable != 0;
+  return 0;
+}
+extern "C" int vs_unet_num_taps(const vs_unet* h) { return (int)h->taps.size(); }
+extern "C" int vs_unet_get_tap(const vs_unet* h, int i, const char** name, const void** p, int* n, int* hh, int* ww, int* c) {
+  VS_REQUIRE(i >= 0 && i < (int)h->taps.size(), "tap index out of range");
+  const auto& t = h->taps[i];
+  *name = t.name.c_str(); *p = t.p; *n = t.n; *hh = t.h; *ww = t.w; *c = t.c;
+  return 0;
+}
+
+extern "C" int vs_unet_forward(vs_unet* h, void* stream, const void* d_sample, int io_f32, int B, int F, int H, int W,
+                               const float* d_timesteps, const void* d_ehs, int ehs_tokens, int ehs_layers,
+                               const void* const* d_residuals, int residuals_nhwc, float residual_scale, void* d_out) {
+  VS_REQUIRE(h && d_sample && d_timesteps && d_ehs && d_out, "vs_unet_forward: null argument");
+  VS_REQUIRE(B >= 1 && F >= 1 && H >= 1 && W >= 1, "vs_unet_forward: bad shape");
+  VS_REQUIRE(ehs_tokens >= 1 && ehs_tokens <= 128, "vs_unet_forward: ehs_tokens out of range");
+  VS_REQUIRE(h->cfg.in_channels <= 8 && h->cfg.out_channels <= 8, "in/out channels > 8 unsupported");
+  cudaStream_t st = (cudaStream_t)stream;
+  RUN(ensure_workspace(h, B, F, H, W));
+  if (h->taps_on) { for (auto& t : h->taps) cudaFree(t.p); h->taps.clear(); }
+  const vs_unet_config& cf = h->cfg;
+  const int* boc = cf.block_out_channels;
+  const int temb = boc[0] * 4, lpb = cf.layers_per_block;
+  Ctx c{h, st, B, F, B * F, H, W, (const __half*)d_ehs, ehs_tokens, ehs_layers};
+
+  // ---- time embedding (unet.py:376-397): Timesteps -> Linear -> SiLU -> Linear; then every resnet's projection of
+  //      SiLU(emb) in one stacked tiny-M linear (resnet.py:171-172)
+  RUN(timestep_embedding(st, d_timesteps, B, boc[0], h->F_TE0));
+  RUN(small_linear(st, h->F_TE0, B, boc[0], h->te1.w, h->te1.b, temb, false, true, h->F_TE1));
+  RUN(small_linear(st, h->F_TE1, B, temb, h->te2.w, h->te2.b, temb, false, false, h->F_EMB));
+  RUN(small_linear(st, h->F_EMB, B, temb, h->tproj_w, h->tproj_b, h->tproj_n, true, false, h->F_TPROJ));
+
+  // ---- conv_in
+  RUN(ncfhw_to_nhwc(st, d_sample, io_f32, B, cf.in_channels, F, H, W, h->XIN));
+  int si = 0;
+  RUN(conv_in_3x3(st, h->XIN, c.NI, H, W, cf.in_channels, h->conv_in_w, h->conv_in_b, boc[0], h->skip[si]));
+  RUN(tap(c, "conv_in", h->skip[si], boc[0]));
+  const __half* cur = h->skip[si];
+  int curC = boc[0];
+  std::vector<std::pair<const __half*, int>> skips;
+  skips.push_back({cur, curC});
+  ++si;
+
+  // ---- down path
+  for (int i = 0; i < 4; ++i) {
+    const Block& blk = h->down[i];
+    const __half* res_l = nullptr;
+    if (d_residuals && d_residuals[i]) {
+      if (residuals_nhwc) res_l = (const __half*)d_residuals[i];
+      else {
+        // all four levels share RES sequentially: convert right before use
+        res_l = h->RES;
+      }
+    }
+    for (int j = 0; j < lpb; ++j) {
+      const Layer& L = blk.layers[j];
+      __half* out = h->skip[si];
+      RUN(resnet(c, L.res, cur, curC, nullptr, 0, out));
+      curC = L.res.cout;
+      if (L.has_tr) RUN(transformer(c, L.tr, out));
+      if (L.has_mo) RUN(motion(c, L.mo, i, out));
+      if (i < 3 && j == lpb - 1 && res_l) {
+        const size_t n = (size_t)c.NI * c.H * c.W * curC;
+        if (!residuals_nhwc) RUN(nchw_to_nhwc(st, (const __half*)d_residuals[i], c.NI, curC, c.H, c.W, residual_scale, h->RES));
+        RUN(add_inplace(st, out, res_l, n, residuals_nhwc ? residual_scale : 1.f));
+      }
+      RUN(tap(c, "down_blocks." + std::to_string(i) + "." + std::to_string(j), out, curC));
+      cur = out;
+      skips.push_back({cur, curC});
+      ++si;
+    }
+    if (blk.has_sampler) {
+      // Downsample3D: 3x3 stride-2 pad-1 conv (resnet.py:72-95) = stride-2 im2col + GEMM
+      const int Ho = (c.H - 1) / 2 + 1, Wo = (c.W - 1) / 2 + 1;
+      RUN(im2col_s2(st, cur, c.NI, c.H, c.W, curC, h->SCR));
+      GemmArgs g;
+      g.A = h->SCR; g.K1 = 9 * curC; g.lda1 = 9 * curC; g.Bw = blk.sampler.w; g.M = c.NI * Ho * Wo; g.N = blk.sampler.co;
+      g.bias = blk.sampler.b; g.out = h->skip[si]; g.ldc = blk.sampler.co;
+      RUN(gemm_tc(st, g));
+      c.H = Ho; c.W = Wo;
+      cur = h->skip[si];
+      skips.push_back({cur, curC});
+      ++si;
+    }
+    if (i == 3 && res_l) {
+      // DownBlock3D: residual added to the running sample only, the skip stays untouched (unet.py:432-438)
+      const size_t n = (size_t)c.NI * c.H * c.W * curC;
+      if (!residuals_nhwc) RUN(nchw_to_nhwc(st, (const __half*)d_residuals[i], c.NI, curC, c.H, c.W, residual_scale, h->RES));
+      VS_CHECK_CUDA(cudaMemcpyAsync(h->P0, cur, n * 2, cudaMemcpyDeviceToDevice, st));
+      RUN(add_inplace(st, h->P0, res_l, n, residuals_nhwc ? residual_scale : 1.f));
+      cur = h->P0;
+    }
+  }
+  // ---- mid
+  {
+    __half* o = (cur == h->P0) ? h->P1 : h->P0;
+    RUN(resnet(c, h->mid0.res, cur, curC, nullptr, 0, o));
+    RUN(transformer(c, h->mid0.tr, o));
+    if (h->mid0.has_mo) RUN(motion(c, h->mid0.mo, 3, o));
+    __half* o2 = (o == h->P0) ? h->P1 : h->P0;
+    RUN(resnet(c, h->mid1, o, curC, nullptr, 0, o2));
+    RUN(tap(c, "mid_block", o2, curC));
+    cur = o2;
+  }
+  // ---- up path
+  for (int i = 0; i < 4; ++i) {
+    const Block& blk = h->up[i];
+    for (int j = 0; j <= lpb; ++j) {
+      const Layer& L = blk.layers[j];
+      const auto sk = skips.back();
+      skips.pop_back();
+      __half* o = (cur == h->P0) ? h->P1 : h->P0;
+      RUN(resnet(c, L.res, cur, curC, sk.first, sk.second, o));
+      curC = L.res.cout;
+      if (L.has_tr) RUN(transformer(c, L.tr, o));
+      if (L.has_mo) RUN(motion(c, L.mo, 3 - i, o));
+      RUN(tap(c, "up_blocks." + std::to_string(i) + "." + std::to_string(j), o, curC));
+      cur = o;
+    }
+    if (blk.has_sampler) {
+      // Upsample3D: nearest [1,2,2] then 3x3 conv (resnet.py:54,67)
+      RUN(upsample_nearest2x(st, cur, c.NI, c.H, c.W, curC, h->SCR));
+      c.H *= 2; c.W *= 2;
+      __half* o = (cur == h->P0) ? h->P1 : h->P0;
+      RUN(conv(c, h->SCR, curC, blk.sampler, nullptr, nullptr, o));
+      cur = o;
+    }
+  }
+  VS_REQUIRE(c.H == H && c.W == W, "input H/W (%d,%d) must be multiples of 8 (the reference's forward_upsample_size path is not implemented)", H, W);
+  // ---- out: GroupNorm(5-D) + SiLU + conv_out
+  RUN(groupnorm_stats(st, cur, curC, nullptr, 0, c.NI, H * W, F, cf.norm_num_groups, h->F_SUMS));
+  RUN(groupnorm_apply(st, cur, curC, nullptr, 0, c.NI, H * W, F, cf.norm_num_groups, h->F_SUMS, cf.norm_eps, h->norm_out.g, h->norm_out.b, true, h->XN));
+  {
+    GemmArgs g;
+    g.A = h->XN; g.K1 = curC; g.lda1 = curC; g.Bw = h->conv_out.w; g.taps = 9; g.nimg = c.NI; g.H = H; g.W = W;
+    g.M = c.NI * H * W; g.N = cf.out_channels; g.bias = h->conv_out.b; g.out = h->OUT; g.ldc = cf.out_channels;
+    RUN(gemm_tc(st, g));
+  }
+  RUN(tap(c, "conv_out", h->OUT, cf.out_channels));
+  RUN(nhwc_to_ncfhw(st, h->OUT, B, cf.out_channels, F, H, W, d_out, io_f32));
+  return 0;
+}

@@ -1,0 +1,176 @@
+"""Thin torch-tensor wrappers over the per-kernel C-ABI entry points (torch is only used for device memory and the
+current stream).  All activations are NHWC fp16 CUDA tensors.  Used by the parity tests and the host-side model."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+
+GEGLU_GRANULE = 80
+EPI_LINEAR, EPI_GEGLU = 0, 1
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _chk16(*ts):
+    for t in ts:
+        if t is not None:
+            assert t.is_cuda and t.dtype == torch.float16 and t.is_contiguous(), "expected contiguous fp16 CUDA tensor"
+
+
+def _chk32(*ts):
+    for t in ts:
+        if t is not None:
+            assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), "expected contiguous fp32 CUDA tensor"
+
+
+def gemm(A, W, bias=None, residual=None, A2=None, rowvec=None, pix_per_batch=1, mode=EPI_LINEAR, force_bn=0):
+    """out[M, N] = [A | A2] @ W^T (+bias +rowvec[row // pix_per_batch] +residual); GEGLU mode expects packed W/bias."""
+    _chk16(A, W, residual, A2)
+    _chk32(bias, rowvec)
+    M, K1 = A.shape
+    K2 = 0 if A2 is None else A2.shape[1]
+    N = W.shape[0]
+    assert W.shape[1] == K1 + K2
+    out = torch.empty((M, N // 2 if mode == EPI_GEGLU else N), dtype=torch.float16, device=A.device)
+    _lib.call("vs_gemm", _stream(), _p(A), K1, _p(A2), K2, _p(W), M, N, _p(bias), _p(rowvec), pix_per_batch,
+              _p(residual), _p(out), mode, force_bn)
+    return out
+
+
+def pack_conv3x3(w):
+    """[Co, Ci, 3, 3] fp16 -> [Co, 9*Ci] tap-major."""
+    _chk16(w)
+    co, ci = w.shape[:2]
+    out = torch.empty((co, 9 * ci), dtype=torch.float16, device=w.device)
+    _lib.call("vs_pack_conv3x3", _stream(), _p(w), co, ci, _p(out))
+    return out
+
+
+def pack_geglu(w, b):
+    """FeedForward.net.0.proj [8C, C] / [8C] -> value/gate interleaved in 80-row granules (+ fp32 bias)."""
+    _chk16(w, b)
+    hidden, K = w.shape[0] // 2, w.shape[1]
+    wout = torch.empty_like(w)
+    bout = torch.empty((2 * hidden,), dtype=torch.float32, device=w.device)
+    _lib.call("vs_pack_geglu", _stream(), _p(w), _p(b), hidden, K, _p(wout), _p(bout))
+    return wout, bout
+
+
+def conv3x3(x, w_packed, bias=None, x2=None, rowvec=None, imgs_per_batch=1, residual=None):
+    """x: [N, H, W, C1] (+x2 [N, H, W, C2] channel concat), w_packed [Co, 9*(C1+C2)] -> [N, H, W, Co]."""
+    _chk16(x, w_packed, x2, residual)
+    _chk32(bias, rowvec)
+    n, H, W, C1 = x.shape
+    C2 = 0 if x2 is None else x2.shape[3]
+    co = w_packed.shape[0]
+    out = torch.empty((n, H, W, co), dtype=torch.float16, device=x.device)
+    _lib.call("vs_conv3x3", _stream(), _p(x), C1, _p(x2), C2, _p(w_packed), n, H, W, co, _p(bias), _p(rowvec),
+              imgs_per_batch, _p(residual), _p(out))
+    return out
+
+
+def conv3x3_s2(x, w_packed, bias=None):
+    _chk16(x, w_packed)
+    n, H, W, Ci = x.shape
+    co = w_packed.shape[0]
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    scratch = torch.empty((n * Ho * Wo, 9 * Ci), dtype=torch.float16, device=x.device)
+    out = torch.empty((n, Ho, Wo, co), dtype=torch.float16, device=x.device)
+    _lib.call("vs_conv3x3_s2", _stream(), _p(x), n, H, W, Ci, _p(w_packed), co, _p(bias), _p(scratch), _p(out))
+    return out
+
+
+def groupnorm(x1, gamma, beta, groups, eps, imgs_per_set=1, silu=False, x2=None):
+    """x1 [N, H, W, C1] (+ x2) -> normalised [N, H, W, C1+C2]; statistics over imgs_per_set images x (C/groups)."""
+    _chk16(x1, x2)
+    _chk32(gamma, beta)
+    n, H, W, c1 = x1.shape
+    c2 = 0 if x2 is None else x2.shape[3]
+    sums = torch.empty((n // imgs_per_set, groups, 2), dtype=torch.float32, device=x1.device)
+    out = torch.empty((n, H, W, c1 + c2), dtype=torch.float16, device=x1.device)
+    _lib.call("vs_groupnorm", _stream(), _p(x1), c1, _p(x2), c2, n, H * W, imgs_per_set, groups, eps, _p(gamma), _p(beta),
+              int(silu), _p(sums), _p(out))
+    return out
+
+
+def layernorm(x, gamma, beta, pe=None, hw=1, F=1):
+    _chk16(x)
+    _chk32(gamma, beta, pe)
+    rows, Cc = x.shape
+    out = torch.empty_like(x)
+    _lib.call("vs_layernorm", _stream(), _p(x), rows, Cc, _p(gamma), _p(beta), _p(pe), hw, F, _p(out))
+    return out
+
+
+def attention(q, k, v, heads, kv_div=1):
+    """q [B, Nq, h*d], k/v [Bk, Nk, h*d] (may be strided views with contiguous last dim) -> [B, Nq, h*d]."""
+    B, nq, Cc = q.shape
+    nk = k.shape[1]
+    d = Cc // heads
+    for t in (q, k, v):
+        assert t.dtype == torch.float16 and t.stride(2) == 1
+    out = torch.empty((B, nq, Cc), dtype=torch.float16, device=q.device)
+    _lib.call("vs_attention", _stream(), _p(q), q.stride(1), _p(k), k.stride(1), _p(v), v.stride(1), _p(out), Cc, B, nq, nk,
+              heads, d, q.stride(0), k.stride(0), nq * Cc, kv_div)
+    return out
+
+
+def temporal_attention(qkv, heads):
+    """qkv [B, F, HW, 3C] -> [B, F, HW, C]: attention over the F axis for every (b, pixel, head)."""
+    _chk16(qkv)
+    B, F, HW, C3 = qkv.shape
+    out = torch.empty((B, F, HW, C3 // 3), dtype=torch.float16, device=qkv.device)
+    _lib.call("vs_temporal_attention", _stream(), _p(qkv), _p(out), B, F, HW, C3 // 3, heads)
+    return out
+
+
+def conv_in(x, w, bias):
+    _chk16(x, w)
+    _chk32(bias)
+    n, H, W, ci = x.shape
+    co = w.shape[0]
+    out = torch.empty((n, H, W, co), dtype=torch.float16, device=x.device)
+    _lib.call("vs_conv_in", _stream(), _p(x), n, H, W, ci, _p(w), _p(bias), co, _p(out))
+    return out
+
+
+def upsample2x(x):
+    _chk16(x)
+    n, H, W, Cc = x.shape
+    out = torch.empty((n, 2 * H, 2 * W, Cc), dtype=torch.float16, device=x.device)
+    _lib.call("vs_upsample2x", _stream(), _p(x), n, H, W, Cc, _p(out))
+    return out
+
+
+def cfg_ddim_step(eps2, latents, guidance, alpha_t, alpha_prev, cfg=True, out=None):
+    assert eps2.dtype == latents.dtype and eps2.is_contiguous() and latents.is_contiguous()
+    is_f32 = int(latents.dtype == torch.float32)
+    if out is None:
+        out = torch.empty_like(latents)
+    _lib.call("vs_cfg_ddim_step", _stream(), _p(eps2), _p(latents), is_f32, latents.numel(), int(cfg), float(guidance),
+              float(alpha_t), float(alpha_prev), _p(out))
+    return out
+
+
+def adapter_level(w0, b0, w1, b1, point_embedding, tracks, h, w, rate, point_mask=None, coord_fp16=True, scale=1.0):
+    """One level of SparsePointAdapter: returns the NHWC fp16 map [F, h, w, C]."""
+    _chk16(w0, b0, w1, b1)
+    _chk32(point_embedding, tracks)
+    mid, E = w0.shape
+    Cc = w1.shape[0]
+    F, P = tracks.shape[:2]
+    ws = torch.empty((mid + Cc + P * (mid + Cc),), dtype=torch.float32, device=w0.device)
+    out = torch.empty((F, h, w, Cc), dtype=torch.float16, device=w0.device)
+    _lib.call("vs_adapter_level", _stream(), _p(w0), _p(b0), _p(w1), _p(b1), E, mid, Cc, _p(point_embedding), _p(tracks),
+              _p(point_mask), F, P, h, w, float(rate), int(coord_fp16), float(scale), _p(ws), _p(out))
+    return out
