@@ -1,0 +1,303 @@
+"""Benchmark of the denoising hot path (BASELINE.json metric: denoise-steps/sec, 16 f x 512^2 SD-1.5 UNet3D).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+
+One "step" = one loop body of the reference pipeline (pipelines/pipeline_videoswap.py:556-587): CFG batch
+duplication, AnimateDiffUNet3DModel forward on [2,4,16,64,64], CFG combine, DDIM update.  Workload = BASELINE config
+"16-frame 512x512 ... 1xB200 fp16" with ED-LoRA per-layer embeddings and adapter residuals active (superset of
+configs[1] and configs[2]); synthetic inputs, seeded random weights of the real architecture (no checkpoints offline).
+N > 1: one process per GPU (torchrun), each rank denoises its own video (independent editing jobs -> weak scaling,
+no data-path collective); barrier + device timing, max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "denoise-steps/sec, 16f 512^2 SD1.5 UNet3D (CFG UNet fwd + CFG combine + DDIM step)"
+UNIT = "steps/s"
+FLOP_PER_STEP = 35.26e12          # algorithmic FLOPs of one CFG step at this config
+FRAMES, LATENT = 16, 64
+CATS = ["gemm", "conv3x3", "attention", "temporal_attention", "groupnorm", "layernorm", "other"]
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"tflops": d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0)), "tflops_burst": d.get("bf16_tflops", 1590.0),
+                "gbs": d.get("hbm_gbs", 6650.0), "source": "MEASURED_PEAKS.json (sustained bf16 cuBLAS / copy)"}
+    return {"tflops": 1400.0, "tflops_burst": 1590.0, "gbs": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def gpu_weights(cfg, device):
+    """Random weights of the real architecture generated directly on the GPU (values are irrelevant for timing)."""
+    import torch
+    from videoswap_b200 import unet_param_shapes
+    from videoswap_b200.weights import temporal_pe_table
+    g = torch.Generator(device=device).manual_seed(0)
+    sd = {}
+    for name, shape in unet_param_shapes(cfg).items():
+        if name.endswith(".pe"):
+            sd[name] = temporal_pe_table(shape[1], shape[2]).to(device)
+        elif len(shape) >= 2:
+            fan_in = math.prod(shape[1:])
+            sd[name] = ((torch.rand(shape, device=device, generator=g) * 2 - 1) / math.sqrt(fan_in)).half()
+        elif name.endswith(".weight"):
+            sd[name] = (1 + 0.1 * torch.randn(shape, device=device, generator=g)).half()
+        else:
+            sd[name] = (0.02 * torch.randn(shape, device=device, generator=g)).half()
+    return sd
+
+
+def cpu_oracle_sample(frames=2, latent=LATENT, reps_budget_s=15.0, warmup=1, max_reps=5):
+    """Times the CPU oracle (restatement of the reference's UNet forward) on a bounded sample of the workload:
+    one UNet forward on [1,4,frames,latent,latent] with ED-LoRA embeddings = frames/16 of one half of a CFG step."""
+    import torch
+    from oracle import unet3d_oracle as O
+    from videoswap_b200 import UNetConfig, seeded_state_dict, unet_param_shapes
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = seeded_state_dict(unet_param_shapes(UNetConfig()), seed=0)
+    x = torch.randn(1, 4, frames, latent, latent)
+    ehs = torch.randn(1, 16, 77, 768)
+    times = []
+    with torch.no_grad():
+        for _ in range(warmup):
+            O.unet_forward(sd, O.OracleConfig(), x, 981, ehs)
+        t_total = 0.0
+        while len(times) < max_reps and (t_total < reps_budget_s or not times):
+            t0 = time.perf_counter()
+            O.unet_forward(sd, O.OracleConfig(), x, 981, ehs)
+            times.append(time.perf_counter() - t0)
+            t_total += times[-1]
+    frac = frames / (2.0 * FRAMES)                 # fraction of one CFG step (B=2 x 16 frames) this sample covers
+    return times, frac
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU path.  The reference is pure Python on diffusers (not installable offline)
+    and /root/reference does not travel to the GPU box, so this times oracle/ (the pinned CPU restatement) on the host
+    cores; rank 0 only."""
+    if rank != 0:
+        return
+    import torch
+    times, frac = cpu_oracle_sample(frames=2, reps_budget_s=1e9, warmup=min(args.warmup, 1), max_reps=max(args.steps, 1))
+    t = sorted(times)[len(times) // 2]
+    v = frac / t
+    sample = "oracle UNet forward fp32 on [1,4,2,64,64] + ED-LoRA embeds = 1/16 of a CFG step; value = (1/16)/median time"
+    print(json.dumps({
+        "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times), "warmup": min(args.warmup, 1),
+        "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "impl": "reference",
+        "config": {"workload": "16f 512^2 CFG denoise step (configs[1]/[2]); CPU arm runs a 2-frame no-CFG sample"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--frames", type=int, default=FRAMES)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from videoswap_b200 import AnimateDiffUNet3DModel, DDIMScheduler, VideoSwapPipeline, _lib, ops
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(args.warmup, 3)
+    K = args.steps
+    Fr = args.frames
+
+    model = AnimateDiffUNet3DModel(init="empty")
+    model.load_state_dict(gpu_weights(model.cfg, dev), assign=True)
+    pipe = VideoSwapPipeline(model, DDIMScheduler())
+    pipe.scheduler.set_timesteps(50)
+    ts = pipe.scheduler.timesteps
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    lat0 = torch.randn((1, 4, Fr, LATENT, LATENT), device=dev, generator=g).half()
+    embeds = torch.randn((2, 16, 77, 768), device=dev, generator=g).half()
+    boc = model.cfg.block_out_channels
+    residuals = [(0.1 * torch.randn((2 * Fr, c, LATENT >> l, LATENT >> l), device=dev, generator=g)).half() for l, c in enumerate(boc)]
+
+    def step(lat, i):
+        return pipe.step(lat, ts[i % len(ts)], embeds, 7.5, list(residuals))
+
+    lib = _lib.lib()
+    lat = lat0
+    for i in range(W):
+        lat = step(lat, i)
+    torch.cuda.synchronize()
+
+    # ---------------- timed region 1: inputs resident in HBM, per-launch CUDA-event profile for the roofline numbers
+    lib.vs_profile_reset()
+    lib.vs_profile_enable(1)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    n0 = lib.vs_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        lat = step(lat, W + i)
+    e1.record()
+    torch.cuda.synchronize()
+    launches = lib.vs_launch_count() - n0
+    lib.vs_profile_enable(0)
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        ms = t.item()
+    clocks = sampler.stop() if rank == 0 else None
+    prof = {}
+    for ci, name in enumerate(CATS):
+        a, b, c = C.c_double(), C.c_double(), C.c_longlong()
+        _lib.call("vs_profile_collect", ci, C.byref(a), C.byref(b), C.byref(c))
+        prof[name] = {"ms_per_step": a.value / K, "work_per_step": b.value / K, "launches_per_step": c.value / K}
+    lib.vs_profile_reset()
+    finite = bool(torch.isfinite(lat).all().item())
+
+    # ---------------- timed region 2: end to end through the public API with HOST buffers (pinned), H2D + D2H inside
+    h_lat = lat0.cpu().pin_memory()
+    h_emb = embeds.cpu().pin_memory()
+    h_out = torch.empty_like(h_lat).pin_memory()
+    d_lat = torch.empty_like(lat0)
+    d_emb = torch.empty_like(embeds)
+
+    def e2e_step(i):
+        d_lat.copy_(h_lat, non_blocking=True)
+        d_emb.copy_(h_emb, non_blocking=True)
+        out = pipe.step(d_lat, ts[i % len(ts)], d_emb, 7.5, list(residuals))
+        h_out.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the caller reads the result on the host every step
+        h_lat.copy_(h_out)
+
+    for i in range(2):
+        e2e_step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(K):
+        e2e_step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = t.item()
+
+    if rank == 0:
+        pk = peaks()
+        value = world * K / (ms / 1e3)
+        e2e = world * K / (ms_e2e / 1e3)
+        tensor_cats = ["gemm", "conv3x3", "attention"]
+        dom = max(tensor_cats, key=lambda n: prof[n]["ms_per_step"])
+        d = prof[dom]
+        ach = d["work_per_step"] / (d["ms_per_step"] / 1e3) / 1e12 if d["ms_per_step"] > 0 else 0.0
+        kernels = {}
+        for n, p_ in prof.items():
+            if p_["ms_per_step"] <= 0:
+                continue
+            rate = p_["work_per_step"] / (p_["ms_per_step"] / 1e3)
+            if n in tensor_cats:
+                kernels[n] = {"ms_per_step": round(p_["ms_per_step"], 3), "tflops": round(rate / 1e12, 1),
+                              "frac_of_peak": round(rate / 1e12 / pk["tflops"], 3), "launches": p_["launches_per_step"]}
+            else:
+                kernels[n] = {"ms_per_step": round(p_["ms_per_step"], 3), "gbs": round(rate / 1e9, 1),
+                              "frac_of_peak": round(rate / 1e9 / pk["gbs"], 3), "launches": p_["launches_per_step"]}
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+            "data": "synthetic",
+            "config": {"workload": f"{Fr}-frame 512x512 (latent [1,4,{Fr},64,64]), CFG 7.5 (UNet batch 2), ED-LoRA embeds "
+                                   f"[2,16,77,768], adapter residuals active, DDIM step; one video per GPU",
+                       "timing": "CUDA events; working set (2.55 GB weights + activations) >> 126 MB L2, no flush needed",
+                       "whole_step_tflops": round(FLOP_PER_STEP * (Fr / FRAMES) * (K / (ms / 1e3)) / 1e12, 1)},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h_lat.numel() * 2 + h_emb.numel() * 2,
+                    "d2h_bytes_per_step": h_out.numel() * 2},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": {"gemm": "gemm_tc_kernel (GEMM)", "conv3x3": "gemm_tc_kernel (implicit-GEMM 3x3 conv)",
+                                    "attention": "attn_kernel"}[dom], "bound": "tensor", "achieved": ach, "peak": pk["tflops"],
+                         "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": None, "peak_source": pk["source"]},
+            "kernels": kernels, "finite": finite,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            times, frac = cpu_oracle_sample(frames=2, reps_budget_s=12.0)
+            tmed = sorted(times)[len(times) // 2]
+            out["cpu_baseline"] = {"value": frac / tmed, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                   "sample": f"oracle UNet fwd fp32 on [1,4,2,64,64] (1/16 CFG step), median of {len(times)} reps = {tmed:.2f} s"}
+        else:
+            out["cpu_baseline"] = None
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -75,6 +75,7 @@ size_t vs_unet_workspace_bytes(const vs_unet* h);
 int vs_unet_enable_taps(vs_unet* h, int enable);
 int vs_unet_num_taps(const vs_unet* h);
 int vs_unet_get_tap(const vs_unet* h, int i, const char** name, const void** d_ptr, int* nimg, int* hh, int* ww, int* c);
+int vs_unet_copy_tap(const vs_unet* h, void* stream, int i, void* d_dst);   /* NHWC fp16 [nimg, hh, ww, c] */
 
 /* Replaces the CFG combine + DDIMScheduler.step of the loop body (pipeline_videoswap.py:578-587; diffusers
  * DDIMScheduler.step, eta = 0):  eps = eps_u + g (eps_c - eps_u);  x' = sqrt(a_p) (x - sqrt(1-a_t) eps)/sqrt(a_t)
@@ -112,6 +113,14 @@ int vs_conv_in(void* stream, const void* d_x, int nimg, int H, int W, int cin, c
 int vs_upsample2x(void* stream, const void* d_x, int nimg, int H, int W, int C, void* d_out);
 int vs_conv3x3_s2(void* stream, const void* d_x, int nimg, int H, int W, int C, const void* d_w_packed, int Cout,
                   const float* d_bias, void* d_scratch, void* d_out);
+
+/* ---- measurement hooks (bench.py): per-launch CUDA-event timing on the launching stream, by kernel category
+ * 0 gemm, 1 conv3x3, 2 spatial/cross attention, 3 temporal attention, 4 groupnorm, 5 layernorm, 6 other.
+ * `work` = algorithmic FLOPs (categories 0-2) or algorithmic bytes (3-5) summed over the recorded launches. */
+int vs_profile_enable(int on);
+int vs_profile_reset(void);
+int vs_profile_collect(int category, double* ms, double* work, long long* count);
+long long vs_launch_count(void);   /* kernels launched by this library since load */
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,95 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every declared symbol, the host-side mirror has the
+reference's module tree / state_dict keys, scheduler tables match the oracle, failure modes are loud, and the product
+package never imports the oracle."""
+import os
+import re
+
+import pytest
+import torch
+
+import videoswap_b200 as V
+from oracle import unet3d_oracle as O
+from videoswap_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_header_symbol():
+    lib = _lib.lib()
+    syms = _lib.header_symbols()
+    assert len(syms) >= 25
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+    assert set(syms) == set(_lib._SIGNATURES), set(syms) ^ set(_lib._SIGNATURES)
+    assert lib.vs_version() >= 100
+
+
+def test_model_tree_matches_reference_surface():
+    m = V.AnimateDiffUNet3DModel(init="empty")
+    sd = m.state_dict()
+    shapes = V.unet_param_shapes(m.cfg)
+    assert {k: tuple(v.shape) for k, v in sd.items()} == dict(shapes)
+    n_params = sum(v.numel() for k, v in sd.items() if not k.endswith(".pe"))
+    assert n_params == 1_276_658_564            # 859.5 M SD-1.5 + 417.1 M motion modules
+    # the walk of revise_edlora_unet_attention_forward (edlora_util.py:85-99): class name 'Attention', 'attn2' in name
+    count = 0
+
+    def walk(mod):
+        nonlocal count
+        for name, layer in mod.named_children():
+            if layer.__class__.__name__ == "Attention" and "attn2" in name:
+                layer.set_processor(object())
+                count += 1
+            else:
+                walk(layer)
+    walk(m.down_blocks), walk(m.mid_block), walk(m.up_blocks)
+    assert count == 16
+    assert sum(1 for k, _ in m.named_modules() if k.endswith("temporal_transformer")) == 20
+    assert m.config.in_channels == 4 and m.config.sample_size == 64
+    a = m.down_blocks[0].attentions[0].transformer_blocks[0].attn1
+    assert a.heads == 8 and abs(a.scale - 40 ** -0.5) < 1e-9 and a.to_q.weight.shape == (320, 320)
+    assert "down_blocks.0.motion_modules.0.temporal_transformer.transformer_blocks.0.attention_blocks.0.processor.pos_encoder.pe" in sd
+
+
+def test_cpu_tensor_is_rejected_loudly():
+    m = V.AnimateDiffUNet3DModel(block_out_channels=(320, 640, 1280, 1280), init="empty")
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        m(torch.zeros(1, 4, 1, 8, 8), 1, torch.zeros(1, 77, 768))
+
+
+def test_missing_library_is_an_error(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libvideoswap_b200.so")
+    with pytest.raises(_lib.VSError, match="no CPU/PyTorch fallback"):
+        _lib.lib()
+
+
+def test_scheduler_tables_match_oracle():
+    s = V.DDIMScheduler()
+    s.set_timesteps(50)
+    o = O.DDIM()
+    assert s.timesteps == o.timesteps(50)
+    assert torch.allclose(s.alphas_cumprod, o.alphas_cumprod)
+    a_t, a_p = s.alphas(981)
+    assert abs(a_t - float(o.alphas_cumprod[981])) < 1e-9 and abs(a_p - float(o.alphas_cumprod[961])) < 1e-9
+    a_t, a_p = s.alphas(1)
+    assert abs(a_p - float(o.alphas_cumprod[0])) < 1e-9       # set_alpha_to_one=False
+    inv = V.DDIMInverseScheduler()
+    inv.set_timesteps(50)
+    assert inv.timesteps == o.inverse_timesteps(50)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "videoswap_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "/root/reference" not in text, f
+
+
+def test_registry_names():
+    assert V.build_model("AnimateDiffUNet3DModel") is V.AnimateDiffUNet3DModel
+    assert V.build_model("UNet3DConditionModel") is V.AnimateDiffUNet3DModel
+    assert V.build_pipeline("TuneAVideoPipeline") is V.VideoSwapPipeline

@@ -1,0 +1,49 @@
+"""GPU parity tests (pytest -m gpu) of the whole path through the reference-facing surface:
+AnimateDiffUNet3DModel.forward / VideoSwapPipeline loop body / SparsePointAdapter vs the CPU oracle and vs the
+fixtures generated from the reference's own files.  Tolerance (north_star): PSNR >= 40 dB in fp16."""
+import pytest
+import torch
+
+from tests import unet_checks as U
+
+pytestmark = pytest.mark.gpu
+PSNR_MIN = 40.0
+
+
+def test_unet_matches_reference_golden():
+    r = U.unet_vs_reference_golden()
+    assert r["psnr"] >= PSNR_MIN, r
+
+
+@pytest.mark.parametrize("kw", [dict(B=1, Fr=2, hw=8, edlora=True), dict(B=2, Fr=3, hw=16, edlora=True, residuals=True),
+                                dict(B=1, Fr=16, hw=8, edlora=False, t=1)])
+def test_unet_matches_oracle(kw):
+    r = U.unet_vs_oracle(**kw)
+    assert r["finite"] and r["psnr"] >= PSNR_MIN, r
+
+
+def test_frame_count_beyond_pe_table_raises():
+    m, _ = U.get_model()
+    x = torch.zeros(1, 4, 25, 8, 8, dtype=torch.float16, device="cuda")
+    with pytest.raises(Exception):
+        m(x, 1, torch.zeros(1, 77, 768, dtype=torch.float16, device="cuda"))
+
+
+def test_residual_list_is_consumed_in_place():
+    m, _ = U.get_model()
+    x = torch.zeros(1, 4, 1, 8, 8, dtype=torch.float16, device="cuda")
+    res = [torch.zeros(1, c, max(8 >> l, 1), max(8 >> l, 1), dtype=torch.float16, device="cuda")
+           for l, c in enumerate(m.cfg.block_out_channels)]
+    m(x, 1, torch.zeros(1, 77, 768, dtype=torch.float16, device="cuda"), down_block_additional_residuals=res)
+    assert len(res) == 0          # the reference pops the list (unet.py:422,435)
+
+
+def test_denoise_loop_matches_oracle():
+    r = U.pipeline_vs_oracle(steps=3)
+    assert r["psnr"] >= PSNR_MIN, r
+
+
+def test_adapter_matches_reference_golden():
+    r = U.adapter_vs_golden()
+    for e, ref in zip(r["errs"], r["refs"]):
+        assert e <= 2 ** -8 * ref + 2e-3, r

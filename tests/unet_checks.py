@@ -1,0 +1,120 @@
+"""Model-level parity helpers: the native UNet / pipeline (through the C-ABI) vs the CPU oracle on seeded inputs."""
+from __future__ import annotations
+
+import math
+import os
+
+import torch
+
+from oracle import unet3d_oracle as O
+from videoswap_b200 import (AnimateDiffUNet3DModel, DDIMScheduler, SparsePointAdapter, VideoSwapPipeline,
+                            adapter_param_shapes, seeded_state_dict, unet_param_shapes)
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+_CACHE = {}
+
+
+def psnr(out: torch.Tensor, ref: torch.Tensor) -> float:
+    out, ref = out.float().cpu(), ref.float().cpu()
+    mse = ((out - ref) ** 2).mean().item()
+    rng = (ref.max() - ref.min()).item()
+    return float("inf") if mse == 0 else 10 * math.log10(rng * rng / mse)
+
+
+def randn(shape, seed):
+    return torch.randn(shape, generator=torch.Generator().manual_seed(seed))
+
+
+def get_model():
+    """Full SD-1.5 + AnimateDiff architecture with seeded weights: (native model on cuda fp16, fp32 state dict)."""
+    if "m" not in _CACHE:
+        m = AnimateDiffUNet3DModel(init="empty")
+        sd = seeded_state_dict(unet_param_shapes(m.cfg), seed=0)
+        m.load_state_dict(sd)
+        m = m.half().cuda()
+        # the oracle sees the SAME fp16-rounded weights, so the comparison isolates kernel arithmetic
+        sd16 = {k: (v.half().float() if not k.endswith(".pe") else v) for k, v in sd.items()}
+        _CACHE["m"] = (m, sd16)
+    return _CACHE["m"]
+
+
+def nhwc_tap_to_ncfhw(t, B):
+    n, h, w, c = t.shape
+    return t.float().cpu().reshape(B, n // B, h, w, c).permute(0, 4, 1, 2, 3)
+
+
+def unet_vs_oracle(B=1, Fr=2, hw=8, edlora=True, residuals=False, t=981, taps=False):
+    m, sd = get_model()
+    x = randn((B, 4, Fr, hw, hw), 2)
+    ehs = randn((B, 16, 77, 768), 3) if edlora else randn((B, 77, 768), 3)
+    res = None
+    if residuals:
+        boc = m.cfg.block_out_channels
+        res = [0.5 * randn((B * Fr, c, max(hw >> l, 1), max(hw >> l, 1)), 10 + l) for l, c in enumerate(boc)]
+    x16, e16 = x.half(), ehs.half()
+    res16 = [r.half() for r in res] if res else None
+    otaps, ntaps = ({}, {}) if taps else (None, None)
+    with torch.no_grad():
+        ref = O.unet_forward(sd, O.OracleConfig(), x16.float(), t, e16.float(), [r.float() for r in res16] if res16 else None,
+                             taps=otaps)
+    out = m(x16.cuda(), t, e16.cuda(), down_block_additional_residuals=[r.cuda() for r in res16] if res16 else None,
+            return_dict=False, _taps=ntaps)[0]
+    torch.cuda.synchronize()
+    r = {"psnr": psnr(out, ref), "max_err": (out.float().cpu() - ref).abs().max().item(), "ref_max": ref.abs().max().item(),
+         "finite": bool(torch.isfinite(out).all().item())}
+    if taps:
+        r["taps"] = {}
+        for k, v in ntaps.items():
+            if k in otaps:
+                o = nhwc_tap_to_ncfhw(v, B)
+                r["taps"][k] = {"psnr": psnr(o, otaps[k]), "max_err": (o - otaps[k]).abs().max().item(),
+                                "ref_max": otaps[k].abs().max().item()}
+    return r
+
+
+def unet_vs_reference_golden():
+    """tests/golden/unet_full_arch_small.pt was produced by the REFERENCE's own model files (oracle/make_golden.py)."""
+    from oracle.make_golden import make_inputs
+    g = torch.load(os.path.join(GOLD, "unet_full_arch_small.pt"))
+    case = g["case"]
+    m, _ = get_model()
+    x, ehs, _ = make_inputs(case)
+    out = m(x.half().cuda(), case["t"], ehs.half().cuda(), return_dict=False)[0]
+    torch.cuda.synchronize()
+    return {"psnr": psnr(out, g["out"]), "max_err": (out.float().cpu() - g["out"]).abs().max().item()}
+
+
+def pipeline_vs_oracle(steps=3, Fr=2, hw=8, guidance=7.5):
+    m, sd = get_model()
+    pipe = VideoSwapPipeline(m, DDIMScheduler())
+    lat = randn((1, 4, Fr, hw, hw), 21)
+    pos = randn((1, 16, 77, 768), 22).half()
+    neg = randn((1, 16, 77, 768), 23).half()
+    # run only `steps` iterations of the 50-step schedule on both sides
+    sched = O.DDIM()
+    ts = sched.timesteps(50)[:steps]
+    ref = lat.half().float()
+    ehs2 = torch.cat([neg, pos]).float()
+    nat = lat.half().cuda()
+    from videoswap_b200 import ops
+    pipe.scheduler.set_timesteps(50)
+    for t in ts:
+        with torch.no_grad():
+            ref = O.denoise_step(sd, O.OracleConfig(), sched, ref, t, 50, ehs2, guidance)
+        eps = m(torch.cat([nat] * 2), t, torch.cat([neg, pos]).cuda(), return_dict=False)[0]
+        a_t, a_p = pipe.scheduler.alphas(t)
+        nat = ops.cfg_ddim_step(eps, nat, guidance, a_t, a_p)
+    torch.cuda.synchronize()
+    return {"psnr": psnr(nat, ref), "max_err": (nat.float().cpu() - ref).abs().max().item()}
+
+
+def adapter_vs_golden():
+    g = torch.load(os.path.join(GOLD, "adapter.pt"))
+    ad = SparsePointAdapter(init="empty")
+    ad.load_state_dict(seeded_state_dict(adapter_param_shapes(), seed=5))
+    ad = ad.cuda()
+    maps = ad(g["tracks"].cuda(), g["size"], g["emb"].cuda(), coord_fp16=False, as_nchw=True)
+    torch.cuda.synchronize()
+    errs = [(m.float().cpu() - r).abs().max().item() for m, r in zip(maps, g["maps"])]
+    refs = [r.abs().max().item() for r in g["maps"]]
+    return {"errs": errs, "refs": refs}

@@ -101,3 +101,11 @@ extern "C" int vs_conv3x3_s2(void* stream, const void* d_x, int nimg, int H, int
   g.bias = d_bias; g.out = (__half*)d_out; g.ldc = Cout;
   return gemm_tc(st, g);
 }
+
+extern "C" int vs_profile_enable(int on) { prof_enable(on != 0); return 0; }
+extern "C" int vs_profile_reset(void) { prof_reset(); return 0; }
+extern "C" int vs_profile_collect(int category, double* ms, double* work, long long* count) {
+  VS_REQUIRE(category >= 0 && category < PC_COUNT && ms && work && count, "vs_profile_collect: bad argument");
+  return prof_collect(category, ms, work, count);
+}
+extern "C" long long vs_launch_count(void) { return launch_count(); }

@@ -220,6 +220,7 @@ int launch_attn(cudaStream_t st, const AttnParams& p, int batch, int heads) {
     configured = true;
   }
   dim3 grid((p.nq + C::BQ - 1) / C::BQ, heads, batch);
+  ProfScope prof(st, PC_ATTN, 4.0 * batch * heads * (double)p.nq * p.nk * D);
   attn_kernel<D><<<grid, 128, C::SMEM, st>>>(p);
   VS_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -319,6 +320,7 @@ int launch_tattn(cudaStream_t st, const TAttnParams& p) {
     configured = true;
   }
   const long long blocks = (p.items + 3) / 4;
+  ProfScope prof(st, PC_TATTN, 8.0 * p.B * p.F * (double)p.HW * p.C);   // bytes: read 3C + write C fp16 per token
   tattn_kernel<D, FP><<<(unsigned)blocks, 128, SMEM, st>>>(p);
   VS_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -36,6 +36,19 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
 
 int num_sms();
 
+// profiling categories (work = algorithmic FLOPs for tensor kernels, algorithmic bytes for HBM-bound kernels)
+enum ProfCat { PC_GEMM = 0, PC_CONV = 1, PC_ATTN = 2, PC_TATTN = 3, PC_GROUPNORM = 4, PC_LAYERNORM = 5, PC_OTHER = 6, PC_COUNT = 7 };
+struct ProfScope {
+  ProfScope(cudaStream_t st, int cat, double work, int nlaunch = 1);
+  ~ProfScope();
+  cudaStream_t st_; int idx_;
+};
+void prof_enable(bool on);
+void prof_reset();
+int prof_collect(int cat, double* ms, double* work, long long* count);
+long long launch_count();
+void count_launch(int n);
+
 // ------------------------------------------------------------------------------------------------ device side
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -408,6 +408,7 @@ int gemm_tc(cudaStream_t st, const GemmArgs& a) {
     const uint32_t box[2] = {BK, (uint32_t)bn};
     if (make_tmap_f16(&p.tmB, a.Bw, 2, dims, str, box, true)) return 3;
   }
+  ProfScope prof(st, a.taps == 9 ? PC_CONV : PC_GEMM, 2.0 * a.M * (double)a.N * Ktot);
   switch (bn) {
     case 64: return launch<64>(st, p, 0);
     case 128: return launch<128>(st, p, 0);

@@ -199,6 +199,7 @@ int groupnorm_stats(cudaStream_t st, const __half* x1, int c1, const __half* x2,
   if (int e = gn_fill(p, grid, threads, x1, c1, x2, c2, nimg, hw, imgs_per_set, groups)) return e;
   p.sums = sums;
   VS_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * groups * (nimg / imgs_per_set), st));
+  ProfScope prof(st, PC_GROUPNORM, 2.0 * nimg * (double)hw * (c1 + c2));   // bytes read
   gn_stats_kernel<<<grid, threads, groups * 2 * sizeof(float), st>>>(p);
   VS_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -213,6 +214,7 @@ int groupnorm_apply(cudaStream_t st, const __half* x1, int c1, const __half* x2,
   if (int e = gn_fill(p, grid, threads, x1, c1, x2, c2, nimg, hw, imgs_per_set, groups)) return e;
   p.sums = const_cast<float*>(sums);
   p.gamma = gamma; p.beta = beta; p.eps = eps; p.silu = silu ? 1 : 0; p.out = out;
+  ProfScope prof(st, PC_GROUPNORM, 4.0 * nimg * (double)hw * (c1 + c2));   // bytes read + written
   gn_apply_kernel<<<grid, threads, 0, st>>>(p);
   VS_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -226,6 +228,7 @@ int layernorm(cudaStream_t st, const __half* x, int rows, int C, const float* ga
   const int blocks = (rows + wpb - 1) / wpb;
   if (hw <= 0) hw = 1;
   if (F <= 0) F = 1;
+  ProfScope prof(st, PC_LAYERNORM, 4.0 * rows * (double)C);
   switch (vpl) {
     case 1: ln_kernel<1><<<blocks, threads, 0, st>>>(x, rows, C, gamma, beta, pe, hw, F, out); break;
     case 2: ln_kernel<2><<<blocks, threads, 0, st>>>(x, rows, C, gamma, beta, pe, hw, F, out); break;

@@ -280,11 +280,13 @@ int small_linear(cudaStream_t st, const float* x, int rows, int K, const __half*
                  bool silu_out, float* out) {
   VS_REQUIRE(K % 2 == 0, "small_linear: K must be even");
   small_linear_kernel<<<blocks_for((size_t)N * 32), TPB, 0, st>>>(x, rows, K, W, bias, N, silu_in, silu_out, out);
+  count_launch(1);
   VS_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int timestep_embedding(cudaStream_t st, const float* t, int B, int dim, float* out) {
   timestep_embedding_kernel<<<blocks_for((size_t)B * dim / 2), TPB, 0, st>>>(t, B, dim, out);
+  count_launch(1);
   VS_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -294,6 +296,7 @@ int conv_in_3x3(cudaStream_t st, const __half* x, int nimg, int H, int W, int ci
   const size_t smem = (size_t)9 * cin * cout * sizeof(float);
   VS_REQUIRE(smem <= 48 * 1024, "conv_in_3x3: weights do not fit shared memory");
   conv_in_kernel<<<capped((size_t)nimg * H * W * (cout / 8)), TPB, smem, st>>>(x, nimg, H, W, cin, w, bias, cout, out);
+  count_launch(1);
   VS_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -301,6 +304,7 @@ int upsample_nearest2x(cudaStream_t st, const __half* x, int nimg, int H, int W,
   VS_REQUIRE(C % 8 == 0, "upsample: C %% 8 != 0");
   upsample2x_kernel<<<capped((size_t)nimg * 4 * H * W * (C / 8)), TPB, 0, st>>>(
       reinterpret_cast<const uint4*>(x), nimg, H, W, C / 8, reinterpret_cast<uint4*>(out));
+  count_launch(1);
   VS_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -309,11 +313,13 @@ int im2col_s2(cudaStream_t st, const __half* x, int nimg, int H, int W, int C, _
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   im2col_s2_kernel<<<capped((size_t)nimg * Ho * Wo * 9 * (C / 8)), TPB, 0, st>>>(
       reinterpret_cast<const uint4*>(x), nimg, H, W, C / 8, Ho, Wo, reinterpret_cast<uint4*>(out));
+  count_launch(1);
   VS_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int add_inplace(cudaStream_t st, __half* x, const __half* r, size_t n, float scale) {
   add_kernel<<<capped(n / 8 + 1), TPB, 0, st>>>(x, r, n, scale);
+  count_launch(1);
   VS_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -321,6 +327,7 @@ int ncfhw_to_nhwc(cudaStream_t st, const void* src, int src_is_f32, int B, int C
   const size_t n = (size_t)B * C * F * H * W;
   if (src_is_f32) ncfhw_to_nhwc_kernel<float><<<capped(n), TPB, 0, st>>>((const float*)src, B, C, F, H, W, dst);
   else ncfhw_to_nhwc_kernel<__half><<<capped(n), TPB, 0, st>>>((const __half*)src, B, C, F, H, W, dst);
+  count_launch(1);
   VS_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -328,6 +335,7 @@ int nhwc_to_ncfhw(cudaStream_t st, const __half* src, int B, int C, int F, int H
   const size_t n = (size_t)B * C * F * H * W;
   if (dst_is_f32) nhwc_to_ncfhw_kernel<float><<<capped(n), TPB, 0, st>>>(src, B, C, F, H, W, (float*)dst);
   else nhwc_to_ncfhw_kernel<__half><<<capped(n), TPB, 0, st>>>(src, B, C, F, H, W, (__half*)dst);
+  count_launch(1);
   VS_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -335,6 +343,7 @@ int nchw_to_nhwc(cudaStream_t st, const __half* src, int n, int C, int H, int W,
   const int HW = H * W;
   dim3 grid((HW + 31) / 32, (C + 31) / 32, n), block(32, 8);
   nchw_to_nhwc_kernel<<<grid, block, 0, st>>>(src, C, HW, scale, dst);
+  count_launch(1);
   VS_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -344,6 +353,7 @@ int cfg_ddim_step(cudaStream_t st, const void* eps2, const void* latents, int is
   const float c_e = sqrtf(1.f - a_prev) - sqrtf(a_prev) * sqrtf(1.f - a_t) / sqrtf(a_t);
   if (is_f32) cfg_ddim_kernel<float><<<capped(n), TPB, 0, st>>>((const float*)eps2, (const float*)latents, n, cfg, guidance, c_x, c_e, (float*)out);
   else cfg_ddim_kernel<__half><<<capped(n), TPB, 0, st>>>((const __half*)eps2, (const __half*)latents, n, cfg, guidance, c_x, c_e, (__half*)out);
+  count_launch(1);
   VS_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -352,22 +362,26 @@ int adapter_splat(cudaStream_t st, const float* feat, const float* tracks, const
   VS_REQUIRE(C % 8 == 0, "adapter_splat: C %% 8 != 0");
   adapter_splat_kernel<<<capped((size_t)F * h * w * (C / 8)), TPB, 0, st>>>(feat, tracks, point_mask, F, P, C, h, w, rate,
                                                                             coord_fp16, scale, maps);
+  count_launch(1);
   VS_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int pack_conv3x3(cudaStream_t st, const __half* w, int cout, int cin, __half* out) {
   pack_conv3x3_kernel<<<capped((size_t)cout * 9 * cin), TPB, 0, st>>>(w, cout, cin, out);
+  count_launch(1);
   VS_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int pack_geglu(cudaStream_t st, const __half* w, const __half* b, int hidden, int K, int granule, __half* wout, float* bout) {
   VS_REQUIRE(hidden % granule == 0, "pack_geglu: hidden %% granule != 0");
   pack_geglu_kernel<<<capped((size_t)2 * hidden * K), TPB, 0, st>>>(w, b, hidden, K, granule, wout, bout);
+  count_launch(1);
   VS_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 int f16_to_f32(cudaStream_t st, const __half* x, size_t n, float* out) {
   f16_to_f32_kernel<<<capped(n), TPB, 0, st>>>(x, n, out);
+  count_launch(1);
   VS_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -76,3 +76,55 @@ int num_sms() {
 }
 
 }  // namespace vs
+
+// ---------------------------------------------------------------------------------------------------------------
+// Lightweight per-launch profiler (CUDA events on the launching stream) and launch counter, used by bench.py for the
+// live roofline numbers.  Disabled by default; when enabled every launcher brackets its kernel(s) with two events.
+#include <atomic>
+#include <vector>
+
+namespace vs {
+
+static std::atomic<long long> g_launches{0};
+static bool g_prof_on = false;
+struct ProfEntry { cudaEvent_t a, b; int cat; double work; };
+static std::vector<ProfEntry> g_prof;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_pool;
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(); }
+
+ProfScope::ProfScope(cudaStream_t st, int cat, double work, int nlaunch) : st_(st), idx_(-1) {
+  count_launch(nlaunch);
+  if (!g_prof_on) return;
+  ProfEntry e;
+  if (!g_pool.empty()) { e.a = g_pool.back().first; e.b = g_pool.back().second; g_pool.pop_back(); }
+  else { cudaEventCreate(&e.a); cudaEventCreate(&e.b); }
+  e.cat = cat; e.work = work;
+  cudaEventRecord(e.a, st);
+  idx_ = (int)g_prof.size();
+  g_prof.push_back(e);
+}
+ProfScope::~ProfScope() {
+  if (idx_ >= 0) cudaEventRecord(g_prof[idx_].b, st_);
+}
+
+void prof_enable(bool on) { g_prof_on = on; }
+void prof_reset() {
+  for (auto& e : g_prof) g_pool.push_back({e.a, e.b});
+  g_prof.clear();
+}
+int prof_collect(int cat, double* ms, double* work, long long* count) {
+  double t = 0, w = 0; long long n = 0;
+  for (auto& e : g_prof) {
+    if (e.cat != cat) continue;
+    if (cudaEventSynchronize(e.b) != cudaSuccess) { set_error("profile: event sync failed"); return 1; }
+    float m = 0.f;
+    cudaEventElapsedTime(&m, e.a, e.b);
+    t += m; w += e.work; ++n;
+  }
+  *ms = t; *work = w; *count = n;
+  return 0;
+}
+
+}  // namespace vs

@@ -510,6 +510,13 @@ extern "C" int vs_unet_get_tap(const vs_unet* h, int i, const char** name, const
   return 0;
 }
 
+extern "C" int vs_unet_copy_tap(const vs_unet* h, void* stream, int i, void* d_dst) {
+  VS_REQUIRE(i >= 0 && i < (int)h->taps.size(), "tap index out of range");
+  const auto& t = h->taps[i];
+  VS_CHECK_CUDA(cudaMemcpyAsync(d_dst, t.p, (size_t)t.n * t.h * t.w * t.c * 2, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
 extern "C" int vs_unet_forward(vs_unet* h, void* stream, const void* d_sample, int io_f32, int B, int F, int H, int W,
                                const float* d_timesteps, const void* d_ehs, int ehs_tokens, int ehs_layers,
                                const void* const* d_residuals, int residuals_nhwc, float residual_scale, void* d_out) {
