@@ -198,6 +198,15 @@ def check_self_attention(B=3, N=200, C=320, seed=120):
     return _res(out, _mha_ref(q, k, v, 8))
 
 
+def check_self_attention_mma(**kw):
+    """Same problem on the mma.sync kernel (the tcgen05 kernel is the default for d = 40 / 80)."""
+    ops.set_option("attn_tc", 0)
+    try:
+        return check_self_attention(**kw)
+    finally:
+        ops.set_option("attn_tc", 1)
+
+
 def check_cross_attention(B=2, Fr=3, N=100, C=640, nk=77, seed=130):
     q = _rand((B * Fr, N, C), seed).half()
     kv = _rand((B, nk, 2 * C), seed + 1).half()
@@ -260,6 +269,12 @@ CHECKS = {
     "self_attn_d80": lambda: check_self_attention(B=2, N=64, C=640),
     "self_attn_d160": lambda: check_self_attention(B=2, N=130, C=1280),
     "self_attn_tiny": lambda: check_self_attention(B=2, N=4, C=320),
+    "self_attn_d40_n600": lambda: check_self_attention(B=2, N=600, C=320, seed=121),
+    "self_attn_d40_n1024": lambda: check_self_attention(B=1, N=1024, C=320, seed=122),
+    "self_attn_d80_n300": lambda: check_self_attention(B=2, N=300, C=640, seed=123),
+    "self_attn_d40_mma": lambda: check_self_attention_mma(C=320),
+    "self_attn_d80_mma": lambda: check_self_attention_mma(B=2, N=64, C=640),
+    "cross_attn_d40": lambda: check_cross_attention(B=2, Fr=2, N=300, C=320, seed=131),
     "cross_attn": check_cross_attention,
     "temporal_attn_d40": lambda: check_temporal_attention(C=320),
     "temporal_attn_d160_f3": lambda: check_temporal_attention(B=1, Fr=3, HW=7, C=1280),

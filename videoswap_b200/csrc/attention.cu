@@ -333,6 +333,11 @@ int attention(cudaStream_t st, const __half* q, int ldq, const __half* k, int ld
               long long o_bstride, int kv_div) {
   VS_REQUIRE(nq > 0 && nk > 0 && batch > 0, "attention: empty problem");
   VS_REQUIRE((ldq % 8 | ldk % 8 | ldv % 8 | ldo % 2) == 0 && d % 8 == 0, "attention: unaligned leading dims");
+  if (get_option("attn_tc") && (d == 40 || d == 80)) {
+    const int e = attention_tc(st, q, ldq, k, ldk, v, ldv, o, ldo, batch, nq, nk, heads, d, q_bstride, kv_bstride, o_bstride,
+                               kv_div > 0 ? kv_div : 1);
+    if (e != -1) return e;
+  }
   AttnParams p{q, k, v, o, ldq, ldk, ldv, ldo, q_bstride, kv_bstride, o_bstride, nq, nk, kv_div > 0 ? kv_div : 1,
                1.4426950408889634f / sqrtf((float)d)};
   switch (d) {

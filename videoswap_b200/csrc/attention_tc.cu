@@ -1,0 +1,360 @@
+// tcgen05 / TMEM flash attention for sm_100a (spatial self-attention N x N and cross-attention N x 77; d = 40 / 80).
+//
+// One CTA = (batch, head, 256 queries) = two 128-query tiles that ping-pong against the tensor core:
+//   warp 0      TMA producer: Q once (4-D descriptor [d, head, token, batch]; head dim 40 is zero-padded to 64 by TMA
+//               out-of-bounds fill), then a ring of K / V tiles
+//   warp 1      single-thread tcgen05.mma issuer:  S_i = Q_i K^T  (K-major x K-major, fp32 in TMEM)
+//                                                  O_i += P_i V   (P from shared memory, V as MN-major B operand)
+//   warp 2      TMEM allocator
+//   warps 4-7   softmax warpgroup of query tile 0 (thread = one query row, reads S with tcgen05.ld)
+//   warps 8-11  softmax warpgroup of query tile 1
+// The softmax keeps a *stale* running maximum and only rescales O (tcgen05.ld/st round trip) when the true maximum has
+// grown by more than 2^8, so the rescale is off the critical path after the first few key tiles.  exp2 is evaluated in
+// fp32 (v1) and P is written to shared memory in the 128-byte-swizzled K-major layout the MMA consumes.
+//
+// Replaces diffusers AttnProcessor2_0 / EDLoRA_AttnProcessor.__call__ (reference utils/edlora_util.py:47-65,
+// models/animatediff_models/attention.py:229-241).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vs {
+namespace {
+
+constexpr int TQ = 128;              // queries per tile (= UMMA M)
+constexpr int ATT_THREADS = 384;
+
+template <int D, int BKV>
+struct TCfg {
+  static constexpr int NCB = (D + 63) / 64;            // 64-wide (128-byte) column blocks of Q/K/V tiles
+  static constexpr int DPK = (D + 15) / 16 * 16;       // padded contraction length of Q K^T
+  static constexpr int DPO = (D + 15) / 16 * 16;       // N of the P V MMA / O accumulator columns
+  static constexpr int PCB = BKV / 64;                 // column blocks of the P tile
+  static constexpr int ST = 3;                         // K/V ring stages
+  static constexpr int Q_BYTES = 2 * NCB * TQ * 128;
+  static constexpr int KV_BLOCK_BYTES = BKV * 128;
+  static constexpr int KV_STAGE_BYTES = 2 * NCB * KV_BLOCK_BYTES;     // K then V
+  static constexpr int P_TILE_BYTES = PCB * TQ * 128;
+  static constexpr int SMEM = Q_BYTES + ST * KV_STAGE_BYTES + 2 * P_TILE_BYTES + 1024 + 256;
+  static constexpr int O_STRIDE = (DPO <= 64) ? 64 : 128;             // TMEM column stride between O_0 and O_1
+  static constexpr int S_COL = 0, O_COL = 2 * BKV;
+  static constexpr int TMEM_COLS = 512;
+  static_assert(2 * BKV + 2 * O_STRIDE <= 512, "TMEM budget");
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+};
+
+struct TAttnArgs {
+  CUtensorMap tmQ, tmK, tmV;
+  __half* o;
+  int ldo;
+  long long o_bs;
+  int nq, nk, kv_div;
+  float scale_log2;
+};
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// MN-major B operand (V tile [keys][64 channels], 128-byte rows, SWIZZLE_128B): 8-key groups are SBO = 1024 B apart,
+// 64-channel column blocks are LBO apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int D, int BKV>
+__global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_constant__ TAttnArgs p) {
+  using C = TCfg<D, BKV>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t q_s = base;                                   // [2 tiles][NCB][128 rows x 128 B]
+  const uint32_t kv_s = q_s + C::Q_BYTES;                      // [ST][K: NCB blocks | V: NCB blocks]
+  const uint32_t p_s = kv_s + C::ST * C::KV_STAGE_BYTES;       // [2 tiles][PCB][128 rows x 128 B]
+  const uint32_t bars = p_s + 2 * C::P_TILE_BYTES;
+  const uint32_t q_full = bars;
+  auto kv_full = [&](int s) { return bars + 8u * (1 + s); };
+  auto kv_empty = [&](int s) { return bars + 8u * (1 + C::ST + s); };
+  auto s_full = [&](int i) { return bars + 8u * (1 + 2 * C::ST + i); };
+  auto p_full = [&](int i) { return bars + 8u * (3 + 2 * C::ST + i); };
+  const uint32_t o_full = bars + 8u * (5 + 2 * C::ST);
+  const uint32_t tmem_slot = bars + 8u * (6 + 2 * C::ST);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 2 * TQ, head = blockIdx.y, b = blockIdx.z;
+  const int nkt = (p.nk + BKV - 1) / BKV;
+
+  if (warp == 0 && lane == 0) { prefetch_tmap(&p.tmQ); prefetch_tmap(&p.tmK); prefetch_tmap(&p.tmV); }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < C::ST; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(s_full(i), 1); mbar_init(p_full(i), 128); }
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ============================================================== TMA producer
+      mbar_expect_tx(q_full, C::Q_BYTES);
+      for (int i = 0; i < 2; ++i)
+        for (int cb = 0; cb < C::NCB; ++cb)
+          tma_load_4d(q_s + (i * C::NCB + cb) * TQ * 128, &p.tmQ, q_full, cb * 64, head, q0 + i * TQ, b);
+      const int bk = b / p.kv_div;
+      for (int j = 0; j < nkt; ++j) {
+        const int s = j % C::ST;
+        const uint32_t ph = (j / C::ST) & 1;
+        mbar_wait(kv_empty(s), ph ^ 1);
+        mbar_expect_tx(kv_full(s), C::KV_STAGE_BYTES);
+        const uint32_t k_dst = kv_s + s * C::KV_STAGE_BYTES;
+        const uint32_t v_dst = k_dst + C::NCB * C::KV_BLOCK_BYTES;
+        for (int cb = 0; cb < C::NCB; ++cb) {
+          tma_load_4d(k_dst + cb * C::KV_BLOCK_BYTES, &p.tmK, kv_full(s), cb * 64, head, j * BKV, bk);
+          tma_load_4d(v_dst + cb * C::KV_BLOCK_BYTES, &p.tmV, kv_full(s), cb * 64, head, j * BKV, bk);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ============================================================== MMA issuer
+      constexpr uint32_t idesc_qk = umma_idesc_f16(TQ, BKV);
+      constexpr uint32_t idesc_pv = umma_idesc_f16(TQ, C::DPO) | (1u << 16);   // B operand MN-major
+      auto issue_qk = [&](int i, int s) {
+        const uint32_t qa = q_s + i * C::NCB * TQ * 128;
+        const uint32_t ka = kv_s + s * C::KV_STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < C::DPK / 16; ++k) {
+          const int cb = (k * 16) / 64, off = ((k * 16) % 64) * 2;
+          tc_mma_f16(tmem + C::S_COL + i * BKV, umma_desc_sw128_kmajor(qa + cb * TQ * 128 + off),
+                     umma_desc_sw128_kmajor(ka + cb * C::KV_BLOCK_BYTES + off), idesc_qk, k != 0 ? 1u : 0u);
+        }
+        tc_commit(s_full(i));
+      };
+      auto issue_pv = [&](int i, int s, bool acc) {
+        const uint32_t pa = p_s + i * C::P_TILE_BYTES;
+        const uint32_t va = kv_s + s * C::KV_STAGE_BYTES + C::NCB * C::KV_BLOCK_BYTES;
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k) {
+          const int cb = (k * 16) / 64, off = ((k * 16) % 64) * 2;
+          tc_mma_f16(tmem + C::O_COL + i * C::O_STRIDE, umma_desc_sw128_kmajor(pa + cb * TQ * 128 + off),
+                     umma_desc_sw128_mnmajor(va + k * 16 * 128, C::KV_BLOCK_BYTES), idesc_pv, (acc || k != 0) ? 1u : 0u);
+        }
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(kv_full(0), 0);
+      tc_fence_after();
+      issue_qk(0, 0);
+      issue_qk(1, 0);
+      for (int j = 0; j < nkt; ++j) {
+        const int s = j % C::ST, sn = (j + 1) % C::ST;
+        const uint32_t pph = j & 1;
+        mbar_wait(p_full(0), pph);
+        tc_fence_after();
+        issue_pv(0, s, j > 0);
+        if (j + 1 < nkt) {
+          mbar_wait(kv_full(sn), ((j + 1) / C::ST) & 1);
+          tc_fence_after();
+          issue_qk(0, sn);
+        }
+        mbar_wait(p_full(1), pph);
+        tc_fence_after();
+        issue_pv(1, s, j > 0);
+        tc_commit(kv_empty(s));                  // K_j / V_j fully consumed once these MMAs retire
+        if (j + 1 < nkt) issue_qk(1, sn);
+      }
+      tc_commit(o_full);
+    }
+  } else if (warp >= 4) {
+    // ================================================================ softmax warpgroups + epilogue
+    const int i = (warp - 4) >> 2;               // query tile handled by this warpgroup
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;         // query row inside the tile == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const uint32_t s_addr = tmem + lane_addr + C::S_COL + i * BKV;
+    const uint32_t o_addr = tmem + lane_addr + C::O_COL + i * C::O_STRIDE;
+    const uint32_t p_row = p_s + i * C::P_TILE_BYTES + row * 128;
+    const float sc = p.scale_log2;
+    float m_used = -INFINITY, l = 0.f;
+    for (int j = 0; j < nkt; ++j) {
+      mbar_wait(s_full(i), j & 1);
+      tc_fence_after();
+      const int kbase = j * BKV;
+      const bool tail = kbase + BKV > p.nk;
+      // ---- pass 1: tile maximum of this row
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BKV; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(s_addr + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          float f = __uint_as_float(v[t]);
+          if (tail && kbase + c0 + t >= p.nk) f = -INFINITY;
+          mx = fmaxf(mx, f);
+        }
+      }
+      // ---- lazy rescale: only when the maximum moved by more than 2^8 (always true on the first tile: m_used=-inf)
+      const bool need = (mx - m_used) * sc > 8.f;
+      if (j > 0 && __any_sync(0xffffffffu, need)) {
+        const float alpha = need ? exp2f((m_used - mx) * sc) : 1.f;
+        l *= alpha;
+#pragma unroll 1
+        for (int c0 = 0; c0 < C::DPO; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(o_addr + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int t = 0; t < 16; ++t) v[t] = __float_as_uint(__uint_as_float(v[t]) * alpha);
+          tmem_st16(o_addr + c0, v);
+        }
+        tmem_st_wait();
+      }
+      if (need) m_used = mx;
+      const float ms = m_used * sc;
+      // ---- pass 2: P = exp2(S*scale - m) -> fp16 -> swizzled shared memory (A operand of the P V MMA)
+#pragma unroll 1
+      for (int c0 = 0; c0 < BKV; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(s_addr + c0, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int t = 0; t < 32; t += 2) {
+          float e0 = fast_exp2(__uint_as_float(v[t]) * sc - ms);
+          float e1 = fast_exp2(__uint_as_float(v[t + 1]) * sc - ms);
+          if (tail) {
+            if (kbase + c0 + t >= p.nk) e0 = 0.f;
+            if (kbase + c0 + t + 1 >= p.nk) e1 = 0.f;
+          }
+          const __half2 h = __floats2half2_rn(e0, e1);
+          const float2 back = __half22float2(h);
+          l += back.x + back.y;
+          pk[t / 2] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        const int cb = c0 / 64;
+        const int ch0 = (c0 % 64) / 8;           // first 16-byte chunk of this 32-column slab inside the 128-B row
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const uint32_t dst = p_row + cb * (TQ * 128) + (((ch0 + t) ^ (row & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pk[4 * t]), "r"(pk[4 * t + 1]),
+                       "r"(pk[4 * t + 2]), "r"(pk[4 * t + 3]) : "memory");
+        }
+      }
+      fence_proxy_async();                       // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+      tc_fence_before();
+      mbar_arrive(p_full(i));
+    }
+    // ---- epilogue: O / l -> fp16 -> HBM
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const int qrow = q0 + i * TQ + row;
+    const float inv = 1.f / l;
+    __half* orow = p.o + b * p.o_bs + (long long)qrow * p.ldo + head * D;
+#pragma unroll 1
+    for (int c0 = 0; c0 < C::DPO; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(o_addr + c0, v);
+      tmem_ld_wait();
+      if (qrow < p.nq) {
+#pragma unroll
+        for (int t = 0; t < 16; t += 8) {
+          if (c0 + t < D) {
+            uint4 o4;
+            __half2* h = reinterpret_cast<__half2*>(&o4);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              h[u] = __floats2half2_rn(__uint_as_float(v[t + 2 * u]) * inv, __uint_as_float(v[t + 2 * u + 1]) * inv);
+            *reinterpret_cast<uint4*>(orow + c0 + t) = o4;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem, C::TMEM_COLS);
+  }
+}
+
+template <int D, int BKV>
+int launch(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv, __half* o, int ldo,
+           int batch, int nq, int nk, int heads, long long q_bs, long long kv_bs, long long o_bs, int kv_div) {
+  using C = TCfg<D, BKV>;
+  static bool configured = false;
+  if (!configured) {
+    VS_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    configured = true;
+  }
+  TAttnArgs a;
+  memset(&a, 0, sizeof(a));
+  const int bkv = (batch + kv_div - 1) / kv_div;
+  {
+    const uint64_t dims[4] = {(uint64_t)D, (uint64_t)heads, (uint64_t)nq, (uint64_t)batch};
+    const uint64_t str[3] = {(uint64_t)D * 2, (uint64_t)ldq * 2, (uint64_t)(q_bs > 0 ? q_bs : (long long)nq * ldq) * 2};
+    const uint32_t box[4] = {64, 1, TQ, 1};
+    if (make_tmap_f16(&a.tmQ, q, 4, dims, str, box, true)) return 3;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)D, (uint64_t)heads, (uint64_t)nk, (uint64_t)bkv};
+    const uint64_t strk[3] = {(uint64_t)D * 2, (uint64_t)ldk * 2, (uint64_t)(kv_bs > 0 ? kv_bs : (long long)nk * ldk) * 2};
+    const uint64_t strv[3] = {(uint64_t)D * 2, (uint64_t)ldv * 2, (uint64_t)(kv_bs > 0 ? kv_bs : (long long)nk * ldv) * 2};
+    const uint32_t box[4] = {64, 1, (uint32_t)BKV, 1};
+    if (make_tmap_f16(&a.tmK, k, 4, dims, strk, box, true)) return 3;
+    if (make_tmap_f16(&a.tmV, v, 4, dims, strv, box, true)) return 3;
+  }
+  a.o = o; a.ldo = ldo; a.o_bs = o_bs; a.nq = nq; a.nk = nk; a.kv_div = kv_div;
+  a.scale_log2 = 1.4426950408889634f / sqrtf((float)D);
+  dim3 grid((nq + 2 * TQ - 1) / (2 * TQ), heads, batch);
+  ProfScope prof(st, PC_ATTN, 4.0 * batch * heads * (double)nq * nk * D);
+  attn_tc_kernel<D, BKV><<<grid, ATT_THREADS, C::SMEM, st>>>(a);
+  VS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+// Returns -1 when the shape is not handled by the tcgen05 kernel (caller falls back to the mma.sync kernel).
+int attention_tc(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv, __half* o,
+                 int ldo, int batch, int nq, int nk, int heads, int d, long long q_bs, long long kv_bs, long long o_bs,
+                 int kv_div) {
+  if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8)) return -1;
+  if ((q_bs % 8) || (kv_bs % 8)) return -1;
+  if (d == 40) return launch<40, 128>(st, q, ldq, k, ldk, v, ldv, o, ldo, batch, nq, nk, heads, q_bs, kv_bs, o_bs, kv_div);
+  if (d == 80) return launch<80, 64>(st, q, ldq, k, ldk, v, ldv, o, ldo, batch, nq, nk, heads, q_bs, kv_bs, o_bs, kv_div);
+  return -1;
+}
+
+}  // namespace vs

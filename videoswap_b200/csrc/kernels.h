@@ -52,6 +52,13 @@ int layernorm(cudaStream_t st, const __half* x, int rows, int C, const float* ga
 int attention(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv,
               __half* o, int ldo, int batch, int nq, int nk, int heads, int d, long long q_bstride,
               long long kv_bstride, long long o_bstride, int kv_div);   // k/v batch index = batch / kv_div
+// tcgen05/TMEM implementation (d = 40, 80); returns -1 if the shape is not supported by it.
+int attention_tc(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv,
+                 __half* o, int ldo, int batch, int nq, int nk, int heads, int d, long long q_bstride,
+                 long long kv_bstride, long long o_bstride, int kv_div);
+// runtime options: "attn_tc" (1 = use the tcgen05 attention kernel where supported, default 1)
+int set_option(const char* name, int value);
+int get_option(const char* name);
 // Temporal attention across F frames per pixel: qkv [B, F, HW, 3C] -> o [B, F, HW, C].
 int temporal_attention(cudaStream_t st, const __half* qkv, __half* o, int B, int F, int HW, int C, int heads);
 

@@ -6,6 +6,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "kernels.h"
 
 namespace vs {
 
@@ -107,6 +108,17 @@ ProfScope::ProfScope(cudaStream_t st, int cat, double work, int nlaunch) : st_(s
 }
 ProfScope::~ProfScope() {
   if (idx_ >= 0) cudaEventRecord(g_prof[idx_].b, st_);
+}
+
+static int g_opt_attn_tc = 1;
+int set_option(const char* name, int value) {
+  if (strcmp(name, "attn_tc") == 0) { g_opt_attn_tc = value; return 0; }
+  set_error("unknown option '%s'", name);
+  return 2;
+}
+int get_option(const char* name) {
+  if (strcmp(name, "attn_tc") == 0) return g_opt_attn_tc;
+  return 0;
 }
 
 void prof_enable(bool on) { g_prof_on = on; }

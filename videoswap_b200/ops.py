@@ -13,6 +13,11 @@ GEGLU_GRANULE = 80
 EPI_LINEAR, EPI_GEGLU = 0, 1
 
 
+def set_option(name: str, value: int):
+    """Runtime options of the library, e.g. set_option("attn_tc", 0) forces the mma.sync attention kernel."""
+    _lib.call("vs_set_option", name.encode(), int(value))
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
