@@ -51,16 +51,6 @@ struct TAttnArgs {
   float scale_log2;
 };
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
@@ -87,7 +77,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, 
   return d;
 }
 
-template <int D, int BKV>
+template <int D, int BKV, bool EXP16>
 __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_constant__ TAttnArgs p) {
   using C = TCfg<D, BKV>;
   extern __shared__ uint8_t smem_raw[];
@@ -210,20 +200,25 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
       tc_fence_after();
       const int kbase = j * BKV;
       const bool tail = kbase + BKV > p.nk;
-      // ---- pass 1: tile maximum of this row
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BKV; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(s_addr + c0, v);
-        tmem_ld_wait();
+      // ---- the whole S row of this tile lives in registers: one TMEM round trip per tile
+      uint32_t sv[BKV];
 #pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          float f = __uint_as_float(v[t]);
-          if (tail && kbase + c0 + t >= p.nk) f = -INFINITY;
-          mx = fmaxf(mx, f);
-        }
+      for (int c0 = 0; c0 < BKV; c0 += 32) tmem_ld32(s_addr + c0, sv + c0);
+      tmem_ld_wait();
+      if (tail) {   // keys beyond nk were zero-filled by TMA: mask them (last tile only)
+#pragma unroll
+        for (int t = 0; t < BKV; ++t)
+          if (kbase + t >= p.nk) sv[t] = 0xff800000u;   // -inf
       }
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+      for (int t = 0; t < BKV; t += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(sv[t]));
+        mx1 = fmaxf(mx1, __uint_as_float(sv[t + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(sv[t + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(sv[t + 3]));
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       // ---- lazy rescale: only when the maximum moved by more than 2^8 (always true on the first tile: m_used=-inf)
       const bool need = (mx - m_used) * sc > 8.f;
       if (j > 0 && __any_sync(0xffffffffu, need)) {
@@ -242,35 +237,35 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
       }
       if (need) m_used = mx;
       const float ms = m_used * sc;
-      // ---- pass 2: P = exp2(S*scale - m) -> fp16 -> swizzled shared memory (A operand of the P V MMA)
-#pragma unroll 1
-      for (int c0 = 0; c0 < BKV; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(s_addr + c0, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
+      // ---- P = exp2(S*scale - m) -> fp16 -> swizzled shared memory (A operand of the P V MMA); exp(-inf) = 0 masks
+      float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-        for (int t = 0; t < 32; t += 2) {
-          float e0 = fast_exp2(__uint_as_float(v[t]) * sc - ms);
-          float e1 = fast_exp2(__uint_as_float(v[t + 1]) * sc - ms);
-          if (tail) {
-            if (kbase + c0 + t >= p.nk) e0 = 0.f;
-            if (kbase + c0 + t + 1 >= p.nk) e1 = 0.f;
+      for (int c8 = 0; c8 < BKV / 8; ++c8) {       // one 16-byte chunk (8 keys) at a time
+        uint32_t pk[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float a0 = __uint_as_float(sv[c8 * 8 + 2 * u]) * sc - ms;
+          const float a1 = __uint_as_float(sv[c8 * 8 + 2 * u + 1]) * sc - ms;
+          __half2 h;
+          if (EXP16) {   // packed fp16 exponential: one MUFU op per two probabilities (P is fp16 anyway)
+            const __half2 a = __floats2half2_rn(a0, a1);
+            uint32_t r;
+            asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(*reinterpret_cast<const uint32_t*>(&a)));
+            h = *reinterpret_cast<const __half2*>(&r);
+          } else {
+            h = __floats2half2_rn(fast_exp2(a0), fast_exp2(a1));
           }
-          const __half2 h = __floats2half2_rn(e0, e1);
           const float2 back = __half22float2(h);
-          l += back.x + back.y;
-          pk[t / 2] = *reinterpret_cast<const uint32_t*>(&h);
+          l0 += back.x;
+          l1 += back.y;
+          pk[u] = *reinterpret_cast<const uint32_t*>(&h);
         }
-        const int cb = c0 / 64;
-        const int ch0 = (c0 % 64) / 8;           // first 16-byte chunk of this 32-column slab inside the 128-B row
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const uint32_t dst = p_row + cb * (TQ * 128) + (((ch0 + t) ^ (row & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pk[4 * t]), "r"(pk[4 * t + 1]),
-                       "r"(pk[4 * t + 2]), "r"(pk[4 * t + 3]) : "memory");
-        }
+        const int cb = c8 / 8, ch = c8 % 8;        // 64-key column block, 16-byte chunk inside the 128-byte row
+        const uint32_t dst = p_row + cb * (TQ * 128) + ((ch ^ (row & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
+                     : "memory");
       }
+      l += l0 + l1;
       fence_proxy_async();                       // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       tc_fence_before();
       mbar_arrive(p_full(i));
@@ -309,13 +304,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
   }
 }
 
-template <int D, int BKV>
+template <int D, int BKV, bool EXP16>
 int launch(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv, __half* o, int ldo,
            int batch, int nq, int nk, int heads, long long q_bs, long long kv_bs, long long o_bs, int kv_div) {
   using C = TCfg<D, BKV>;
   static bool configured = false;
   if (!configured) {
-    VS_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    VS_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D, BKV, EXP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     configured = true;
   }
   TAttnArgs a;
@@ -339,7 +334,7 @@ int launch(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, 
   a.scale_log2 = 1.4426950408889634f / sqrtf((float)D);
   dim3 grid((nq + 2 * TQ - 1) / (2 * TQ), heads, batch);
   ProfScope prof(st, PC_ATTN, 4.0 * batch * heads * (double)nq * nk * D);
-  attn_tc_kernel<D, BKV><<<grid, ATT_THREADS, C::SMEM, st>>>(a);
+  attn_tc_kernel<D, BKV, EXP16><<<grid, ATT_THREADS, C::SMEM, st>>>(a);
   VS_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -352,8 +347,15 @@ int attention_tc(cudaStream_t st, const __half* q, int ldq, const __half* k, int
                  int kv_div) {
   if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8)) return -1;
   if ((q_bs % 8) || (kv_bs % 8)) return -1;
-  if (d == 40) return launch<40, 128>(st, q, ldq, k, ldk, v, ldv, o, ldo, batch, nq, nk, heads, q_bs, kv_bs, o_bs, kv_div);
-  if (d == 80) return launch<80, 64>(st, q, ldq, k, ldk, v, ldv, o, ldo, batch, nq, nk, heads, q_bs, kv_bs, o_bs, kv_div);
+  const bool e16 = get_option("attn_exp16") != 0;
+  if (d == 40) {
+    return e16 ? launch<40, 128, true>(st, q, ldq, k, ldk, v, ldv, o, ldo, batch, nq, nk, heads, q_bs, kv_bs, o_bs, kv_div)
+               : launch<40, 128, false>(st, q, ldq, k, ldk, v, ldv, o, ldo, batch, nq, nk, heads, q_bs, kv_bs, o_bs, kv_div);
+  }
+  if (d == 80) {
+    return e16 ? launch<80, 64, true>(st, q, ldq, k, ldk, v, ldv, o, ldo, batch, nq, nk, heads, q_bs, kv_bs, o_bs, kv_div)
+               : launch<80, 64, false>(st, q, ldq, k, ldk, v, ldv, o, ldo, batch, nq, nk, heads, q_bs, kv_bs, o_bs, kv_div);
+  }
   return -1;
 }
 

@@ -1,11 +1,17 @@
 // tcgen05 / TMEM / TMA GEMM and implicit-GEMM 3x3 convolution for sm_100a.
 //
 // One persistent, warp-specialised kernel:  warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected thread),
-// warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM -> registers -> fused bias/temb/residual/GEGLU -> HBM).
-// Tiles are 128 (M) x BN (N) x 64 (K, one 128-byte swizzle row of fp16); accumulators are double-buffered in TMEM so
-// the epilogue of tile i overlaps the MMAs of tile i+1.  A 3x3 convolution is the same kernel with nine K segments:
-// tap (dy,dx) loads the NHWC activation box shifted by (dy,dx) through a 4-D TMA descriptor and the out-of-bounds
-// zero fill of TMA provides the padding; a channel concat is two descriptors walked back to back along K.
+// warp 2 = TMEM allocator, warps 4..7 = epilogue.  Tiles are 128 (M) x BN (N) x 64 (K, one 128-byte swizzle row of
+// fp16); accumulators are double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
+// A 3x3 convolution is the same kernel with nine K segments: tap (dy,dx) loads the NHWC activation box shifted by
+// (dy,dx) through a 4-D TMA descriptor and the out-of-bounds zero fill of TMA provides the padding; a channel concat
+// is two descriptors walked back to back along K.
+//
+// Epilogue (v2): TMEM -> registers (thread = output row) -> fused bias / time-embedding row vector / residual / GEGLU ->
+// fp16 -> 64-byte-swizzled shared-memory sub-tile (128 rows x 32 columns) -> TMA store.  The residual sub-tile arrives
+// by TMA load into a second swizzled buffer.  HBM therefore only sees full-line bulk transfers (the v1 epilogue wrote
+// 32-byte pieces per thread and was 4-8x off the HBM roofline for the small-K GEMMs).  Tiny-N outputs (conv_out, N=4)
+// keep the direct-store path.
 //
 // Replaces (reference call sites): InflatedConv3d 3x3 / 1x1 (models/animatediff_models/resnet.py:9-18), every
 // nn.Linear / 1x1 conv of Transformer3DModel (attention.py:65-93,174-204) and the motion module
@@ -20,11 +26,16 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;                   // 4 control warps + 2 epilogue warpgroups
 constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int EPI_COLS = 32;                        // output columns per epilogue sub-tile (64 B of fp16: SWIZZLE_64B)
+constexpr int EPI_BUF_BYTES = BM * EPI_COLS * 2;    // 8 KB
+constexpr int EPI_OUT_BUFS = 3, EPI_RES_BUFS = 2;   // per epilogue warpgroup
+constexpr int EPI_GROUP_BYTES = (EPI_OUT_BUFS + EPI_RES_BUFS) * EPI_BUF_BYTES;
+constexpr int EPI_BYTES = 2 * EPI_GROUP_BYTES;      // two warpgroups
 
 struct GemmParams {
-  CUtensorMap tmA, tmA2, tmB;
+  CUtensorMap tmA, tmA2, tmB, tmC, tmR;
   int M, N;
   int num_kb;        // total K blocks
   int kb_per_tap;    // K blocks per tap (both concat sources)
@@ -42,31 +53,40 @@ struct GemmParams {
   __half* out;
   int ldc;
   int mode;
+  int tma_epi;       // 1 = smem-staged TMA-store epilogue
 };
 
 template <int BN>
 struct Cfg {
   static constexpr int B_STAGE_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (SMEM_LIMIT - 2048) / STAGE_BYTES > 8 ? 8 : (SMEM_LIMIT - 2048) / STAGE_BYTES;
+  static constexpr int STAGES_RAW = (SMEM_LIMIT - 2048 - EPI_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(2 * BN <= 512, "two accumulator stages must fit TMEM");
   static_assert(B_STAGE_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment for SWIZZLE_128B");
+  static_assert(STAGES >= 3, "pipeline too shallow");
 };
+
+__device__ __forceinline__ uint32_t sw64_off(int row, int chunk) {   // byte offset inside a [128 x 64 B] SWIZZLE_64B tile
+  return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+}
 
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + C::STAGES * C::STAGE_BYTES;
-  // barrier layout: full[S], empty[S], tmem_full[2], tmem_empty[2], then the TMEM base address word
+  const uint32_t epi_base = smem_base + C::STAGES * C::STAGE_BYTES;       // out0 | out1 | res0 | res1
+  const uint32_t bar_base = epi_base + EPI_BYTES;
+  // barrier layout: full[S], empty[S], tmem_full[2], tmem_empty[2], res_full[2], then the TMEM base address word
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 4);
+  auto rfull_bar = [&](int grp, int a) { return bar_base + 8u * (2 * C::STAGES + 4 + grp * 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 8);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
@@ -77,6 +97,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     prefetch_tmap(&p.tmA);
     prefetch_tmap(&p.tmB);
     if (p.kb_src1 < p.kb_per_tap) prefetch_tmap(&p.tmA2);
+    if (p.tma_epi) {
+      prefetch_tmap(&p.tmC);
+      if (p.residual) prefetch_tmap(&p.tmR);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -85,7 +109,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128);
+      mbar_init(tempty_bar(a), 256);
+      mbar_init(rfull_bar(0, a), 1);
+      mbar_init(rfull_bar(1, a), 1);
     }
     fence_barrier_init();
   }
@@ -162,17 +188,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     // =================================================================== epilogue
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;          // row of the tile handled by this thread
-    uint32_t t = 0;
+    const int grp = (warp - 4) >> 2;        // epilogue warpgroup: sub-tile s of a tile is handled by group s % 2
+    const bool leader = (threadIdx.x & 127) == 0;
+    const bool has_res = p.residual != nullptr;
+    const uint32_t grp_base = epi_base + grp * EPI_GROUP_BYTES;   // out0 | out1 | out2 | res0 | res1
+    uint32_t t = 0, g = 0;                  // tile counter, sub-tiles processed by this group (staging-buffer rotation)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
       const int m_tile = tile / p.n_tiles, n_tile = tile % p.n_tiles;
       const int acc = t & 1;
       const uint32_t aph = (t >> 1) & 1;
       long long pix;
       bool valid;
+      int x0 = 0, y0 = 0, i0 = 0;
       if (p.a_rank == 4) {
-        const int x0 = (m_tile % p.tiles_x) * p.TW;
-        const int y0 = ((m_tile / p.tiles_x) % p.tiles_y) * p.TH;
-        const int i0 = (m_tile / (p.tiles_x * p.tiles_y)) * p.TN;
+        x0 = (m_tile % p.tiles_x) * p.TW;
+        y0 = ((m_tile / p.tiles_x) % p.tiles_y) * p.TH;
+        i0 = (m_tile / (p.tiles_x * p.tiles_y)) * p.TN;
         const int per_img = p.TH * p.TW;
         const int ti = row / per_img, rem = row - ti * per_img;
         const int y = y0 + rem / p.TW, x = x0 + rem % p.TW, img = i0 + ti;
@@ -189,7 +220,102 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
 
-      if (p.mode == EPI_LINEAR) {
+      if (p.tma_epi) {
+        // ------------------------------------------------------------ v2: staged, TMA-stored sub-tiles
+        const bool geglu = p.mode == EPI_GEGLU;
+        const int oc0 = geglu ? n_tile * (BN / 2) : n0;                    // first output column of this tile
+        const int ocols = geglu ? BN / 2 : ((p.N - n0) < BN ? (p.N - n0) : BN);
+        const int nsub = ocols / EPI_COLS;
+        auto load_res = [&](int s, int buf) {
+          mbar_expect_tx(rfull_bar(grp, buf), EPI_BUF_BYTES);
+          const uint32_t dst = grp_base + (EPI_OUT_BUFS + buf) * EPI_BUF_BYTES;
+          if (p.a_rank == 4) tma_load_4d(dst, &p.tmR, rfull_bar(grp, buf), oc0 + s * EPI_COLS, x0, y0, i0);
+          else tma_load_2d(dst, &p.tmR, rfull_bar(grp, buf), oc0 + s * EPI_COLS, m_tile * BM);
+        };
+        if (leader && has_res) {
+          if (grp < nsub) load_res(grp, g & 1);
+          if (grp + 2 < nsub) load_res(grp + 2, (g + 1) & 1);
+        }
+#pragma unroll 1
+        for (int s = grp; s < nsub; s += 2, ++g) {
+          const int buf = g & 1;               // residual staging buffer
+          float f[32];
+          {
+            uint32_t v[32];
+            tmem_ld32(taddr + (geglu ? s * EPI_COLS : s * EPI_COLS), v);
+            if (geglu) {
+              uint32_t gt[32];
+              tmem_ld32(taddr + BN / 2 + s * EPI_COLS, gt);
+              tmem_ld_wait();
+              const float* bv = p.bias + n0 + s * EPI_COLS;
+              const float* bg = p.bias + n0 + BN / 2 + s * EPI_COLS;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                f[j] = (__uint_as_float(v[j]) + __ldg(bv + j)) * gelu_erf_fast(__uint_as_float(gt[j]) + __ldg(bg + j));
+            } else {
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+              const int n = n0 + s * EPI_COLS;
+              if (p.bias) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+                  f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+                }
+              }
+              if (rv) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(rv + n + j));
+                  f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+                }
+              }
+            }
+          }
+          if (has_res) {
+            mbar_wait(rfull_bar(grp, buf), (g >> 1) & 1);
+            const uint32_t rb = grp_base + (EPI_OUT_BUFS + buf) * EPI_BUF_BYTES;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint32_t r0, r1, r2, r3;
+              asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                           : "r"(rb + sw64_off(row, c)));
+              const uint32_t rr[4] = {r0, r1, r2, r3};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&rr[u]));
+                f[c * 8 + 2 * u] += h.x;
+                f[c * 8 + 2 * u + 1] += h.y;
+              }
+            }
+          }
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const __half2 h = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+            pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          // Output staging rotates over three buffers: buffer g % 3 was last handed to a TMA store at sub-tile g - 3, and
+          // the leader's wait_group.read(1) before the barrier of sub-tile g - 1 guaranteed that store had drained, so one
+          // barrier per sub-tile suffices.
+          const uint32_t ob = grp_base + (g % EPI_OUT_BUFS) * EPI_BUF_BYTES;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(ob + sw64_off(row, c)), "r"(pk[4 * c]),
+                         "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
+          fence_proxy_async();
+          if (leader) tma_store_wait_read<1>();
+          named_bar_sync(1 + grp, 128);
+          if (leader) {
+            if (p.a_rank == 4) tma_store_4d(&p.tmC, ob, oc0 + s * EPI_COLS, x0, y0, i0);
+            else tma_store_2d(&p.tmC, ob, oc0 + s * EPI_COLS, m_tile * BM);
+            tma_store_commit();
+            if (has_res && s + 4 < nsub) load_res(s + 4, buf);
+          }
+        }
+      } else if (p.mode == EPI_LINEAR && grp == 0) {
+        // ------------------------------------------------------------ v1: direct stores (tiny / unaligned N)
         __half* orow = p.out + pix * p.ldc;
         const __half* rrow = p.residual ? p.residual + pix * p.ldr : nullptr;
 #pragma unroll 1
@@ -200,89 +326,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           tmem_ld_wait();
           if (!valid) continue;
           const int n = n0 + c0;
-          if (n + 16 <= p.N && (p.ldc & 7) == 0) {
-            float f[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-            if (p.bias) {
-#pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
-                f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-              }
-            }
-            if (rv) {
-#pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(rv + n + j));
-                f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-              }
-            }
-            if (rrow) {
-              const uint4 r0 = *reinterpret_cast<const uint4*>(rrow + n);
-              const uint4 r1 = *reinterpret_cast<const uint4*>(rrow + n + 8);
-              const __half2* h0 = reinterpret_cast<const __half2*>(&r0);
-              const __half2* h1 = reinterpret_cast<const __half2*>(&r1);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 a = __half22float2(h0[j]);
-                const float2 b = __half22float2(h1[j]);
-                f[2 * j] += a.x; f[2 * j + 1] += a.y;
-                f[8 + 2 * j] += b.x; f[8 + 2 * j + 1] += b.y;
-              }
-            }
-            uint4 o0, o1;
-            __half2* p0 = reinterpret_cast<__half2*>(&o0);
-            __half2* p1 = reinterpret_cast<__half2*>(&o1);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              p0[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
-              p1[j] = __floats2half2_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
-            }
-            *reinterpret_cast<uint4*>(orow + n) = o0;
-            *reinterpret_cast<uint4*>(orow + n + 8) = o1;
-          } else {
-            for (int j = 0; j < 16 && n + j < p.N; ++j) {
-              float f = __uint_as_float(v[j]);
-              if (p.bias) f += p.bias[n + j];
-              if (rv) f += rv[n + j];
-              if (rrow) f += __half2float(rrow[n + j]);
-              orow[n + j] = __float2half_rn(f);
-            }
+          for (int j = 0; j < 16 && n + j < p.N; ++j) {
+            float f = __uint_as_float(v[j]);
+            if (p.bias) f += p.bias[n + j];
+            if (rv) f += rv[n + j];
+            if (rrow) f += __half2float(rrow[n + j]);
+            orow[n + j] = __float2half_rn(f);
           }
-        }
-      } else {  // EPI_GEGLU: columns [0, BN/2) = value, [BN/2, BN) = gate of hidden slice n_tile*BN/2 ...
-        constexpr int HALF = BN / 2;
-        __half* orow = p.out + pix * p.ldc + (long long)n_tile * HALF;
-#pragma unroll 1
-        for (int c0 = 0; c0 < HALF; c0 += 16) {
-          uint32_t a[16], g[16];
-          tmem_ld16(taddr + c0, a);
-          tmem_ld16(taddr + HALF + c0, g);
-          tmem_ld_wait();
-          if (!valid) continue;
-          float f[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float val = __uint_as_float(a[j]) + __ldg(p.bias + n0 + c0 + j);
-            const float gate = __uint_as_float(g[j]) + __ldg(p.bias + n0 + HALF + c0 + j);
-            f[j] = val * gelu_erf_f(gate);
-          }
-          uint4 o0, o1;
-          __half2* p0 = reinterpret_cast<__half2*>(&o0);
-          __half2* p1 = reinterpret_cast<__half2*>(&o1);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            p0[j] = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
-            p1[j] = __floats2half2_rn(f[8 + 2 * j], f[8 + 2 * j + 1]);
-          }
-          *reinterpret_cast<uint4*>(orow + c0) = o0;
-          *reinterpret_cast<uint4*>(orow + c0 + 8) = o1;
         }
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
     }
+    if (leader && p.tma_epi) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -313,7 +369,7 @@ ConvTile pick_conv_tile(int nimg, int H, int W) {
 }
 
 template <int BN>
-int launch(cudaStream_t st, GemmParams& p, int geglu) {
+int launch(cudaStream_t st, GemmParams& p) {
   using C = Cfg<BN>;
   static bool configured = false;
   if (!configured) {
@@ -325,6 +381,20 @@ int launch(cudaStream_t st, GemmParams& p, int geglu) {
   gemm_tc_kernel<BN><<<grid, GEMM_THREADS, C::SMEM_BYTES, st>>>(p);
   VS_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+// 2-D (plain rows) or 4-D (NHWC pixel box) descriptor over an output-side tensor with `cols` columns, row pitch `ld`.
+int make_epi_tmap(CUtensorMap* tm, const __half* base, int cols, int ld, const GemmParams& p) {
+  if (p.a_rank == 4) {
+    const uint64_t dims[4] = {(uint64_t)cols, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.nimg};
+    const uint64_t str[3] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * p.W, (uint64_t)ld * 2 * p.W * p.H};
+    const uint32_t box[4] = {EPI_COLS, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
+    return make_tmap_f16(tm, base, 4, dims, str, box, 2);
+  }
+  const uint64_t dims[2] = {(uint64_t)cols, (uint64_t)p.M};
+  const uint64_t str[1] = {(uint64_t)ld * 2};
+  const uint32_t box[2] = {EPI_COLS, BM};
+  return make_tmap_f16(tm, base, 2, dims, str, box, 2);
 }
 
 }  // namespace
@@ -359,7 +429,7 @@ int gemm_tc(cudaStream_t st, const GemmArgs& a) {
   if (a.mode == EPI_GEGLU) {
     bn = 2 * kGegluGranule;
     VS_REQUIRE(a.N % bn == 0, "gemm_tc: GEGLU needs N %% %d == 0 (N=%d)", bn, a.N);
-    VS_REQUIRE(a.bias != nullptr, "gemm_tc: GEGLU needs a bias");
+    VS_REQUIRE(a.bias != nullptr && a.residual == nullptr && a.rowvec == nullptr, "gemm_tc: GEGLU takes a bias only");
   } else if (bn == 0) {
     if (a.N <= 64) bn = 64;
     else if (a.N % 160 == 0) bn = 160;
@@ -380,12 +450,12 @@ int gemm_tc(cudaStream_t st, const GemmArgs& a) {
     {
       const uint64_t dims[4] = {(uint64_t)a.K1, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.nimg};
       const uint64_t str[3] = {(uint64_t)a.lda1 * 2, (uint64_t)a.lda1 * 2 * a.W, (uint64_t)a.lda1 * 2 * a.W * a.H};
-      if (make_tmap_f16(&p.tmA, a.A, 4, dims, str, box, true)) return 3;
+      if (make_tmap_f16(&p.tmA, a.A, 4, dims, str, box, 1)) return 3;
     }
     if (two) {
       const uint64_t dims[4] = {(uint64_t)a.K2, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.nimg};
       const uint64_t str[3] = {(uint64_t)a.lda2 * 2, (uint64_t)a.lda2 * 2 * a.W, (uint64_t)a.lda2 * 2 * a.W * a.H};
-      if (make_tmap_f16(&p.tmA2, a.A2, 4, dims, str, box, true)) return 3;
+      if (make_tmap_f16(&p.tmA2, a.A2, 4, dims, str, box, 1)) return 3;
     }
   } else {
     p.a_rank = 2;
@@ -394,25 +464,35 @@ int gemm_tc(cudaStream_t st, const GemmArgs& a) {
     {
       const uint64_t dims[2] = {(uint64_t)a.K1, (uint64_t)a.M};
       const uint64_t str[1] = {(uint64_t)a.lda1 * 2};
-      if (make_tmap_f16(&p.tmA, a.A, 2, dims, str, box, true)) return 3;
+      if (make_tmap_f16(&p.tmA, a.A, 2, dims, str, box, 1)) return 3;
     }
     if (two) {
       const uint64_t dims[2] = {(uint64_t)a.K2, (uint64_t)a.M};
       const uint64_t str[1] = {(uint64_t)a.lda2 * 2};
-      if (make_tmap_f16(&p.tmA2, a.A2, 2, dims, str, box, true)) return 3;
+      if (make_tmap_f16(&p.tmA2, a.A2, 2, dims, str, box, 1)) return 3;
     }
   }
   {
     const uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)a.N};
     const uint64_t str[1] = {(uint64_t)Ktot * 2};
     const uint32_t box[2] = {BK, (uint32_t)bn};
-    if (make_tmap_f16(&p.tmB, a.Bw, 2, dims, str, box, true)) return 3;
+    if (make_tmap_f16(&p.tmB, a.Bw, 2, dims, str, box, 1)) return 3;
+  }
+  // staged TMA-store epilogue whenever the output geometry allows it (16-byte strides, whole 32-column sub-tiles)
+  const int out_cols = (a.mode == EPI_GEGLU) ? a.N / 2 : a.N;
+  p.tma_epi = (out_cols % EPI_COLS == 0) && (a.ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0) &&
+              (!a.residual || ((a.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.residual) & 15) == 0)));
+  if (p.tma_epi) {
+    if (make_epi_tmap(&p.tmC, a.out, out_cols, a.ldc, p)) return 3;
+    if (a.residual && make_epi_tmap(&p.tmR, a.residual, out_cols, a.ldr, p)) return 3;
+  } else {
+    VS_REQUIRE(a.mode == EPI_LINEAR, "gemm_tc: GEGLU output must be TMA-storable");
   }
   ProfScope prof(st, a.taps == 9 ? PC_CONV : PC_GEMM, 2.0 * a.M * (double)a.N * Ktot);
   switch (bn) {
-    case 64: return launch<64>(st, p, 0);
-    case 128: return launch<128>(st, p, 0);
-    default: return launch<160>(st, p, 0);
+    case 64: return launch<64>(st, p);
+    case 128: return launch<128>(st, p);
+    default: return launch<160>(st, p);
   }
 }
 

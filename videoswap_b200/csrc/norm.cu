@@ -45,8 +45,7 @@ __global__ void gn_stats_kernel(const GnParams p) {
   const long long p0 = (long long)blockIdx.x * p.pix_per_block;
   const long long p1 = min(p0 + p.pix_per_block, p.pix_per_set);
   const long long base = (long long)set * p.pix_per_set;
-  for (long long i = p0 + r; i < p1; i += p.rows_per_block) {
-    const uint4 v = gn_load(p, base + i, cv);
+  auto accum = [&](const uint4& v) {
     const __half2* h = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -54,7 +53,15 @@ __global__ void gn_stats_kernel(const GnParams p) {
       if (2 * j < split) { sa += f.x; qa += f.x * f.x; } else { sb += f.x; qb += f.x * f.x; }
       if (2 * j + 1 < split) { sa += f.y; qa += f.y * f.y; } else { sb += f.y; qb += f.y * f.y; }
     }
+  };
+  long long i = p0 + r;
+  const long long step = p.rows_per_block;
+  for (; i + 3 * step < p1; i += 4 * step) {       // 4 independent 16-byte loads in flight per thread
+    const uint4 v0 = gn_load(p, base + i, cv), v1 = gn_load(p, base + i + step, cv);
+    const uint4 v2 = gn_load(p, base + i + 2 * step, cv), v3 = gn_load(p, base + i + 3 * step, cv);
+    accum(v0); accum(v1); accum(v2); accum(v3);
   }
+  for (; i < p1; i += step) accum(gn_load(p, base + i, cv));
   atomicAdd(&sh[ga * 2], sa);
   atomicAdd(&sh[ga * 2 + 1], qa);
   if (gb != ga) {
@@ -84,8 +91,7 @@ __global__ void gn_apply_kernel(const GnParams p) {
   const long long p0 = (long long)blockIdx.x * p.pix_per_block;
   const long long p1 = min(p0 + p.pix_per_block, p.pix_per_set);
   const long long base = (long long)set * p.pix_per_set;
-  for (long long i = p0 + r; i < p1; i += p.rows_per_block) {
-    const uint4 v = gn_load(p, base + i, cv);
+  auto apply = [&](const uint4& v, long long pix) {
     const __half2* h = reinterpret_cast<const __half2*>(&v);
     uint4 o;
     __half2* oh = reinterpret_cast<__half2*>(&o);
@@ -96,8 +102,16 @@ __global__ void gn_apply_kernel(const GnParams p) {
       if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
       oh[j] = __floats2half2_rn(y0, y1);
     }
-    *reinterpret_cast<uint4*>(p.out + (base + i) * p.C + cv * 8) = o;
+    *reinterpret_cast<uint4*>(p.out + pix * p.C + cv * 8) = o;
+  };
+  long long i = p0 + r;
+  const long long step = p.rows_per_block;
+  for (; i + 3 * step < p1; i += 4 * step) {
+    const uint4 v0 = gn_load(p, base + i, cv), v1 = gn_load(p, base + i + step, cv);
+    const uint4 v2 = gn_load(p, base + i + 2 * step, cv), v3 = gn_load(p, base + i + 3 * step, cv);
+    apply(v0, base + i); apply(v1, base + i + step); apply(v2, base + i + 2 * step); apply(v3, base + i + 3 * step);
   }
+  for (; i < p1; i += step) apply(gn_load(p, base + i, cv), base + i);
 }
 
 int gn_fill(GnParams& p, dim3& grid, int& threads, const __half* x1, int c1, const __half* x2, int c2, int nimg, int hw,
@@ -189,6 +203,80 @@ __global__ void ln_kernel(const __half* __restrict__ x, int rows, int C, const f
   }
 }
 
+// Fast path for C = 40 * LPR (320 / 640 / 1280): LPR lanes share a row, every lane owns five 16-byte vectors, so a
+// warp normalises 32/LPR rows at once with all lanes busy; persistent grid-stride over row groups; gamma/beta live in
+// registers as packed fp16 (they are fp16 model weights, so this is exact).
+template <int LPR>
+__global__ void __launch_bounds__(256) ln5_kernel(const __half* __restrict__ x, long long rows, const float* __restrict__ gamma,
+                                                  const float* __restrict__ beta, const float* __restrict__ pe, int hw, int F,
+                                                  __half* __restrict__ out) {
+  constexpr int C = LPR * 40, RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane % LPR, rw = lane / LPR;
+  __half2 g2[5][4], b2[5][4];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const int c = (sub + i * LPR) * 8;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      g2[i][j] = __floats2half2_rn(gamma[c + 2 * j], gamma[c + 2 * j + 1]);
+      b2[i][j] = __floats2half2_rn(beta[c + 2 * j], beta[c + 2 * j + 1]);
+    }
+  }
+  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r0 = warp_global * RPW; r0 < rows; r0 += nwarps * RPW) {
+    const long long row = r0 + rw;
+    const bool active = row < rows;
+    const __half* xr = x + (active ? row : 0) * C;
+    uint4 v[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) v[i] = *reinterpret_cast<const uint4*>(xr + (sub + i * LPR) * 8);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); s += f.x + f.y; }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        q += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+      }
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * (1.f / C) + 1e-5f);
+    if (!active) continue;
+    const float* per = pe ? pe + (long long)((row / hw) % F) * C : nullptr;
+    __half* orow = out + row * C;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const int c = (sub + i * LPR) * 8;
+      const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
+      uint4 o;
+      __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        const float2 gg = __half22float2(g2[i][j]), bb = __half22float2(b2[i][j]);
+        float y0 = (f.x - mean) * rstd * gg.x + bb.x;
+        float y1 = (f.y - mean) * rstd * gg.y + bb.y;
+        if (per) { y0 += per[c + 2 * j]; y1 += per[c + 2 * j + 1]; }
+        oh[j] = __floats2half2_rn(y0, y1);
+      }
+      *reinterpret_cast<uint4*>(orow + c) = o;
+    }
+  }
+}
+
 }  // namespace
 
 int groupnorm_stats(cudaStream_t st, const __half* x1, int c1, const __half* x2, int c2, int nimg, int hw,
@@ -229,6 +317,17 @@ int layernorm(cudaStream_t st, const __half* x, int rows, int C, const float* ga
   if (hw <= 0) hw = 1;
   if (F <= 0) F = 1;
   ProfScope prof(st, PC_LAYERNORM, 4.0 * rows * (double)C);
+  if (C == 320 || C == 640 || C == 1280) {
+    const int lpr = C / 40, rpw = 32 / lpr;
+    long long need = ((long long)rows + rpw * 8 - 1) / (rpw * 8);     // blocks of 8 warps
+    const long long cap = (long long)num_sms() * 8;
+    const int grid = (int)(need < cap ? need : cap);
+    if (lpr == 8) ln5_kernel<8><<<grid, 256, 0, st>>>(x, rows, gamma, beta, pe, hw, F, out);
+    else if (lpr == 16) ln5_kernel<16><<<grid, 256, 0, st>>>(x, rows, gamma, beta, pe, hw, F, out);
+    else ln5_kernel<32><<<grid, 256, 0, st>>>(x, rows, gamma, beta, pe, hw, F, out);
+    VS_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   switch (vpl) {
     case 1: ln_kernel<1><<<blocks, threads, 0, st>>>(x, rows, C, gamma, beta, pe, hw, F, out); break;
     case 2: ln_kernel<2><<<blocks, threads, 0, st>>>(x, rows, C, gamma, beta, pe, hw, F, out); break;

@@ -38,7 +38,7 @@ static EncodeTiledFn get_encode() {
 }
 
 int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box, bool swizzle128) {
+                  const uint32_t* box, int swizzle) {
   EncodeTiledFn enc = get_encode();
   VS_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   VS_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base address must be 16-byte aligned");
@@ -58,7 +58,9 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
     VS_REQUIRE(bx[i] >= 1 && bx[i] <= 256, "TMA box dim %d = %u out of range", i, bx[i]);
   }
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B
+                   : swizzle == 3 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u)",
              (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
@@ -110,14 +112,16 @@ ProfScope::~ProfScope() {
   if (idx_ >= 0) cudaEventRecord(g_prof[idx_].b, st_);
 }
 
-static int g_opt_attn_tc = 1;
+static int g_opt_attn_tc = 1, g_opt_attn_exp16 = 0;
 int set_option(const char* name, int value) {
   if (strcmp(name, "attn_tc") == 0) { g_opt_attn_tc = value; return 0; }
+  if (strcmp(name, "attn_exp16") == 0) { g_opt_attn_exp16 = value; return 0; }
   set_error("unknown option '%s'", name);
   return 2;
 }
 int get_option(const char* name) {
   if (strcmp(name, "attn_tc") == 0) return g_opt_attn_tc;
+  if (strcmp(name, "attn_exp16") == 0) return g_opt_attn_exp16;
   return 0;
 }
 
