@@ -246,6 +246,9 @@ CHECKS = {
     "gemm_small_m": lambda: check_gemm(77, 640, 768),
     "gemm_big_k": lambda: check_gemm(256, 320, 5120),
     "gemm_many_tiles": lambda: check_gemm(128 * 150 + 5, 320, 64),
+    "gemm_wres_qkv": lambda: check_gemm(40000, 960, 320, residual=True, seed=5),      # weight-stationary mode
+    "gemm_wres_k64": lambda: check_gemm(128 * 300 + 77, 640, 64, bias=False, seed=6),
+    "geglu_wres": lambda: check_geglu(M=20000, C=320, seed=31),
     "gemm_concat": check_gemm_concat,
     "gemm_rowvec": check_gemm_rowvec,
     "geglu": check_geglu,

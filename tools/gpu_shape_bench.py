@@ -79,12 +79,11 @@ def main():
         res[f"attn_L{li}"] = {"ms": ms, "tflops": fl / ms / 1e9, "count": [5, 5, 5, 1][li], "ms_total": ms * [5, 5, 5, 1][li]}
         print(f"attn_L{li}", res[f"attn_L{li}"], flush=True)
         if li < 2:
-            for opt, tag in (("attn_exp16", "exp16"), ("attn_tc", "mma")):
-                ops.set_option(opt, 1 if opt == "attn_exp16" else 0)
-                ms2 = timeit(lambda: ops.attention(q, k, v, 8))
-                ops.set_option(opt, 0 if opt == "attn_exp16" else 1)
-                res[f"attn_L{li}_{tag}"] = {"ms": ms2, "tflops": fl / ms2 / 1e9}
-                print(f"attn_L{li}_{tag}", res[f"attn_L{li}_{tag}"], flush=True)
+            ops.set_option("attn_tc", 0)
+            ms2 = timeit(lambda: ops.attention(q, k, v, 8))
+            ops.set_option("attn_tc", 1)
+            res[f"attn_L{li}_mma"] = {"ms": ms2, "tflops": fl / ms2 / 1e9}
+            print(f"attn_L{li}_mma", res[f"attn_L{li}_mma"], flush=True)
         kv = torch.randn(2, 77, 2 * C, device=DEV).half()
         qq = torch.randn(NI, hw, C, device=DEV).half()
         ms = timeit(lambda: ops.attention(qq, kv[..., :C], kv[..., C:], 8, kv_div=16))

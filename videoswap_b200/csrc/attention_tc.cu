@@ -1,16 +1,18 @@
 // tcgen05 / TMEM flash attention for sm_100a (spatial self-attention N x N and cross-attention N x 77; d = 40 / 80).
 //
-// One CTA = (batch, head, 256 queries) = two 128-query tiles that ping-pong against the tensor core:
+// One CTA = (batch, head, 256 queries) = two 128-query tiles, each owned by one softmax warpgroup:
 //   warp 0      TMA producer: Q once (4-D descriptor [d, head, token, batch]; head dim 40 is zero-padded to 64 by TMA
-//               out-of-bounds fill), then a ring of K / V tiles
+//               out-of-bounds fill), then a ring of 64-key K / V tiles
 //   warp 1      single-thread tcgen05.mma issuer:  S_i = Q_i K^T  (K-major x K-major, fp32 in TMEM)
 //                                                  O_i += P_i V   (P from shared memory, V as MN-major B operand)
 //   warp 2      TMEM allocator
 //   warps 4-7   softmax warpgroup of query tile 0 (thread = one query row, reads S with tcgen05.ld)
 //   warps 8-11  softmax warpgroup of query tile 1
-// The softmax keeps a *stale* running maximum and only rescales O (tcgen05.ld/st round trip) when the true maximum has
-// grown by more than 2^8, so the rescale is off the critical path after the first few key tiles.  exp2 is evaluated in
-// fp32 (v1) and P is written to shared memory in the 128-byte-swizzled K-major layout the MMA consumes.
+// S is DOUBLE-BUFFERED per query tile in TMEM and the issuer runs Q K^T two key tiles ahead, so a softmax warpgroup
+// never waits for a tensor-core round trip: it goes from the exponentials of tile j straight to tile j+1 (the kernel is
+// bound by the 16 ex2/clk/SM MUFU rate at d = 40, not by the MMAs -- see DESIGN.md).  The softmax keeps a *stale*
+// running maximum and only rescales O (tcgen05.ld/st round trip) when the true maximum grew by more than 2^8.
+// P is written to shared memory in the 128-byte-swizzled K-major layout the MMA consumes.
 //
 // Replaces diffusers AttnProcessor2_0 / EDLoRA_AttnProcessor.__call__ (reference utils/edlora_util.py:47-65,
 // models/animatediff_models/attention.py:229-241).
@@ -21,24 +23,24 @@ namespace vs {
 namespace {
 
 constexpr int TQ = 128;              // queries per tile (= UMMA M)
+constexpr int BKV = 64;              // keys per tile (one 128-byte swizzle row of P)
 constexpr int ATT_THREADS = 384;
 
-template <int D, int BKV>
+template <int D>
 struct TCfg {
   static constexpr int NCB = (D + 63) / 64;            // 64-wide (128-byte) column blocks of Q/K/V tiles
   static constexpr int DPK = (D + 15) / 16 * 16;       // padded contraction length of Q K^T
   static constexpr int DPO = (D + 15) / 16 * 16;       // N of the P V MMA / O accumulator columns
-  static constexpr int PCB = BKV / 64;                 // column blocks of the P tile
-  static constexpr int ST = 3;                         // K/V ring stages
+  static constexpr int ST = (D <= 64) ? 4 : 3;         // K/V ring stages (>= 3: K runs two tiles ahead of V)
   static constexpr int Q_BYTES = 2 * NCB * TQ * 128;
   static constexpr int KV_BLOCK_BYTES = BKV * 128;
   static constexpr int KV_STAGE_BYTES = 2 * NCB * KV_BLOCK_BYTES;     // K then V
-  static constexpr int P_TILE_BYTES = PCB * TQ * 128;
+  static constexpr int P_TILE_BYTES = TQ * 128;
   static constexpr int SMEM = Q_BYTES + ST * KV_STAGE_BYTES + 2 * P_TILE_BYTES + 1024 + 256;
   static constexpr int O_STRIDE = (DPO <= 64) ? 64 : 128;             // TMEM column stride between O_0 and O_1
-  static constexpr int S_COL = 0, O_COL = 2 * BKV;
+  static constexpr int S_COL = 0, O_COL = 4 * BKV;                    // S_{i,b} at (2 i + b) * BKV
   static constexpr int TMEM_COLS = 512;
-  static_assert(2 * BKV + 2 * O_STRIDE <= 512, "TMEM budget");
+  static_assert(4 * BKV + 2 * O_STRIDE <= 512, "TMEM budget");
   static_assert(SMEM <= 227 * 1024, "shared memory budget");
 };
 
@@ -77,22 +79,23 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, 
   return d;
 }
 
-template <int D, int BKV, bool EXP16>
+template <int D>
 __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_constant__ TAttnArgs p) {
-  using C = TCfg<D, BKV>;
+  using C = TCfg<D>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t q_s = base;                                   // [2 tiles][NCB][128 rows x 128 B]
   const uint32_t kv_s = q_s + C::Q_BYTES;                      // [ST][K: NCB blocks | V: NCB blocks]
-  const uint32_t p_s = kv_s + C::ST * C::KV_STAGE_BYTES;       // [2 tiles][PCB][128 rows x 128 B]
+  const uint32_t p_s = kv_s + C::ST * C::KV_STAGE_BYTES;       // [2 tiles][128 rows x 128 B]
   const uint32_t bars = p_s + 2 * C::P_TILE_BYTES;
   const uint32_t q_full = bars;
   auto kv_full = [&](int s) { return bars + 8u * (1 + s); };
   auto kv_empty = [&](int s) { return bars + 8u * (1 + C::ST + s); };
-  auto s_full = [&](int i) { return bars + 8u * (1 + 2 * C::ST + i); };
-  auto p_full = [&](int i) { return bars + 8u * (3 + 2 * C::ST + i); };
-  const uint32_t o_full = bars + 8u * (5 + 2 * C::ST);
-  const uint32_t tmem_slot = bars + 8u * (6 + 2 * C::ST);
+  auto s_full = [&](int i, int b) { return bars + 8u * (1 + 2 * C::ST + 2 * i + b); };
+  auto p_full = [&](int i) { return bars + 8u * (5 + 2 * C::ST + i); };
+  auto p_empty = [&](int i) { return bars + 8u * (7 + 2 * C::ST + i); };
+  const uint32_t o_full = bars + 8u * (9 + 2 * C::ST);
+  const uint32_t tmem_slot = bars + 8u * (10 + 2 * C::ST);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -103,7 +106,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
     for (int s = 0; s < C::ST; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(s_full(i), 1); mbar_init(p_full(i), 128); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(s_full(i, 0), 1); mbar_init(s_full(i, 1), 1);
+      mbar_init(p_full(i), 128); mbar_init(p_empty(i), 1);
+    }
     mbar_init(o_full, 1);
     fence_barrier_init();
   }
@@ -139,48 +145,50 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
       // ============================================================== MMA issuer
       constexpr uint32_t idesc_qk = umma_idesc_f16(TQ, BKV);
       constexpr uint32_t idesc_pv = umma_idesc_f16(TQ, C::DPO) | (1u << 16);   // B operand MN-major
-      auto issue_qk = [&](int i, int s) {
+      auto issue_qk = [&](int i, int s, int buf) {
         const uint32_t qa = q_s + i * C::NCB * TQ * 128;
         const uint32_t ka = kv_s + s * C::KV_STAGE_BYTES;
 #pragma unroll
         for (int k = 0; k < C::DPK / 16; ++k) {
           const int cb = (k * 16) / 64, off = ((k * 16) % 64) * 2;
-          tc_mma_f16(tmem + C::S_COL + i * BKV, umma_desc_sw128_kmajor(qa + cb * TQ * 128 + off),
+          tc_mma_f16(tmem + C::S_COL + (2 * i + buf) * BKV, umma_desc_sw128_kmajor(qa + cb * TQ * 128 + off),
                      umma_desc_sw128_kmajor(ka + cb * C::KV_BLOCK_BYTES + off), idesc_qk, k != 0 ? 1u : 0u);
         }
-        tc_commit(s_full(i));
+        tc_commit(s_full(i, buf));
       };
       auto issue_pv = [&](int i, int s, bool acc) {
         const uint32_t pa = p_s + i * C::P_TILE_BYTES;
         const uint32_t va = kv_s + s * C::KV_STAGE_BYTES + C::NCB * C::KV_BLOCK_BYTES;
 #pragma unroll
-        for (int k = 0; k < BKV / 16; ++k) {
-          const int cb = (k * 16) / 64, off = ((k * 16) % 64) * 2;
-          tc_mma_f16(tmem + C::O_COL + i * C::O_STRIDE, umma_desc_sw128_kmajor(pa + cb * TQ * 128 + off),
+        for (int k = 0; k < BKV / 16; ++k)
+          tc_mma_f16(tmem + C::O_COL + i * C::O_STRIDE, umma_desc_sw128_kmajor(pa + k * 32),
                      umma_desc_sw128_mnmajor(va + k * 16 * 128, C::KV_BLOCK_BYTES), idesc_pv, (acc || k != 0) ? 1u : 0u);
-        }
+        tc_commit(p_empty(i));                   // P_i consumed, O_i quiescent once this retires
       };
       mbar_wait(q_full, 0);
-      mbar_wait(kv_full(0), 0);
-      tc_fence_after();
-      issue_qk(0, 0);
-      issue_qk(1, 0);
+      for (int jj = 0; jj < 2 && jj < nkt; ++jj) {     // Q K^T runs two key tiles ahead of the softmax
+        mbar_wait(kv_full(jj % C::ST), 0);
+        tc_fence_after();
+        issue_qk(0, jj % C::ST, jj & 1);
+        issue_qk(1, jj % C::ST, jj & 1);
+      }
       for (int j = 0; j < nkt; ++j) {
-        const int s = j % C::ST, sn = (j + 1) % C::ST;
-        const uint32_t pph = j & 1;
-        mbar_wait(p_full(0), pph);
-        tc_fence_after();
-        issue_pv(0, s, j > 0);
-        if (j + 1 < nkt) {
-          mbar_wait(kv_full(sn), ((j + 1) / C::ST) & 1);
+        const int s = j % C::ST;
+        const int jn = j + 2, sn = jn % C::ST;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          mbar_wait(p_full(i), j & 1);
           tc_fence_after();
-          issue_qk(0, sn);
+          issue_pv(i, s, j > 0);
+          if (jn < nkt) {
+            if (i == 0) {
+              mbar_wait(kv_full(sn), (jn / C::ST) & 1);
+              tc_fence_after();
+            }
+            issue_qk(i, sn, j & 1);               // S_{i, j&1} was drained by the softmax before it signalled p_full
+          }
         }
-        mbar_wait(p_full(1), pph);
-        tc_fence_after();
-        issue_pv(1, s, j > 0);
         tc_commit(kv_empty(s));                  // K_j / V_j fully consumed once these MMAs retire
-        if (j + 1 < nkt) issue_qk(1, sn);
       }
       tc_commit(o_full);
     }
@@ -190,22 +198,21 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;         // query row inside the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    const uint32_t s_addr = tmem + lane_addr + C::S_COL + i * BKV;
     const uint32_t o_addr = tmem + lane_addr + C::O_COL + i * C::O_STRIDE;
     const uint32_t p_row = p_s + i * C::P_TILE_BYTES + row * 128;
     const float sc = p.scale_log2;
     float m_used = -INFINITY, l = 0.f;
     for (int j = 0; j < nkt; ++j) {
-      mbar_wait(s_full(i), j & 1);
+      mbar_wait(s_full(i, j & 1), (j >> 1) & 1);
       tc_fence_after();
       const int kbase = j * BKV;
-      const bool tail = kbase + BKV > p.nk;
-      // ---- the whole S row of this tile lives in registers: one TMEM round trip per tile
+      // ---- the S row of this tile lives in registers: one TMEM round trip per tile
       uint32_t sv[BKV];
-#pragma unroll
-      for (int c0 = 0; c0 < BKV; c0 += 32) tmem_ld32(s_addr + c0, sv + c0);
+      const uint32_t s_addr = tmem + lane_addr + C::S_COL + (2 * i + (j & 1)) * BKV;
+      tmem_ld32(s_addr, sv);
+      tmem_ld32(s_addr + 32, sv + 32);
       tmem_ld_wait();
-      if (tail) {   // keys beyond nk were zero-filled by TMA: mask them (last tile only)
+      if (kbase + BKV > p.nk) {   // keys beyond nk were zero-filled by TMA: mask them (last tile only)
 #pragma unroll
         for (int t = 0; t < BKV; ++t)
           if (kbase + t >= p.nk) sv[t] = 0xff800000u;   // -inf
@@ -219,6 +226,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
         mx3 = fmaxf(mx3, __uint_as_float(sv[t + 3]));
       }
       const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      // P_i(j-1) has been consumed and O_i is quiescent once p_empty flips (issued a whole softmax ago: no real wait)
+      if (j > 0) {
+        mbar_wait(p_empty(i), (j - 1) & 1);
+        tc_fence_after();
+      }
       // ---- lazy rescale: only when the maximum moved by more than 2^8 (always true on the first tile: m_used=-inf)
       const bool need = (mx - m_used) * sc > 8.f;
       if (j > 0 && __any_sync(0xffffffffu, need)) {
@@ -237,31 +249,22 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
       }
       if (need) m_used = mx;
       const float ms = m_used * sc;
-      // ---- P = exp2(S*scale - m) -> fp16 -> swizzled shared memory (A operand of the P V MMA); exp(-inf) = 0 masks
+      // ---- P = exp2(S*scale - m) -> fp16 -> swizzled shared memory (A operand of the P V MMA); exp2(-inf) = 0 masks
       float l0 = 0.f, l1 = 0.f;
 #pragma unroll
       for (int c8 = 0; c8 < BKV / 8; ++c8) {       // one 16-byte chunk (8 keys) at a time
         uint32_t pk[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const float a0 = __uint_as_float(sv[c8 * 8 + 2 * u]) * sc - ms;
-          const float a1 = __uint_as_float(sv[c8 * 8 + 2 * u + 1]) * sc - ms;
-          __half2 h;
-          if (EXP16) {   // packed fp16 exponential: one MUFU op per two probabilities (P is fp16 anyway)
-            const __half2 a = __floats2half2_rn(a0, a1);
-            uint32_t r;
-            asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(*reinterpret_cast<const uint32_t*>(&a)));
-            h = *reinterpret_cast<const __half2*>(&r);
-          } else {
-            h = __floats2half2_rn(fast_exp2(a0), fast_exp2(a1));
-          }
-          const float2 back = __half22float2(h);
+          const float e0 = fast_exp2(__uint_as_float(sv[c8 * 8 + 2 * u]) * sc - ms);
+          const float e1 = fast_exp2(__uint_as_float(sv[c8 * 8 + 2 * u + 1]) * sc - ms);
+          const __half2 h = __floats2half2_rn(e0, e1);
+          const float2 back = __half22float2(h);    // the row sum uses the rounded probabilities the MMA sees
           l0 += back.x;
           l1 += back.y;
           pk[u] = *reinterpret_cast<const uint32_t*>(&h);
         }
-        const int cb = c8 / 8, ch = c8 % 8;        // 64-key column block, 16-byte chunk inside the 128-byte row
-        const uint32_t dst = p_row + cb * (TQ * 128) + ((ch ^ (row & 7)) << 4);
+        const uint32_t dst = p_row + ((c8 ^ (row & 7)) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
                      : "memory");
       }
@@ -304,13 +307,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
   }
 }
 
-template <int D, int BKV, bool EXP16>
+template <int D>
 int launch(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv, __half* o, int ldo,
            int batch, int nq, int nk, int heads, long long q_bs, long long kv_bs, long long o_bs, int kv_div) {
-  using C = TCfg<D, BKV>;
+  using C = TCfg<D>;
   static bool configured = false;
   if (!configured) {
-    VS_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D, BKV, EXP16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    VS_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     configured = true;
   }
   TAttnArgs a;
@@ -320,21 +323,21 @@ int launch(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, 
     const uint64_t dims[4] = {(uint64_t)D, (uint64_t)heads, (uint64_t)nq, (uint64_t)batch};
     const uint64_t str[3] = {(uint64_t)D * 2, (uint64_t)ldq * 2, (uint64_t)(q_bs > 0 ? q_bs : (long long)nq * ldq) * 2};
     const uint32_t box[4] = {64, 1, TQ, 1};
-    if (make_tmap_f16(&a.tmQ, q, 4, dims, str, box, true)) return 3;
+    if (make_tmap_f16(&a.tmQ, q, 4, dims, str, box, 1)) return 3;
   }
   {
     const uint64_t dims[4] = {(uint64_t)D, (uint64_t)heads, (uint64_t)nk, (uint64_t)bkv};
     const uint64_t strk[3] = {(uint64_t)D * 2, (uint64_t)ldk * 2, (uint64_t)(kv_bs > 0 ? kv_bs : (long long)nk * ldk) * 2};
     const uint64_t strv[3] = {(uint64_t)D * 2, (uint64_t)ldv * 2, (uint64_t)(kv_bs > 0 ? kv_bs : (long long)nk * ldv) * 2};
     const uint32_t box[4] = {64, 1, (uint32_t)BKV, 1};
-    if (make_tmap_f16(&a.tmK, k, 4, dims, strk, box, true)) return 3;
-    if (make_tmap_f16(&a.tmV, v, 4, dims, strv, box, true)) return 3;
+    if (make_tmap_f16(&a.tmK, k, 4, dims, strk, box, 1)) return 3;
+    if (make_tmap_f16(&a.tmV, v, 4, dims, strv, box, 1)) return 3;
   }
   a.o = o; a.ldo = ldo; a.o_bs = o_bs; a.nq = nq; a.nk = nk; a.kv_div = kv_div;
   a.scale_log2 = 1.4426950408889634f / sqrtf((float)D);
   dim3 grid((nq + 2 * TQ - 1) / (2 * TQ), heads, batch);
   ProfScope prof(st, PC_ATTN, 4.0 * batch * heads * (double)nq * nk * D);
-  attn_tc_kernel<D, BKV, EXP16><<<grid, ATT_THREADS, C::SMEM, st>>>(a);
+  attn_tc_kernel<D><<<grid, ATT_THREADS, C::SMEM, st>>>(a);
   VS_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -347,15 +350,8 @@ int attention_tc(cudaStream_t st, const __half* q, int ldq, const __half* k, int
                  int kv_div) {
   if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8)) return -1;
   if ((q_bs % 8) || (kv_bs % 8)) return -1;
-  const bool e16 = get_option("attn_exp16") != 0;
-  if (d == 40) {
-    return e16 ? launch<40, 128, true>(st, q, ldq, k, ldk, v, ldv, o, ldo, batch, nq, nk, heads, q_bs, kv_bs, o_bs, kv_div)
-               : launch<40, 128, false>(st, q, ldq, k, ldk, v, ldv, o, ldo, batch, nq, nk, heads, q_bs, kv_bs, o_bs, kv_div);
-  }
-  if (d == 80) {
-    return e16 ? launch<80, 64, true>(st, q, ldq, k, ldk, v, ldv, o, ldo, batch, nq, nk, heads, q_bs, kv_bs, o_bs, kv_div)
-               : launch<80, 64, false>(st, q, ldq, k, ldk, v, ldv, o, ldo, batch, nq, nk, heads, q_bs, kv_bs, o_bs, kv_div);
-  }
+  if (d == 40) return launch<40>(st, q, ldq, k, ldk, v, ldv, o, ldo, batch, nq, nk, heads, q_bs, kv_bs, o_bs, kv_div);
+  if (d == 80) return launch<80>(st, q, ldq, k, ldk, v, ldv, o, ldo, batch, nq, nk, heads, q_bs, kv_bs, o_bs, kv_div);
   return -1;
 }
 

@@ -30,9 +30,7 @@ constexpr int GEMM_THREADS = 384;                   // 4 control warps + 2 epilo
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int EPI_COLS = 32;                        // output columns per epilogue sub-tile (64 B of fp16: SWIZZLE_64B)
 constexpr int EPI_BUF_BYTES = BM * EPI_COLS * 2;    // 8 KB
-constexpr int EPI_OUT_BUFS = 3, EPI_RES_BUFS = 2;   // per epilogue warpgroup
-constexpr int EPI_GROUP_BYTES = (EPI_OUT_BUFS + EPI_RES_BUFS) * EPI_BUF_BYTES;
-constexpr int EPI_BYTES = 2 * EPI_GROUP_BYTES;      // two warpgroups
+constexpr int EPI_BYTES = 8 * 4096;                 // per epilogue warp: 2 KB residual + 2 KB output staging
 
 struct GemmParams {
   CUtensorMap tmA, tmA2, tmB, tmC, tmR;
@@ -53,7 +51,8 @@ struct GemmParams {
   __half* out;
   int ldc;
   int mode;
-  int tma_epi;       // 1 = smem-staged TMA-store epilogue
+  int tma_epi;       // 1 = smem-staged (warp-transposed, coalesced) epilogue; 0 = direct stores for tiny / unaligned N
+  int b_resident;    // 1 = weight-stationary tile order with the [BN x K] panel resident in shared memory
 };
 
 template <int BN>
@@ -85,22 +84,34 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
-  auto rfull_bar = [&](int grp, int a) { return bar_base + 8u * (2 * C::STAGES + 4 + grp * 2 + a); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 8);
+  const uint32_t bfull_bar = bar_base + 8u * (2 * C::STAGES + 4);   // resident weight panel loaded
+  const uint32_t bfree_bar = bar_base + 8u * (2 * C::STAGES + 5);   // resident weight panel no longer read
+  const uint32_t tmem_slot = bar_base + 8u * (2 * C::STAGES + 6);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
+  // Tile order.  Default: n fastest, tiles round-robin over CTAs (neighbouring CTAs share the A tile through L2).
+  // Weight-stationary mode (small K: the [BN x K] weight panel fits in shared memory): m fastest, a contiguous range of
+  // tiles per CTA, the panel is loaded once per n-tile and only A is streamed -- the small-K GEMMs are L2-bandwidth
+  // bound (184 KB through L2 for 13 MFLOP per tile) and this removes the weight re-fetch.
+  const bool wres = p.b_resident != 0;
+  const int t_begin = wres ? (int)((long long)blockIdx.x * total_tiles / gridDim.x) : (int)blockIdx.x;
+  const int t_end = wres ? (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x) : total_tiles;
+  const int t_step = wres ? 1 : (int)gridDim.x;
+  const uint32_t panel_bytes = wres ? (uint32_t)p.num_kb * C::B_STAGE_BYTES : 0u;
+  auto a_stage = [&](int s) { return wres ? smem_base + panel_bytes + s * A_STAGE_BYTES : smem_base + s * C::STAGE_BYTES; };
+  auto b_stage = [&](int s, int kb) { return wres ? smem_base + kb * C::B_STAGE_BYTES : smem_base + s * C::STAGE_BYTES + A_STAGE_BYTES; };
+  auto decode = [&](int tile, int& m_tile, int& n_tile) {
+    if (wres) { n_tile = tile / p.m_tiles; m_tile = tile - n_tile * p.m_tiles; }
+    else { m_tile = tile / p.n_tiles; n_tile = tile - m_tile * p.n_tiles; }
+  };
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmA);
     prefetch_tmap(&p.tmB);
     if (p.kb_src1 < p.kb_per_tap) prefetch_tmap(&p.tmA2);
-    if (p.tma_epi) {
-      prefetch_tmap(&p.tmC);
-      if (p.residual) prefetch_tmap(&p.tmR);
-    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
@@ -110,9 +121,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
       mbar_init(tempty_bar(a), 256);
-      mbar_init(rfull_bar(0, a), 1);
-      mbar_init(rfull_bar(1, a), 1);
     }
+    mbar_init(bfull_bar, 1);
+    mbar_init(bfree_bar, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
@@ -124,22 +135,31 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   if (warp == 0) {
     if (lane == 0) {
       // ================================================================= TMA producer
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.n_tiles, n_tile = tile % p.n_tiles;
+      uint32_t it = 0, npanel = 0;
+      int cur_n = -1;
+      for (int tile = t_begin; tile < t_end; tile += t_step) {
+        int m_tile, n_tile;
+        decode(tile, m_tile, n_tile);
         int x0 = 0, y0 = 0, i0 = 0;
         if (p.a_rank == 4) {
           x0 = (m_tile % p.tiles_x) * p.TW;
           y0 = ((m_tile / p.tiles_x) % p.tiles_y) * p.TH;
           i0 = (m_tile / (p.tiles_x * p.tiles_y)) * p.TN;
         }
+        if (wres && n_tile != cur_n) {        // (re)load the resident weight panel of this n-tile
+          if (npanel > 0) mbar_wait(bfree_bar, (npanel - 1) & 1);
+          mbar_expect_tx(bfull_bar, panel_bytes);
+          for (int kb = 0; kb < p.num_kb; ++kb) tma_load_2d(b_stage(0, kb), &p.tmB, bfull_bar, kb * BK, n_tile * BN);
+          cur_n = n_tile;
+          ++npanel;
+        }
         for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
           const int s = it % C::STAGES;
           const uint32_t ph = (it / C::STAGES) & 1;
           mbar_wait(empty_bar(s), ph ^ 1);
-          mbar_expect_tx(full_bar(s), C::STAGE_BYTES);
-          const uint32_t a_dst = smem_base + s * C::STAGE_BYTES;
-          const uint32_t b_dst = a_dst + A_STAGE_BYTES;
+          mbar_expect_tx(full_bar(s), wres ? A_STAGE_BYTES : C::STAGE_BYTES);
+          const uint32_t a_dst = a_stage(s);
+          const uint32_t b_dst = b_stage(s, kb);
           const int tap = kb / p.kb_per_tap;
           const int r = kb - tap * p.kb_per_tap;
           const CUtensorMap* tm = (r < p.kb_src1) ? &p.tmA : &p.tmA2;
@@ -151,7 +171,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           } else {
             tma_load_2d(a_dst, tm, full_bar(s), c, m_tile * BM);
           }
-          tma_load_2d(b_dst, &p.tmB, full_bar(s), kb * BK, n_tile * BN);
+          if (!wres) tma_load_2d(b_dst, &p.tmB, full_bar(s), kb * BK, n_tile * BN);
         }
       }
     }
@@ -159,8 +179,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     if (lane == 0) {
       // ================================================================= MMA issuer
       constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
-      uint32_t it = 0, t = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+      uint32_t it = 0, t = 0, npanel = 0;
+      int cur_n = -1;
+      for (int tile = t_begin; tile < t_end; tile += t_step, ++t) {
+        int m_tile, n_tile;
+        decode(tile, m_tile, n_tile);
+        if (wres && n_tile != cur_n) {
+          mbar_wait(bfull_bar, npanel & 1);
+          ++npanel;
+          cur_n = n_tile;
+        }
         const int acc = t & 1;
         const uint32_t aph = (t >> 1) & 1;
         mbar_wait(tempty_bar(acc), aph ^ 1);
@@ -171,8 +199,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           const uint32_t ph = (it / C::STAGES) & 1;
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_base + s * C::STAGE_BYTES;
-          const uint32_t b_addr = a_addr + A_STAGE_BYTES;
+          const uint32_t a_addr = a_stage(s);
+          const uint32_t b_addr = b_stage(s, kb);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t ad = umma_desc_sw128_kmajor(a_addr + k * 32);
@@ -182,6 +210,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           tc_commit(empty_bar(s));   // frees the smem slot once these MMAs have read it
         }
         tc_commit(tfull_bar(acc));   // accumulator complete -> epilogue
+        if (wres) {                  // last tile of this n-tile on this CTA: the panel may be overwritten afterwards
+          const int nxt = tile + t_step;
+          if (nxt >= t_end || nxt / p.m_tiles != n_tile) tc_commit(bfree_bar);
+        }
       }
     }
   } else if (warp >= 4) {
@@ -189,12 +221,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     const int q = warp & 3;                 // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;          // row of the tile handled by this thread
     const int grp = (warp - 4) >> 2;        // epilogue warpgroup: sub-tile s of a tile is handled by group s % 2
-    const bool leader = (threadIdx.x & 127) == 0;
     const bool has_res = p.residual != nullptr;
-    const uint32_t grp_base = epi_base + grp * EPI_GROUP_BYTES;   // out0 | out1 | out2 | res0 | res1
-    uint32_t t = 0, g = 0;                  // tile counter, sub-tiles processed by this group (staging-buffer rotation)
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
-      const int m_tile = tile / p.n_tiles, n_tile = tile % p.n_tiles;
+    uint32_t t = 0;                         // tile counter
+    for (int tile = t_begin; tile < t_end; tile += t_step, ++t) {
+      int m_tile, n_tile;
+      decode(tile, m_tile, n_tile);
       const int acc = t & 1;
       const uint32_t aph = (t >> 1) & 1;
       long long pix;
@@ -226,19 +257,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         const int oc0 = geglu ? n_tile * (BN / 2) : n0;                    // first output column of this tile
         const int ocols = geglu ? BN / 2 : ((p.N - n0) < BN ? (p.N - n0) : BN);
         const int nsub = ocols / EPI_COLS;
-        auto load_res = [&](int s, int buf) {
-          mbar_expect_tx(rfull_bar(grp, buf), EPI_BUF_BYTES);
-          const uint32_t dst = grp_base + (EPI_OUT_BUFS + buf) * EPI_BUF_BYTES;
-          if (p.a_rank == 4) tma_load_4d(dst, &p.tmR, rfull_bar(grp, buf), oc0 + s * EPI_COLS, x0, y0, i0);
-          else tma_load_2d(dst, &p.tmR, rfull_bar(grp, buf), oc0 + s * EPI_COLS, m_tile * BM);
-        };
-        if (leader && has_res) {
-          if (grp < nsub) load_res(grp, g & 1);
-          if (grp + 2 < nsub) load_res(grp + 2, (g + 1) & 1);
+        // Warp-private staging (32 rows x 64 B for the residual, the same for the output): the accumulator layout is
+        // thread = row, HBM wants lanes along columns, so each warp transposes its own 32 rows through shared memory with
+        // nothing but __syncwarp.  (TMA stores were tried first: they queue behind the producer's prefetched TMA loads
+        // in the same engine and their completion wait serialised the epilogue.)
+        const uint32_t res_stage = epi_base + (warp - 4) * 4096, out_stage = res_stage + 2048;
+        const int tr = lane >> 2, tch = lane & 3;        // transposed mapping: 8 rows x four 16-byte chunks per instruction
+        long long tpix[4];
+        bool tvalid[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          tpix[i] = __shfl_sync(0xffffffffu, pix, i * 8 + tr);
+          tvalid[i] = __shfl_sync(0xffffffffu, (int)valid, i * 8 + tr) != 0;
         }
 #pragma unroll 1
-        for (int s = grp; s < nsub; s += 2, ++g) {
-          const int buf = g & 1;               // residual staging buffer
+        for (int s = grp; s < nsub; s += 2) {
+          const int col0 = oc0 + s * EPI_COLS;
+          uint4 rres[4];
+          if (has_res) {                       // coalesced residual loads, issued before the TMEM round trip
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              rres[i] = tvalid[i] ? __ldg(reinterpret_cast<const uint4*>(p.residual + tpix[i] * p.ldr + col0 + tch * 8))
+                                  : make_uint4(0, 0, 0, 0);
+          }
           float f[32];
           {
             uint32_t v[32];
@@ -274,13 +315,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             }
           }
           if (has_res) {
-            mbar_wait(rfull_bar(grp, buf), (g >> 1) & 1);
-            const uint32_t rb = grp_base + (EPI_OUT_BUFS + buf) * EPI_BUF_BYTES;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(res_stage + sw64_off(i * 8 + tr, tch)),
+                           "r"(rres[i].x), "r"(rres[i].y), "r"(rres[i].z), "r"(rres[i].w) : "memory");
+            __syncwarp();
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               uint32_t r0, r1, r2, r3;
               asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-                           : "r"(rb + sw64_off(row, c)));
+                           : "r"(res_stage + sw64_off(lane, c)));
               const uint32_t rr[4] = {r0, r1, r2, r3};
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
@@ -296,23 +340,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             const __half2 h = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
             pk[j] = *reinterpret_cast<const uint32_t*>(&h);
           }
-          // Output staging rotates over three buffers: buffer g % 3 was last handed to a TMA store at sub-tile g - 3, and
-          // the leader's wait_group.read(1) before the barrier of sub-tile g - 1 guaranteed that store had drained, so one
-          // barrier per sub-tile suffices.
-          const uint32_t ob = grp_base + (g % EPI_OUT_BUFS) * EPI_BUF_BYTES;
 #pragma unroll
           for (int c = 0; c < 4; ++c)
-            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(ob + sw64_off(row, c)), "r"(pk[4 * c]),
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(out_stage + sw64_off(lane, c)), "r"(pk[4 * c]),
                          "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]), "r"(pk[4 * c + 3]) : "memory");
-          fence_proxy_async();
-          if (leader) tma_store_wait_read<1>();
-          named_bar_sync(1 + grp, 128);
-          if (leader) {
-            if (p.a_rank == 4) tma_store_4d(&p.tmC, ob, oc0 + s * EPI_COLS, x0, y0, i0);
-            else tma_store_2d(&p.tmC, ob, oc0 + s * EPI_COLS, m_tile * BM);
-            tma_store_commit();
-            if (has_res && s + 4 < nsub) load_res(s + 4, buf);
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {       // 8 rows x 64 contiguous bytes per store instruction
+            uint4 o;
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
+                         : "r"(out_stage + sw64_off(i * 8 + tr, tch)));
+            if (tvalid[i]) *reinterpret_cast<uint4*>(p.out + tpix[i] * p.ldc + col0 + tch * 8) = o;
           }
+          __syncwarp();                        // staging is reused by this warp's next sub-tile
         }
       } else if (p.mode == EPI_LINEAR && grp == 0) {
         // ------------------------------------------------------------ v1: direct stores (tiny / unaligned N)
@@ -338,7 +378,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
     }
-    if (leader && p.tma_epi) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -381,20 +420,6 @@ int launch(cudaStream_t st, GemmParams& p) {
   gemm_tc_kernel<BN><<<grid, GEMM_THREADS, C::SMEM_BYTES, st>>>(p);
   VS_CHECK_CUDA(cudaGetLastError());
   return 0;
-}
-
-// 2-D (plain rows) or 4-D (NHWC pixel box) descriptor over an output-side tensor with `cols` columns, row pitch `ld`.
-int make_epi_tmap(CUtensorMap* tm, const __half* base, int cols, int ld, const GemmParams& p) {
-  if (p.a_rank == 4) {
-    const uint64_t dims[4] = {(uint64_t)cols, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.nimg};
-    const uint64_t str[3] = {(uint64_t)ld * 2, (uint64_t)ld * 2 * p.W, (uint64_t)ld * 2 * p.W * p.H};
-    const uint32_t box[4] = {EPI_COLS, (uint32_t)p.TW, (uint32_t)p.TH, (uint32_t)p.TN};
-    return make_tmap_f16(tm, base, 4, dims, str, box, 2);
-  }
-  const uint64_t dims[2] = {(uint64_t)cols, (uint64_t)p.M};
-  const uint64_t str[1] = {(uint64_t)ld * 2};
-  const uint32_t box[2] = {EPI_COLS, BM};
-  return make_tmap_f16(tm, base, 2, dims, str, box, 2);
 }
 
 }  // namespace
@@ -482,12 +507,10 @@ int gemm_tc(cudaStream_t st, const GemmArgs& a) {
   const int out_cols = (a.mode == EPI_GEGLU) ? a.N / 2 : a.N;
   p.tma_epi = (out_cols % EPI_COLS == 0) && (a.ldc % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0) &&
               (!a.residual || ((a.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.residual) & 15) == 0)));
-  if (p.tma_epi) {
-    if (make_epi_tmap(&p.tmC, a.out, out_cols, a.ldc, p)) return 3;
-    if (a.residual && make_epi_tmap(&p.tmR, a.residual, out_cols, a.ldr, p)) return 3;
-  } else {
-    VS_REQUIRE(a.mode == EPI_LINEAR, "gemm_tc: GEGLU output must be TMA-storable");
-  }
+  if (!p.tma_epi) VS_REQUIRE(a.mode == EPI_LINEAR, "gemm_tc: GEGLU output needs 32-column aligned, 16-byte strided rows");
+  // weight-stationary mode: plain GEMM, the whole K extent of the weight panel fits next to the A ring, enough M tiles
+  p.b_resident = (a.taps == 1 && p.num_kb <= 5 && p.m_tiles >= 4 && (long long)p.m_tiles * p.n_tiles >= 2LL * num_sms() &&
+                  get_option("gemm_wres") != 0) ? 1 : 0;
   ProfScope prof(st, a.taps == 9 ? PC_CONV : PC_GEMM, 2.0 * a.M * (double)a.N * Ktot);
   switch (bn) {
     case 64: return launch<64>(st, p);

@@ -112,16 +112,16 @@ ProfScope::~ProfScope() {
   if (idx_ >= 0) cudaEventRecord(g_prof[idx_].b, st_);
 }
 
-static int g_opt_attn_tc = 1, g_opt_attn_exp16 = 0;
+static int g_opt_attn_tc = 1, g_opt_gemm_wres = 1;
 int set_option(const char* name, int value) {
   if (strcmp(name, "attn_tc") == 0) { g_opt_attn_tc = value; return 0; }
-  if (strcmp(name, "attn_exp16") == 0) { g_opt_attn_exp16 = value; return 0; }
+  if (strcmp(name, "gemm_wres") == 0) { g_opt_gemm_wres = value; return 0; }
   set_error("unknown option '%s'", name);
   return 2;
 }
 int get_option(const char* name) {
   if (strcmp(name, "attn_tc") == 0) return g_opt_attn_tc;
-  if (strcmp(name, "attn_exp16") == 0) return g_opt_attn_exp16;
+  if (strcmp(name, "gemm_wres") == 0) return g_opt_gemm_wres;
   return 0;
 }
 
