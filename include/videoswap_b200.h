@@ -83,6 +83,12 @@ int vs_unet_copy_tap(const vs_unet* h, void* stream, int i, void* d_dst);   /* N
 int vs_cfg_ddim_step(void* stream, const void* d_eps2, const void* d_latents, int io_f32, size_t n, int cfg,
                      float guidance, float alpha_t, float alpha_prev, void* d_out);
 
+/* Same update with the two coefficients in DEVICE memory: d_coef[0] = sqrt(a_p)/sqrt(a_t),
+ * d_coef[1] = sqrt(1-a_p) - sqrt(a_p) sqrt(1-a_t)/sqrt(a_t).  Together with the device-side timestep of vs_unet_forward
+ * this makes one whole denoising step capturable in a CUDA graph that is replayed for every timestep. */
+int vs_cfg_ddim_step_dev(void* stream, const void* d_eps2, const void* d_latents, int io_f32, size_t n, int cfg,
+                         float guidance, const float* d_coef, void* d_out);
+
 /* Replaces  SparsePointAdapter.forward  (models/adapter_model.py:97-136): MLP_l(point_embedding) then bilinear splat.
  *   d_w0 [mid, E], d_b0 [mid], d_w1 [C, mid], d_b1 [C] fp16; d_point_embedding [P, E] fp32; d_tracks [F, P, 2] fp32
  *   (x, y; negative = invisible); d_point_mask [P] int32 or NULL (index_list); d_ws: >= P*(mid + C) floats scratch.

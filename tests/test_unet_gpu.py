@@ -43,6 +43,23 @@ def test_denoise_loop_matches_oracle():
     assert r["psnr"] >= PSNR_MIN, r
 
 
+def test_cuda_graph_step_equals_eager_step():
+    from videoswap_b200 import DDIMScheduler, VideoSwapPipeline
+    from videoswap_b200.pipeline import GraphedStep
+    m, _ = U.get_model()
+    pipe = VideoSwapPipeline(m, DDIMScheduler())
+    pipe.scheduler.set_timesteps(50)
+    lat = U.randn((1, 4, 2, 8, 8), 31).half().cuda()
+    emb = U.randn((2, 16, 77, 768), 32).half().cuda()
+    g = GraphedStep(pipe, lat, emb, 7.5)
+    for t in (981, 501, 1):                      # one captured graph, replayed at different timesteps
+        ref = pipe.step(lat, t, emb, 7.5)
+        out = g(lat, t).clone()
+        torch.cuda.synchronize()
+        assert torch.isfinite(out).all()
+        assert (out.float() - ref.float()).abs().max().item() <= 2e-3, t
+
+
 def test_adapter_matches_reference_golden():
     r = U.adapter_vs_golden()
     for e, ref in zip(r["errs"], r["refs"]):

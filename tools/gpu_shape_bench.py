@@ -58,6 +58,13 @@ def main():
         ms = timeit(lambda: ops.gemm(A, W, bias=b, residual=R, mode=mode))
         res[name] = {"ms": ms, "tflops": 2.0 * M * N * K / ms / 1e9, "count": cnt, "ms_total": ms * cnt, "shape": [M, N, K]}
         print(name, res[name], flush=True)
+        if K <= 320:                      # stationary-operand modes: 0 off, 1 weights resident, 2 activations resident
+            for opt in (0, 1):
+                ops.set_option("gemm_wres", opt)
+                ms2 = timeit(lambda: ops.gemm(A, W, bias=b, residual=R, mode=mode))
+                res[f"{name}_wres{opt}"] = {"ms": ms2, "tflops": 2.0 * M * N * K / ms2 / 1e9}
+                print(f"{name}_wres{opt}", res[f"{name}_wres{opt}"], flush=True)
+            ops.set_option("gemm_wres", 2)
     # ---- convs
     for name, n, H, ci, co, cnt in [("conv_L0_320", NI, 64, 320, 320, 8), ("conv_L0_960_320", NI, 64, 960, 320, 1),
                                     ("conv_L0_640_320", NI, 64, 640, 320, 2), ("conv_L1_640", NI, 32, 640, 640, 8),

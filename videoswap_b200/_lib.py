@@ -55,6 +55,7 @@ _SIGNATURES = {
     "vs_launch_count": (C.c_longlong, []),
     "vs_set_option": (_I, [C.c_char_p, _I]),
     "vs_cfg_ddim_step": (_I, [_P, _P, _P, _I, _SZ, _I, _F, _F, _F, _P]),
+    "vs_cfg_ddim_step_dev": (_I, [_P, _P, _P, _I, _SZ, _I, _F, _P, _P]),
     "vs_adapter_level": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _F, _I, _F, _P, _P]),
     "vs_gemm": (_I, [_P, _P, _I, _P, _I, _P, _I, _I, _P, _P, _I, _P, _P, _I, _I]),
     "vs_conv3x3": (_I, [_P, _P, _I, _P, _I, _P, _I, _I, _I, _I, _P, _P, _I, _P, _P]),

@@ -15,6 +15,12 @@ extern "C" int vs_cfg_ddim_step(void* stream, const void* d_eps2, const void* d_
   return cfg_ddim_step((cudaStream_t)stream, d_eps2, d_latents, io_f32, n, cfg, guidance, alpha_t, alpha_prev, d_out);
 }
 
+extern "C" int vs_cfg_ddim_step_dev(void* stream, const void* d_eps2, const void* d_latents, int io_f32, size_t n, int cfg,
+                                    float guidance, const float* d_coef, void* d_out) {
+  VS_REQUIRE(d_eps2 && d_latents && d_out && d_coef, "vs_cfg_ddim_step_dev: null pointer");
+  return cfg_ddim_step_dev((cudaStream_t)stream, d_eps2, d_latents, io_f32, n, cfg, guidance, d_coef, d_out);
+}
+
 extern "C" int vs_adapter_level(void* stream, const void* d_w0, const void* d_b0, const void* d_w1, const void* d_b1, int E,
                                 int mid, int C, const float* d_pe, const float* d_tracks, const int* d_mask, int F, int P,
                                 int h, int w, float rate, int coord_fp16, float scale, float* d_ws, void* d_map) {

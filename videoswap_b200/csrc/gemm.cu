@@ -92,21 +92,31 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
-  // Tile order.  Default: n fastest, tiles round-robin over CTAs (neighbouring CTAs share the A tile through L2).
-  // Weight-stationary mode (small K: the [BN x K] weight panel fits in shared memory): m fastest, a contiguous range of
-  // tiles per CTA, the panel is loaded once per n-tile and only A is streamed -- the small-K GEMMs are L2-bandwidth
-  // bound (184 KB through L2 for 13 MFLOP per tile) and this removes the weight re-fetch.
-  const bool wres = p.b_resident != 0;
+  // Tile order.  Default (stationary = 0): n fastest, tiles round-robin over CTAs.
+  // Stationary modes (small K, one operand panel over the whole K extent fits in shared memory next to the ring of the
+  // other operand); each CTA owns a contiguous range of tiles:
+  //   1  weight panel [BN x K] resident, m fastest, only A is streamed;
+  //   2  activation panel [128 x K] resident, n fastest, only B (L2-resident weights) is streamed: A is read from HBM
+  //      exactly once (ncu on the K=320 QKV GEMM showed A being fetched 3x from DRAM with an L2 hit rate of 41%).
+  const int stat = p.b_resident;
+  const bool wres = stat != 0;
   const int t_begin = wres ? (int)((long long)blockIdx.x * total_tiles / gridDim.x) : (int)blockIdx.x;
   const int t_end = wres ? (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x) : total_tiles;
   const int t_step = wres ? 1 : (int)gridDim.x;
-  const uint32_t panel_bytes = wres ? (uint32_t)p.num_kb * C::B_STAGE_BYTES : 0u;
-  auto a_stage = [&](int s) { return wres ? smem_base + panel_bytes + s * A_STAGE_BYTES : smem_base + s * C::STAGE_BYTES; };
-  auto b_stage = [&](int s, int kb) { return wres ? smem_base + kb * C::B_STAGE_BYTES : smem_base + s * C::STAGE_BYTES + A_STAGE_BYTES; };
+  const uint32_t panel_bytes = stat == 1 ? (uint32_t)p.num_kb * C::B_STAGE_BYTES : stat == 2 ? (uint32_t)p.num_kb * A_STAGE_BYTES : 0u;
+  const uint32_t ring_bytes = stat == 1 ? (uint32_t)A_STAGE_BYTES : stat == 2 ? (uint32_t)C::B_STAGE_BYTES : (uint32_t)C::STAGE_BYTES;
+  auto a_stage = [&](int s, int kb) {
+    return stat == 2 ? smem_base + kb * A_STAGE_BYTES : stat == 1 ? smem_base + panel_bytes + s * A_STAGE_BYTES : smem_base + s * C::STAGE_BYTES;
+  };
+  auto b_stage = [&](int s, int kb) {
+    return stat == 1 ? smem_base + kb * C::B_STAGE_BYTES
+                     : stat == 2 ? smem_base + panel_bytes + s * C::B_STAGE_BYTES : smem_base + s * C::STAGE_BYTES + A_STAGE_BYTES;
+  };
   auto decode = [&](int tile, int& m_tile, int& n_tile) {
-    if (wres) { n_tile = tile / p.m_tiles; m_tile = tile - n_tile * p.m_tiles; }
+    if (stat == 1) { n_tile = tile / p.m_tiles; m_tile = tile - n_tile * p.m_tiles; }
     else { m_tile = tile / p.n_tiles; n_tile = tile - m_tile * p.n_tiles; }
   };
+  auto panel_key = [&](int tile) { return stat == 1 ? tile / p.m_tiles : tile / p.n_tiles; };   // n-tile or m-tile id
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmA);
@@ -146,20 +156,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           y0 = ((m_tile / p.tiles_x) % p.tiles_y) * p.TH;
           i0 = (m_tile / (p.tiles_x * p.tiles_y)) * p.TN;
         }
-        if (wres && n_tile != cur_n) {        // (re)load the resident weight panel of this n-tile
+        if (wres && panel_key(tile) != cur_n) {   // (re)load the resident panel
           if (npanel > 0) mbar_wait(bfree_bar, (npanel - 1) & 1);
           mbar_expect_tx(bfull_bar, panel_bytes);
-          for (int kb = 0; kb < p.num_kb; ++kb) tma_load_2d(b_stage(0, kb), &p.tmB, bfull_bar, kb * BK, n_tile * BN);
-          cur_n = n_tile;
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            if (stat == 1) tma_load_2d(b_stage(0, kb), &p.tmB, bfull_bar, kb * BK, n_tile * BN);
+            else tma_load_2d(a_stage(0, kb), &p.tmA, bfull_bar, kb * BK, m_tile * BM);
+          }
+          cur_n = panel_key(tile);
           ++npanel;
         }
         for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
           const int s = it % C::STAGES;
           const uint32_t ph = (it / C::STAGES) & 1;
           mbar_wait(empty_bar(s), ph ^ 1);
-          mbar_expect_tx(full_bar(s), wres ? A_STAGE_BYTES : C::STAGE_BYTES);
-          const uint32_t a_dst = a_stage(s);
+          mbar_expect_tx(full_bar(s), ring_bytes);
+          const uint32_t a_dst = a_stage(s, kb);
           const uint32_t b_dst = b_stage(s, kb);
+          if (stat == 2) {                         // activations are resident: stream the weight tile only
+            tma_load_2d(b_dst, &p.tmB, full_bar(s), kb * BK, n_tile * BN);
+            continue;
+          }
           const int tap = kb / p.kb_per_tap;
           const int r = kb - tap * p.kb_per_tap;
           const CUtensorMap* tm = (r < p.kb_src1) ? &p.tmA : &p.tmA2;
@@ -184,10 +201,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       for (int tile = t_begin; tile < t_end; tile += t_step, ++t) {
         int m_tile, n_tile;
         decode(tile, m_tile, n_tile);
-        if (wres && n_tile != cur_n) {
+        if (wres && panel_key(tile) != cur_n) {
           mbar_wait(bfull_bar, npanel & 1);
           ++npanel;
-          cur_n = n_tile;
+          cur_n = panel_key(tile);
         }
         const int acc = t & 1;
         const uint32_t aph = (t >> 1) & 1;
@@ -199,7 +216,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           const uint32_t ph = (it / C::STAGES) & 1;
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
-          const uint32_t a_addr = a_stage(s);
+          const uint32_t a_addr = a_stage(s, kb);
           const uint32_t b_addr = b_stage(s, kb);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
@@ -212,7 +229,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         tc_commit(tfull_bar(acc));   // accumulator complete -> epilogue
         if (wres) {                  // last tile of this n-tile on this CTA: the panel may be overwritten afterwards
           const int nxt = tile + t_step;
-          if (nxt >= t_end || nxt / p.m_tiles != n_tile) tc_commit(bfree_bar);
+          if (nxt >= t_end || panel_key(nxt) != cur_n) tc_commit(bfree_bar);
         }
       }
     }
@@ -509,8 +526,12 @@ int gemm_tc(cudaStream_t st, const GemmArgs& a) {
               (!a.residual || ((a.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.residual) & 15) == 0)));
   if (!p.tma_epi) VS_REQUIRE(a.mode == EPI_LINEAR, "gemm_tc: GEGLU output needs 32-column aligned, 16-byte strided rows");
   // weight-stationary mode: plain GEMM, the whole K extent of the weight panel fits next to the A ring, enough M tiles
-  p.b_resident = (a.taps == 1 && p.num_kb <= 5 && p.m_tiles >= 4 && (long long)p.m_tiles * p.n_tiles >= 2LL * num_sms() &&
-                  get_option("gemm_wres") != 0) ? 1 : 0;
+  p.b_resident = 0;
+  if (a.taps == 1 && !two && p.num_kb <= 5 && p.m_tiles >= 4 && (long long)p.m_tiles * p.n_tiles >= 2LL * num_sms()) {
+    const int opt = get_option("gemm_wres");            // 0 off, 1 weight panel resident, 2 activation panel resident
+    if (opt == 1) p.b_resident = 1;
+    else if (opt == 2 && p.n_tiles >= 2) p.b_resident = 2;
+  }
   ProfScope prof(st, a.taps == 9 ? PC_CONV : PC_GEMM, 2.0 * a.M * (double)a.N * Ktot);
   switch (bn) {
     case 64: return launch<64>(st, p);

@@ -78,6 +78,9 @@ int nchw_to_nhwc(cudaStream_t st, const __half* src, int n, int C, int H, int W,
 // first) or [1, n] when guidance is disabled (cfg == 0).
 int cfg_ddim_step(cudaStream_t st, const void* eps2, const void* latents, int is_f32, size_t n, int cfg,
                   float guidance, float a_t, float a_prev, void* out);
+// Same, with the two DDIM coefficients (c_x, c_e) read from device memory (CUDA-graph replayable across timesteps).
+int cfg_ddim_step_dev(cudaStream_t st, const void* eps2, const void* latents, int is_f32, size_t n, int cfg,
+                      float guidance, const float* d_coef, void* out);
 // SparsePointAdapter splat: feat [P, C] fp32, tracks [F, P, 2] fp32 -> maps NHWC [F, h, w, C] fp16 (zeroed inside)
 int adapter_splat(cudaStream_t st, const float* feat, const float* tracks, const int* point_mask, int F, int P, int C,
                   int h, int w, float rate, int coord_fp16, float scale, __half* maps);

@@ -186,8 +186,12 @@ __global__ void nchw_to_nhwc_kernel(const __half* __restrict__ src, int C, int H
 // ---------------------------------------------------------------------------------------------- CFG + DDIM
 template <typename T>
 __global__ void cfg_ddim_kernel(const T* __restrict__ eps2, const T* __restrict__ x, size_t n, int cfg, float g,
-                                float c_x, float c_e, T* __restrict__ out) {
+                                float c_x, float c_e, const float* __restrict__ d_coef, T* __restrict__ out) {
   // x_prev = sqrt(a_p)/sqrt(a_t) * x + (sqrt(1-a_p) - sqrt(a_p) sqrt(1-a_t)/sqrt(a_t)) * eps   (eta = 0)
+  if (d_coef) {   // coefficients in device memory: the launch stays valid inside a replayed CUDA graph
+    c_x = d_coef[0];
+    c_e = d_coef[1];
+  }
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float e = (float)eps2[i];
     if (cfg) {
@@ -351,8 +355,16 @@ int cfg_ddim_step(cudaStream_t st, const void* eps2, const void* latents, int is
                   float a_t, float a_prev, void* out) {
   const float c_x = sqrtf(a_prev) / sqrtf(a_t);
   const float c_e = sqrtf(1.f - a_prev) - sqrtf(a_prev) * sqrtf(1.f - a_t) / sqrtf(a_t);
-  if (is_f32) cfg_ddim_kernel<float><<<capped(n), TPB, 0, st>>>((const float*)eps2, (const float*)latents, n, cfg, guidance, c_x, c_e, (float*)out);
-  else cfg_ddim_kernel<__half><<<capped(n), TPB, 0, st>>>((const __half*)eps2, (const __half*)latents, n, cfg, guidance, c_x, c_e, (__half*)out);
+  if (is_f32) cfg_ddim_kernel<float><<<capped(n), TPB, 0, st>>>((const float*)eps2, (const float*)latents, n, cfg, guidance, c_x, c_e, nullptr, (float*)out);
+  else cfg_ddim_kernel<__half><<<capped(n), TPB, 0, st>>>((const __half*)eps2, (const __half*)latents, n, cfg, guidance, c_x, c_e, nullptr, (__half*)out);
+  count_launch(1);
+  VS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int cfg_ddim_step_dev(cudaStream_t st, const void* eps2, const void* latents, int is_f32, size_t n, int cfg, float guidance,
+                      const float* d_coef, void* out) {
+  if (is_f32) cfg_ddim_kernel<float><<<capped(n), TPB, 0, st>>>((const float*)eps2, (const float*)latents, n, cfg, guidance, 0.f, 0.f, d_coef, (float*)out);
+  else cfg_ddim_kernel<__half><<<capped(n), TPB, 0, st>>>((const __half*)eps2, (const __half*)latents, n, cfg, guidance, 0.f, 0.f, d_coef, (__half*)out);
   count_launch(1);
   VS_CHECK_CUDA(cudaGetLastError());
   return 0;

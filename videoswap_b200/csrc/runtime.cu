@@ -112,7 +112,7 @@ ProfScope::~ProfScope() {
   if (idx_ >= 0) cudaEventRecord(g_prof[idx_].b, st_);
 }
 
-static int g_opt_attn_tc = 1, g_opt_gemm_wres = 1;
+static int g_opt_attn_tc = 1, g_opt_gemm_wres = 2;
 int set_option(const char* name, int value) {
   if (strcmp(name, "attn_tc") == 0) { g_opt_attn_tc = value; return 0; }
   if (strcmp(name, "gemm_wres") == 0) { g_opt_gemm_wres = value; return 0; }

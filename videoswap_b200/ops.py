@@ -157,11 +157,25 @@ def upsample2x(x):
     return out
 
 
-def cfg_ddim_step(eps2, latents, guidance, alpha_t, alpha_prev, cfg=True, out=None):
+def ddim_coefficients(alpha_t: float, alpha_prev: float):
+    """(c_x, c_e) with x_prev = c_x * x + c_e * eps  (DDIM, eta = 0)."""
+    import math
+    c_x = math.sqrt(alpha_prev) / math.sqrt(alpha_t)
+    c_e = math.sqrt(1.0 - alpha_prev) - math.sqrt(alpha_prev) * math.sqrt(1.0 - alpha_t) / math.sqrt(alpha_t)
+    return c_x, c_e
+
+
+def cfg_ddim_step(eps2, latents, guidance, alpha_t=None, alpha_prev=None, cfg=True, out=None, coef=None):
+    """coef: optional device tensor [2] fp32 (c_x, c_e) instead of host alphas (CUDA-graph replayable)."""
     assert eps2.dtype == latents.dtype and eps2.is_contiguous() and latents.is_contiguous()
     is_f32 = int(latents.dtype == torch.float32)
     if out is None:
         out = torch.empty_like(latents)
+    if coef is not None:
+        _chk32(coef)
+        _lib.call("vs_cfg_ddim_step_dev", _stream(), _p(eps2), _p(latents), is_f32, latents.numel(), int(cfg), float(guidance),
+                  _p(coef), _p(out))
+        return out
     _lib.call("vs_cfg_ddim_step", _stream(), _p(eps2), _p(latents), is_f32, latents.numel(), int(cfg), float(guidance),
               float(alpha_t), float(alpha_prev), _p(out))
     return out
