@@ -238,7 +238,27 @@ def check_cfg_ddim(dtype=torch.float16, seed=150):
     return _res(out, ref, rel=2 ** -9, abs_=1e-3)
 
 
+def with_option(name, value, fn, restore):
+    """Runs a check with a library option flipped (A/B coverage of alternative kernel paths)."""
+    def run():
+        ops.set_option(name, value)
+        try:
+            return fn()
+        finally:
+            ops.set_option(name, restore)
+    return run
+
+
 CHECKS = {
+    # 2-CTA cluster mode (weight tile shared by TMA multicast): odd tile counts, concat, conv, epilogue variants
+    "cluster_gemm": with_option("gemm_cluster", 1, lambda: check_gemm(1024, 1280, 1280, residual=True, seed=7), 0),
+    "cluster_gemm_odd_m": with_option("gemm_cluster", 1, lambda: check_gemm(128 * 5 + 9, 640, 640, seed=8), 0),
+    "cluster_gemm_bn128": with_option("gemm_cluster", 1, lambda: check_gemm(700, 768, 640, bn=128, seed=9), 0),
+    "cluster_geglu": with_option("gemm_cluster", 1, lambda: check_geglu(M=1000, C=640, seed=32), 0),
+    "cluster_concat": with_option("gemm_cluster", 1, check_gemm_concat, 0),
+    "cluster_conv": with_option("gemm_cluster", 1, lambda: check_conv3x3(rowvec=True, residual=True), 0),
+    "cluster_conv_odd": with_option("gemm_cluster", 1, lambda: _conv_odd(3, 7, 12, 320, 320, 55), 0),
+    "cluster_conv_w64": with_option("gemm_cluster", 1, lambda: check_conv3x3(n=2, H=64, W=64, ci=64, co=160), 0),
     "gemm_bn160": lambda: check_gemm(512, 320, 320),
     "gemm_bn128_tail": lambda: check_gemm(300, 768, 320, bn=128),
     "gemm_bn64": lambda: check_gemm(130, 64, 128, bn=64),

@@ -57,7 +57,8 @@ def test_cuda_graph_step_equals_eager_step():
         out = g(lat, t).clone()
         torch.cuda.synchronize()
         assert torch.isfinite(out).all()
-        assert (out.float() - ref.float()).abs().max().item() <= 2e-3, t
+        # same kernels, same inputs: only fp32-atomic summation order in the GroupNorm statistics may differ
+        assert U.psnr(out, ref) >= 60.0, (t, U.psnr(out, ref))
 
 
 def test_adapter_matches_reference_golden():

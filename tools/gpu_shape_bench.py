@@ -58,13 +58,15 @@ def main():
         ms = timeit(lambda: ops.gemm(A, W, bias=b, residual=R, mode=mode))
         res[name] = {"ms": ms, "tflops": 2.0 * M * N * K / ms / 1e9, "count": cnt, "ms_total": ms * cnt, "shape": [M, N, K]}
         print(name, res[name], flush=True)
-        if K <= 320:                      # stationary-operand modes: 0 off, 1 weights resident, 2 activations resident
-            for opt in (0, 1):
-                ops.set_option("gemm_wres", opt)
-                ms2 = timeit(lambda: ops.gemm(A, W, bias=b, residual=R, mode=mode))
-                res[f"{name}_wres{opt}"] = {"ms": ms2, "tflops": 2.0 * M * N * K / ms2 / 1e9}
-                print(f"{name}_wres{opt}", res[f"{name}_wres{opt}"], flush=True)
-            ops.set_option("gemm_wres", 2)
+        # A/B: 2-CTA cluster mode with the weight tile multicast (stationary modes off so that it applies to every K)
+        ops.set_option("gemm_wres", 0)
+        ops.set_option("gemm_cluster", 1)
+        ms2 = timeit(lambda: ops.gemm(A, W, bias=b, residual=R, mode=mode))
+        ops.set_option("gemm_cluster", 0)
+        ms3 = timeit(lambda: ops.gemm(A, W, bias=b, residual=R, mode=mode))
+        ops.set_option("gemm_wres", 2)
+        res[f"{name}_cluster"] = {"ms": ms2, "tflops": 2.0 * M * N * K / ms2 / 1e9, "ms_plain": ms3}
+        print(f"{name}_cluster", res[f"{name}_cluster"], flush=True)
     # ---- convs
     for name, n, H, ci, co, cnt in [("conv_L0_320", NI, 64, 320, 320, 8), ("conv_L0_960_320", NI, 64, 960, 320, 1),
                                     ("conv_L0_640_320", NI, 64, 640, 320, 2), ("conv_L1_640", NI, 32, 640, 640, 8),
@@ -75,7 +77,12 @@ def main():
         w = ops.pack_conv3x3((torch.randn(co, ci, 3, 3, device=DEV) / math.sqrt(9 * ci)).half())
         b = torch.randn(co, device=DEV)
         ms = timeit(lambda: ops.conv3x3(x, w, bias=b))
-        res[name] = {"ms": ms, "tflops": 2.0 * n * H * H * co * 9 * ci / ms / 1e9, "count": cnt, "ms_total": ms * cnt}
+        ops.set_option("gemm_cluster", 1)
+        ms2 = timeit(lambda: ops.conv3x3(x, w, bias=b))
+        ops.set_option("gemm_cluster", 0)
+        fl = 2.0 * n * H * H * co * 9 * ci
+        res[name] = {"ms": ms, "tflops": fl / ms / 1e9, "count": cnt, "ms_total": ms * cnt, "ms_cluster": ms2,
+                     "tflops_cluster": fl / ms2 / 1e9}
         print(name, res[name], flush=True)
     # ---- attention
     for li, (C, hw) in enumerate(levels):

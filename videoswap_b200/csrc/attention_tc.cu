@@ -30,7 +30,10 @@ template <int D>
 struct TCfg {
   static constexpr int NCB = (D + 63) / 64;            // 64-wide (128-byte) column blocks of Q/K/V tiles
   static constexpr int DPK = (D + 15) / 16 * 16;       // padded contraction length of Q K^T
-  static constexpr int DPO = (D + 15) / 16 * 16;       // N of the P V MMA / O accumulator columns
+  // N of the P V MMA / O accumulator columns: d value columns + ONE extra column of ones written into the V tile, so
+  // that O[:, D] accumulates the softmax row sum on the tensor core (it is rescaled with O for free); the softmax
+  // warps then spend no instructions on it.  For d = 40 the column lives in the padding that exists anyway (48).
+  static constexpr int DPO = (D + 1 + 15) / 16 * 16;
   static constexpr int ST = (D <= 64) ? 4 : 3;         // K/V ring stages (>= 3: K runs two tiles ahead of V)
   static constexpr int Q_BYTES = 2 * NCB * TQ * 128;
   static constexpr int KV_BLOCK_BYTES = BKV * 128;
@@ -65,6 +68,11 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // MN-major B operand (V tile [keys][64 channels], 128-byte rows, SWIZZLE_128B): 8-key groups are SBO = 1024 B apart,
@@ -95,7 +103,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
   auto p_full = [&](int i) { return bars + 8u * (5 + 2 * C::ST + i); };
   auto p_empty = [&](int i) { return bars + 8u * (7 + 2 * C::ST + i); };
   const uint32_t o_full = bars + 8u * (9 + 2 * C::ST);
-  const uint32_t tmem_slot = bars + 8u * (10 + 2 * C::ST);
+  auto v_ready = [&](int s) { return bars + 8u * (10 + 2 * C::ST + s); };      // ones column written into V stage s
+  const uint32_t tmem_slot = bars + 8u * (10 + 3 * C::ST);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -105,7 +114,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
   if (warp == 0 && lane == 0) { prefetch_tmap(&p.tmQ); prefetch_tmap(&p.tmK); prefetch_tmap(&p.tmV); }
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
-    for (int s = 0; s < C::ST; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
+    for (int s = 0; s < C::ST; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); mbar_init(v_ready(s), 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(s_full(i, 0), 1); mbar_init(s_full(i, 1), 1);
       mbar_init(p_full(i), 128); mbar_init(p_empty(i), 1);
@@ -178,6 +187,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           mbar_wait(p_full(i), j & 1);
+          if (i == 0) mbar_wait(v_ready(s), (j / C::ST) & 1);   // ones column of this V tile is in place
           tc_fence_after();
           issue_pv(i, s, j > 0);
           if (jn < nkt) {
@@ -192,6 +202,22 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
       }
       tc_commit(o_full);
     }
+  } else if (warp == 3) {
+    // ================================================================ ones column: V[:, D] = 1 for every landed V tile
+    constexpr int blk = D / 64, chunk = ((D % 64) * 2) / 16, within = ((D % 64) * 2) % 16;
+    for (int j = 0; j < nkt; ++j) {
+      const int s = j % C::ST;
+      mbar_wait(kv_full(s), (j / C::ST) & 1);
+      const uint32_t v_blk = kv_s + s * C::KV_STAGE_BYTES + (C::NCB + blk) * C::KV_BLOCK_BYTES;
+#pragma unroll
+      for (int r = lane; r < BKV; r += 32) {
+        const uint32_t dst = v_blk + r * 128 + ((chunk ^ (r & 7)) << 4) + within;
+        asm volatile("st.shared.b16 [%0], %1;" ::"r"(dst), "h"((unsigned short)0x3C00) : "memory");   // fp16 1.0
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(v_ready(s));
+    }
   } else if (warp >= 4) {
     // ================================================================ softmax warpgroups + epilogue
     const int i = (warp - 4) >> 2;               // query tile handled by this warpgroup
@@ -201,7 +227,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
     const uint32_t o_addr = tmem + lane_addr + C::O_COL + i * C::O_STRIDE;
     const uint32_t p_row = p_s + i * C::P_TILE_BYTES + row * 128;
     const float sc = p.scale_log2;
-    float m_used = -INFINITY, l = 0.f;
+    float m_used = -INFINITY;
     for (int j = 0; j < nkt; ++j) {
       mbar_wait(s_full(i, j & 1), (j >> 1) & 1);
       tc_fence_after();
@@ -219,11 +245,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
       }
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int t = 0; t < BKV; t += 4) {
-        mx0 = fmaxf(mx0, __uint_as_float(sv[t]));
-        mx1 = fmaxf(mx1, __uint_as_float(sv[t + 1]));
-        mx2 = fmaxf(mx2, __uint_as_float(sv[t + 2]));
-        mx3 = fmaxf(mx3, __uint_as_float(sv[t + 3]));
+      for (int t = 0; t < BKV; t += 8) {           // FMNMX3: two new elements per instruction, four independent chains
+        mx0 = fmax3(mx0, __uint_as_float(sv[t]), __uint_as_float(sv[t + 1]));
+        mx1 = fmax3(mx1, __uint_as_float(sv[t + 2]), __uint_as_float(sv[t + 3]));
+        mx2 = fmax3(mx2, __uint_as_float(sv[t + 4]), __uint_as_float(sv[t + 5]));
+        mx3 = fmax3(mx3, __uint_as_float(sv[t + 6]), __uint_as_float(sv[t + 7]));
       }
       const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       // P_i(j-1) has been consumed and O_i is quiescent once p_empty flips (issued a whole softmax ago: no real wait)
@@ -234,8 +260,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
       // ---- lazy rescale: only when the maximum moved by more than 2^8 (always true on the first tile: m_used=-inf)
       const bool need = (mx - m_used) * sc > 8.f;
       if (j > 0 && __any_sync(0xffffffffu, need)) {
-        const float alpha = need ? exp2f((m_used - mx) * sc) : 1.f;
-        l *= alpha;
+        const float alpha = need ? exp2f((m_used - mx) * sc) : 1.f;   // also rescales the row-sum column O[:, D]
 #pragma unroll 1
         for (int c0 = 0; c0 < C::DPO; c0 += 16) {
           uint32_t v[16];
@@ -250,7 +275,6 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
       if (need) m_used = mx;
       const float ms = m_used * sc;
       // ---- P = exp2(S*scale - m) -> fp16 -> swizzled shared memory (A operand of the P V MMA); exp2(-inf) = 0 masks
-      float l0 = 0.f, l1 = 0.f;
 #pragma unroll
       for (int c8 = 0; c8 < BKV / 8; ++c8) {       // one 16-byte chunk (8 keys) at a time
         uint32_t pk[4];
@@ -258,18 +282,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
         for (int u = 0; u < 4; ++u) {
           const float e0 = fast_exp2(__uint_as_float(sv[c8 * 8 + 2 * u]) * sc - ms);
           const float e1 = fast_exp2(__uint_as_float(sv[c8 * 8 + 2 * u + 1]) * sc - ms);
-          const __half2 h = __floats2half2_rn(e0, e1);
-          const float2 back = __half22float2(h);    // the row sum uses the rounded probabilities the MMA sees
-          l0 += back.x;
-          l1 += back.y;
+          const __half2 h = __floats2half2_rn(e0, e1);   // the row sum is formed by the MMA from these rounded values
           pk[u] = *reinterpret_cast<const uint32_t*>(&h);
         }
         const uint32_t dst = p_row + ((c8 ^ (row & 7)) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
                      : "memory");
       }
-      l += l0 + l1;
-      fence_proxy_async();                       // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+      fence_proxy_async();                     // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       tc_fence_before();
       mbar_arrive(p_full(i));
     }
@@ -277,7 +297,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
     mbar_wait(o_full, 0);
     tc_fence_after();
     const int qrow = q0 + i * TQ + row;
-    const float inv = 1.f / l;
+    float inv;
+    {   // softmax denominator = the ones column of the accumulator
+      uint32_t v[16];
+      tmem_ld16(o_addr + (D / 16) * 16, v);
+      tmem_ld_wait();
+      inv = 1.f / __uint_as_float(v[D % 16]);
+    }
     __half* orow = p.o + b * p.o_bs + (long long)qrow * p.ldo + head * D;
 #pragma unroll 1
     for (int c0 = 0; c0 < C::DPO; c0 += 16) {

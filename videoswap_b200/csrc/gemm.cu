@@ -52,7 +52,8 @@ struct GemmParams {
   int ldc;
   int mode;
   int tma_epi;       // 1 = smem-staged (warp-transposed, coalesced) epilogue; 0 = direct stores for tiny / unaligned N
-  int b_resident;    // 1 = weight-stationary tile order with the [BN x K] panel resident in shared memory
+  int b_resident;    // stationary mode: 0 off, 1 = weight panel [BN x K] resident, 2 = activation panel [128 x K] resident
+  int cluster;       // 1, or 2 = CTA pairs sharing the weight tile through TMA multicast
 };
 
 template <int BN>
@@ -98,11 +99,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   //   1  weight panel [BN x K] resident, m fastest, only A is streamed;
   //   2  activation panel [128 x K] resident, n fastest, only B (L2-resident weights) is streamed: A is read from HBM
   //      exactly once (ncu on the K=320 QKV GEMM showed A being fetched 3x from DRAM with an L2 hit rate of 41%).
+  //
+  // Cluster mode (p.cluster == 2, stationary = 0): two CTAs of a cluster take the two M tiles of a tile *pair* with the
+  // same N tile; each loads its own A tile and HALF of the weight tile, multicast into both CTAs' shared memory, so the
+  // L2 -> SM traffic per MMA drops from 36 KB to 26 KB per k-block (ncu: the 128x160 tiles need ~31 TB/s of L2 feed at
+  // full tensor rate; the conv kernel sat at 44% tensor-pipe utilisation with nothing else saturated).
   const int stat = p.b_resident;
   const bool wres = stat != 0;
-  const int t_begin = wres ? (int)((long long)blockIdx.x * total_tiles / gridDim.x) : (int)blockIdx.x;
-  const int t_end = wres ? (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x) : total_tiles;
-  const int t_step = wres ? 1 : (int)gridDim.x;
+  const bool cl2 = p.cluster == 2;
+  const uint32_t crank = cl2 ? cluster_ctarank() : 0u;
+  const int pair_tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
+  const int t_begin = cl2 ? (int)(blockIdx.x >> 1) : wres ? (int)((long long)blockIdx.x * total_tiles / gridDim.x) : (int)blockIdx.x;
+  const int t_end = cl2 ? pair_tiles : wres ? (int)((long long)(blockIdx.x + 1) * total_tiles / gridDim.x) : total_tiles;
+  const int t_step = cl2 ? (int)(gridDim.x >> 1) : wres ? 1 : (int)gridDim.x;
   const uint32_t panel_bytes = stat == 1 ? (uint32_t)p.num_kb * C::B_STAGE_BYTES : stat == 2 ? (uint32_t)p.num_kb * A_STAGE_BYTES : 0u;
   const uint32_t ring_bytes = stat == 1 ? (uint32_t)A_STAGE_BYTES : stat == 2 ? (uint32_t)C::B_STAGE_BYTES : (uint32_t)C::STAGE_BYTES;
   auto a_stage = [&](int s, int kb) {
@@ -115,6 +124,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   auto decode = [&](int tile, int& m_tile, int& n_tile) {
     if (stat == 1) { n_tile = tile / p.m_tiles; m_tile = tile - n_tile * p.m_tiles; }
     else { m_tile = tile / p.n_tiles; n_tile = tile - m_tile * p.n_tiles; }
+    if (cl2) m_tile = 2 * m_tile + (int)crank;      // may be == m_tiles (odd count): an all-out-of-bounds dummy tile
   };
   auto panel_key = [&](int tile) { return stat == 1 ? tile / p.m_tiles : tile / p.n_tiles; };   // n-tile or m-tile id
 
@@ -126,7 +136,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), cl2 ? 2 : 1);       // cluster mode: both CTAs' MMAs must have drained the stage
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -139,6 +149,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if (cl2) cluster_sync_all();                    // peers' barriers are initialised before any multicast / remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -188,7 +199,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           } else {
             tma_load_2d(a_dst, tm, full_bar(s), c, m_tile * BM);
           }
-          if (!wres) tma_load_2d(b_dst, &p.tmB, full_bar(s), kb * BK, n_tile * BN);
+          if (cl2) {   // my half of the weight tile, delivered to both CTAs (tmB's box is BN/2 rows in cluster mode)
+            tma_load_2d_mc(b_dst + crank * (C::B_STAGE_BYTES / 2), &p.tmB, full_bar(s), kb * BK,
+                           n_tile * BN + (int)crank * (BN / 2), (uint16_t)0x3);
+          } else if (!wres) {
+            tma_load_2d(b_dst, &p.tmB, full_bar(s), kb * BK, n_tile * BN);
+          }
         }
       }
     }
@@ -224,7 +240,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             const uint64_t bd = umma_desc_sw128_kmajor(b_addr + k * 32);
             tc_mma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          tc_commit(empty_bar(s));   // frees the smem slot once these MMAs have read it
+          if (cl2) tc_commit_mc(empty_bar(s), (uint16_t)0x3);   // the peer's producer also writes into this slot
+          else tc_commit(empty_bar(s));   // frees the smem slot once these MMAs have read it
         }
         tc_commit(tfull_bar(acc));   // accumulator complete -> epilogue
         if (wres) {                  // last tile of this n-tile on this CTA: the panel may be overwritten afterwards
@@ -399,6 +416,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 
   tc_fence_before();
   __syncthreads();
+  if (cl2) cluster_sync_all();                    // nobody leaves while the peer may still signal or write into it
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -431,6 +449,25 @@ int launch(cudaStream_t st, GemmParams& p) {
   if (!configured) {
     VS_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
+  }
+  if (p.cluster == 2) {
+    const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
+    const int max_clusters = num_sms() / 2;
+    const int clusters = pairs < max_clusters ? pairs : max_clusters;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN>, p));
+    return 0;
   }
   const int total = p.m_tiles * p.n_tiles;
   int grid = total < num_sms() ? total : num_sms();
@@ -514,10 +551,18 @@ int gemm_tc(cudaStream_t st, const GemmArgs& a) {
       if (make_tmap_f16(&p.tmA2, a.A2, 2, dims, str, box, 1)) return 3;
     }
   }
+  // stationary modes (small K) and cluster mode (everything else with >= 2 M tiles) are mutually exclusive
+  p.b_resident = 0;
+  if (a.taps == 1 && !two && p.num_kb <= 5 && p.m_tiles >= 4 && (long long)p.m_tiles * p.n_tiles >= 2LL * num_sms()) {
+    const int opt = get_option("gemm_wres");            // 0 off, 1 weight panel resident, 2 activation panel resident
+    if (opt == 1) p.b_resident = 1;
+    else if (opt == 2 && p.n_tiles >= 2) p.b_resident = 2;
+  }
+  p.cluster = (p.b_resident == 0 && p.m_tiles >= 2 && get_option("gemm_cluster") != 0) ? 2 : 1;
   {
     const uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)a.N};
     const uint64_t str[1] = {(uint64_t)Ktot * 2};
-    const uint32_t box[2] = {BK, (uint32_t)bn};
+    const uint32_t box[2] = {BK, (uint32_t)(p.cluster == 2 ? bn / 2 : bn)};   // cluster mode: each CTA fetches half
     if (make_tmap_f16(&p.tmB, a.Bw, 2, dims, str, box, 1)) return 3;
   }
   // staged TMA-store epilogue whenever the output geometry allows it (16-byte strides, whole 32-column sub-tiles)
@@ -526,12 +571,6 @@ int gemm_tc(cudaStream_t st, const GemmArgs& a) {
               (!a.residual || ((a.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.residual) & 15) == 0)));
   if (!p.tma_epi) VS_REQUIRE(a.mode == EPI_LINEAR, "gemm_tc: GEGLU output needs 32-column aligned, 16-byte strided rows");
   // weight-stationary mode: plain GEMM, the whole K extent of the weight panel fits next to the A ring, enough M tiles
-  p.b_resident = 0;
-  if (a.taps == 1 && !two && p.num_kb <= 5 && p.m_tiles >= 4 && (long long)p.m_tiles * p.n_tiles >= 2LL * num_sms()) {
-    const int opt = get_option("gemm_wres");            // 0 off, 1 weight panel resident, 2 activation panel resident
-    if (opt == 1) p.b_resident = 1;
-    else if (opt == 2 && p.n_tiles >= 2) p.b_resident = 2;
-  }
   ProfScope prof(st, a.taps == 9 ? PC_CONV : PC_GEMM, 2.0 * a.M * (double)a.N * Ktot);
   switch (bn) {
     case 64: return launch<64>(st, p);
