@@ -80,9 +80,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // Bounded wait: a pipeline bug must trap (-> CUDA error at the next sync) instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
+  // try_wait suspends the thread in hardware for a bounded time, so this loop iterates every ~100 cycles; the watchdog
+  // counts iterations (2^25 of them is seconds) instead of reading the clock on the hot path
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
+    if (++spins > (1u << 25)) {
       printf("vs: mbarrier wait timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar, parity);
       __trap();
     }

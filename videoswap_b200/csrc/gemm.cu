@@ -54,6 +54,7 @@ struct GemmParams {
   int tma_epi;       // 1 = smem-staged (warp-transposed, coalesced) epilogue; 0 = direct stores for tiny / unaligned N
   int b_resident;    // stationary mode: 0 off, 1 = weight panel [BN x K] resident, 2 = activation panel [128 x K] resident
   int cluster;       // 1, or 2 = CTA pairs sharing the weight tile through TMA multicast
+  int stages;        // 0 = all, else limits the smem ring depth (pipeline-depth experiments)
 };
 
 template <int BN>
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
+  const int nst = (p.stages > 0 && p.stages < C::STAGES) ? p.stages : C::STAGES;   // ring depth (debug knob: "gemm_stages")
   // Tile order.  Default (stationary = 0): n fastest, tiles round-robin over CTAs.
   // Stationary modes (small K, one operand panel over the whole K extent fits in shared memory next to the ring of the
   // other operand); each CTA owns a contiguous range of tiles:
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   if (warp == 0) {
     if (lane == 0) {
       // ================================================================= TMA producer
-      uint32_t it = 0, npanel = 0;
+      uint32_t pr_s = 0, pr_ph = 0, npanel = 0;   // ring stage / phase, carried across tiles
       int cur_n = -1;
       for (int tile = t_begin; tile < t_end; tile += t_step) {
         int m_tile, n_tile;
@@ -177,34 +179,40 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           cur_n = panel_key(tile);
           ++npanel;
         }
-        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-          const int s = it % C::STAGES;
-          const uint32_t ph = (it / C::STAGES) & 1;
-          mbar_wait(empty_bar(s), ph ^ 1);
-          mbar_expect_tx(full_bar(s), ring_bytes);
+        // The k-block loop is ONE thread's dependent instruction chain, so it carries no division / modulo: stage,
+        // phase, tap offsets and channel coordinates are advanced incrementally.  (ncu: with `kb / kb_per_tap`, `tap / 3`
+        // and `it % stages` in here the loop cost ~600 cycles per k-block and capped the tensor pipe at 44%.)
+        const int n0 = n_tile * BN;
+        const int bn_row = cl2 ? n0 + (int)crank * (BN / 2) : n0;
+        const uint32_t b_half = cl2 ? crank * (C::B_STAGE_BYTES / 2) : 0u;
+        const int m0 = m_tile * BM;
+        int kcoord = 0;                          // K coordinate into the weight panel (kb * 64)
+        int dy = p.taps == 9 ? -1 : 0, dx = dy;  // tap offsets, advanced like an odometer
+        int r = 0;                               // k-block inside the tap
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          const int s = (int)pr_s;
+          mbar_wait(empty_bar(s), pr_ph ^ 1);
+          const uint32_t fb = full_bar(s);
+          mbar_expect_tx(fb, ring_bytes);
           const uint32_t a_dst = a_stage(s, kb);
           const uint32_t b_dst = b_stage(s, kb);
           if (stat == 2) {                         // activations are resident: stream the weight tile only
-            tma_load_2d(b_dst, &p.tmB, full_bar(s), kb * BK, n_tile * BN);
-            continue;
-          }
-          const int tap = kb / p.kb_per_tap;
-          const int r = kb - tap * p.kb_per_tap;
-          const CUtensorMap* tm = (r < p.kb_src1) ? &p.tmA : &p.tmA2;
-          const int c = (r < p.kb_src1) ? r * BK : (r - p.kb_src1) * BK;
-          if (p.a_rank == 4) {
-            const int dy = (p.taps == 9) ? tap / 3 - 1 : 0;
-            const int dx = (p.taps == 9) ? tap % 3 - 1 : 0;
-            tma_load_4d(a_dst, tm, full_bar(s), c, x0 + dx, y0 + dy, i0);
+            tma_load_2d(b_dst, &p.tmB, fb, kcoord, n0);
           } else {
-            tma_load_2d(a_dst, tm, full_bar(s), c, m_tile * BM);
+            const bool first = r < p.kb_src1;
+            const CUtensorMap* tm = first ? &p.tmA : &p.tmA2;
+            const int c = (first ? r : r - p.kb_src1) * BK;
+            if (p.a_rank == 4) tma_load_4d(a_dst, tm, fb, c, x0 + dx, y0 + dy, i0);
+            else tma_load_2d(a_dst, tm, fb, c, m0);
+            if (cl2) tma_load_2d_mc(b_dst + b_half, &p.tmB, fb, kcoord, bn_row, (uint16_t)0x3);   // my half, to both CTAs
+            else if (!wres) tma_load_2d(b_dst, &p.tmB, fb, kcoord, n0);
           }
-          if (cl2) {   // my half of the weight tile, delivered to both CTAs (tmB's box is BN/2 rows in cluster mode)
-            tma_load_2d_mc(b_dst + crank * (C::B_STAGE_BYTES / 2), &p.tmB, full_bar(s), kb * BK,
-                           n_tile * BN + (int)crank * (BN / 2), (uint16_t)0x3);
-          } else if (!wres) {
-            tma_load_2d(b_dst, &p.tmB, full_bar(s), kb * BK, n_tile * BN);
+          kcoord += BK;
+          if (++r == p.kb_per_tap) {               // next tap
+            r = 0;
+            if (++dx == 2) { dx = -1; ++dy; }
           }
+          if (++pr_s == (uint32_t)nst) { pr_s = 0; pr_ph ^= 1; }
         }
       }
     }
@@ -212,7 +220,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     if (lane == 0) {
       // ================================================================= MMA issuer
       constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
-      uint32_t it = 0, t = 0, npanel = 0;
+      uint32_t mm_s = 0, mm_ph = 0, t = 0, npanel = 0;
       int cur_n = -1;
       for (int tile = t_begin; tile < t_end; tile += t_step, ++t) {
         int m_tile, n_tile;
@@ -227,21 +235,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         mbar_wait(tempty_bar(acc), aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.num_kb; ++kb, ++it) {
-          const int s = it % C::STAGES;
-          const uint32_t ph = (it / C::STAGES) & 1;
-          mbar_wait(full_bar(s), ph);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          const int s = (int)mm_s;
+          mbar_wait(full_bar(s), mm_ph);
           tc_fence_after();
-          const uint32_t a_addr = a_stage(s, kb);
-          const uint32_t b_addr = b_stage(s, kb);
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            const uint64_t ad = umma_desc_sw128_kmajor(a_addr + k * 32);
-            const uint64_t bd = umma_desc_sw128_kmajor(b_addr + k * 32);
-            tc_mma_f16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
+          // one descriptor per operand per k-block; the K = 16 sub-steps advance the 16-byte-unit address field by 2
+          const uint64_t ad = umma_desc_sw128_kmajor(a_stage(s, kb));
+          const uint64_t bd = umma_desc_sw128_kmajor(b_stage(s, kb));
+          tc_mma_f16(d_tmem, ad, bd, idesc, kb != 0 ? 1u : 0u);
+          tc_mma_f16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+          tc_mma_f16(d_tmem, ad + 4, bd + 4, idesc, 1u);
+          tc_mma_f16(d_tmem, ad + 6, bd + 6, idesc, 1u);
           if (cl2) tc_commit_mc(empty_bar(s), (uint16_t)0x3);   // the peer's producer also writes into this slot
           else tc_commit(empty_bar(s));   // frees the smem slot once these MMAs have read it
+          if (++mm_s == (uint32_t)nst) { mm_s = 0; mm_ph ^= 1; }
         }
         tc_commit(tfull_bar(acc));   // accumulator complete -> epilogue
         if (wres) {                  // last tile of this n-tile on this CTA: the panel may be overwritten afterwards
@@ -558,6 +565,7 @@ int gemm_tc(cudaStream_t st, const GemmArgs& a) {
     if (opt == 1) p.b_resident = 1;
     else if (opt == 2 && p.n_tiles >= 2) p.b_resident = 2;
   }
+  p.stages = get_option("gemm_stages");
   p.cluster = (p.b_resident == 0 && p.m_tiles >= 2 && get_option("gemm_cluster") != 0) ? 2 : 1;
   {
     const uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)a.N};

@@ -112,11 +112,12 @@ ProfScope::~ProfScope() {
   if (idx_ >= 0) cudaEventRecord(g_prof[idx_].b, st_);
 }
 
-static int g_opt_attn_tc = 1, g_opt_gemm_wres = 2, g_opt_gemm_cluster = 0;
+static int g_opt_attn_tc = 1, g_opt_gemm_wres = 2, g_opt_gemm_cluster = 0, g_opt_gemm_stages = 0;
 int set_option(const char* name, int value) {
   if (strcmp(name, "attn_tc") == 0) { g_opt_attn_tc = value; return 0; }
   if (strcmp(name, "gemm_wres") == 0) { g_opt_gemm_wres = value; return 0; }
   if (strcmp(name, "gemm_cluster") == 0) { g_opt_gemm_cluster = value; return 0; }
+  if (strcmp(name, "gemm_stages") == 0) { g_opt_gemm_stages = value; return 0; }
   set_error("unknown option '%s'", name);
   return 2;
 }
@@ -124,6 +125,7 @@ int get_option(const char* name) {
   if (strcmp(name, "attn_tc") == 0) return g_opt_attn_tc;
   if (strcmp(name, "gemm_wres") == 0) return g_opt_gemm_wres;
   if (strcmp(name, "gemm_cluster") == 0) return g_opt_gemm_cluster;
+  if (strcmp(name, "gemm_stages") == 0) return g_opt_gemm_stages;
   return 0;
 }
 
