@@ -36,6 +36,68 @@ def test_two_rank_partition_and_timing():
     assert res[0][3] == res[1][3] == [0.0, 1.0]
 
 
+def _fake_unet(x, t, encoder_hidden_states=None, down_block_additional_residuals=None, return_dict=False):
+    """Stand-in for the native UNet (CUDA only): per-batch-element affine map, so halves are distinguishable."""
+    e = encoder_hidden_states.reshape(encoder_hidden_states.shape[0], -1).mean(dim=1).reshape(-1, 1, 1, 1, 1)
+    out = x * 0.5 + e
+    if down_block_additional_residuals is not None:
+        out = out + down_block_additional_residuals[0].mean()
+    return (out,)
+
+
+def _test_combine(eps, latents, g, a_t, a_p, cfg):
+    from videoswap_b200 import ops
+    c_x, c_e = ops.ddim_coefficients(a_t, a_p)
+    e = eps[0:1] + g * (eps[1:2] - eps[0:1]) if cfg else eps
+    return c_x * latents + c_e * e
+
+
+def _cfg_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import videoswap_b200.pipeline as P
+    P._combine = _test_combine                      # the product's combine is CUDA-only; the exchange logic is what we test
+    pipe = P.VideoSwapPipeline.__new__(P.VideoSwapPipeline)
+    pipe.unet = _fake_unet
+    pipe.scheduler = P.DDIMScheduler()
+    pipe.scheduler.set_timesteps(50)
+    g = torch.Generator().manual_seed(7)
+    lat = torch.randn((1, 4, 2, 4, 4), generator=g)
+    emb = torch.randn((2, 77, 8), generator=g)
+    res = [torch.randn((4, 3, 4, 4), generator=g)]          # [(B F), C, h, w] with B = 2 (CFG), F = 2
+    split = pipe.step(lat, 981, emb, 7.5, [r.clone() for r in res], cfg_group=dist.group.WORLD)
+    q.put((rank, split))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_cfg_split_two_ranks_equals_single_process():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_cfg_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    # single-process reference with the same fake UNet on the CFG batch of 2
+    import videoswap_b200.pipeline as P
+    g = torch.Generator().manual_seed(7)
+    lat = torch.randn((1, 4, 2, 4, 4), generator=g)
+    emb = torch.randn((2, 77, 8), generator=g)
+    r0 = torch.randn((4, 3, 4, 4), generator=g)
+    sched = P.DDIMScheduler()
+    sched.set_timesteps(50)
+    x2 = torch.cat([lat] * 2)
+    e = emb.reshape(2, -1).mean(dim=1).reshape(-1, 1, 1, 1, 1)
+    halves = r0.chunk(2, dim=0)
+    eps = torch.cat([x2[i:i + 1] * 0.5 + e[i:i + 1] + halves[i].mean() for i in range(2)])
+    ref = _test_combine(eps, lat, 7.5, *sched.alphas(981), True)
+    assert torch.allclose(res[0], ref, atol=1e-6) and torch.allclose(res[1], ref, atol=1e-6)
+
+
 def test_shard_jobs_covers_everything():
     for n in (0, 1, 7, 16):
         for w in (1, 2, 4, 8):

@@ -128,33 +128,40 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
 
+  // Single-issuer roles run with the whole warp (uniform values) and predicate the issuing instructions on one elected
+  // lane -- see the note in gemm.cu.
   if (warp == 0) {
-    if (lane == 0) {
-      // ============================================================== TMA producer
+    // ================================================================ TMA producer
+    if (elect_one()) {
       mbar_expect_tx(q_full, C::Q_BYTES);
       for (int i = 0; i < 2; ++i)
         for (int cb = 0; cb < C::NCB; ++cb)
           tma_load_4d(q_s + (i * C::NCB + cb) * TQ * 128, &p.tmQ, q_full, cb * 64, head, q0 + i * TQ, b);
-      const int bk = b / p.kv_div;
-      for (int j = 0; j < nkt; ++j) {
-        const int s = j % C::ST;
-        const uint32_t ph = (j / C::ST) & 1;
-        mbar_wait(kv_empty(s), ph ^ 1);
+    }
+    __syncwarp();
+    const int bk = b / p.kv_div;
+    uint32_t s = 0, ph = 0;
+    for (int j = 0; j < nkt; ++j) {
+      mbar_wait(kv_empty(s), ph ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(kv_full(s), C::KV_STAGE_BYTES);
         const uint32_t k_dst = kv_s + s * C::KV_STAGE_BYTES;
         const uint32_t v_dst = k_dst + C::NCB * C::KV_BLOCK_BYTES;
+#pragma unroll
         for (int cb = 0; cb < C::NCB; ++cb) {
           tma_load_4d(k_dst + cb * C::KV_BLOCK_BYTES, &p.tmK, kv_full(s), cb * 64, head, j * BKV, bk);
           tma_load_4d(v_dst + cb * C::KV_BLOCK_BYTES, &p.tmV, kv_full(s), cb * 64, head, j * BKV, bk);
         }
       }
+      __syncwarp();
+      if (++s == (uint32_t)C::ST) { s = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ============================================================== MMA issuer
-      constexpr uint32_t idesc_qk = umma_idesc_f16(TQ, BKV);
-      constexpr uint32_t idesc_pv = umma_idesc_f16(TQ, C::DPO) | (1u << 16);   // B operand MN-major
-      auto issue_qk = [&](int i, int s, int buf) {
+    // ================================================================ MMA issuer
+    constexpr uint32_t idesc_qk = umma_idesc_f16(TQ, BKV);
+    constexpr uint32_t idesc_pv = umma_idesc_f16(TQ, C::DPO) | (1u << 16);   // B operand MN-major
+    auto issue_qk = [&](int i, uint32_t s, int buf) {
+      if (elect_one()) {
         const uint32_t qa = q_s + i * C::NCB * TQ * 128;
         const uint32_t ka = kv_s + s * C::KV_STAGE_BYTES;
 #pragma unroll
@@ -164,8 +171,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
                      umma_desc_sw128_kmajor(ka + cb * C::KV_BLOCK_BYTES + off), idesc_qk, k != 0 ? 1u : 0u);
         }
         tc_commit(s_full(i, buf));
-      };
-      auto issue_pv = [&](int i, int s, bool acc) {
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](int i, uint32_t s, bool acc, bool release_kv) {
+      if (elect_one()) {
         const uint32_t pa = p_s + i * C::P_TILE_BYTES;
         const uint32_t va = kv_s + s * C::KV_STAGE_BYTES + C::NCB * C::KV_BLOCK_BYTES;
 #pragma unroll
@@ -173,35 +183,40 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
           tc_mma_f16(tmem + C::O_COL + i * C::O_STRIDE, umma_desc_sw128_kmajor(pa + k * 32),
                      umma_desc_sw128_mnmajor(va + k * 16 * 128, C::KV_BLOCK_BYTES), idesc_pv, (acc || k != 0) ? 1u : 0u);
         tc_commit(p_empty(i));                   // P_i consumed, O_i quiescent once this retires
-      };
-      mbar_wait(q_full, 0);
-      for (int jj = 0; jj < 2 && jj < nkt; ++jj) {     // Q K^T runs two key tiles ahead of the softmax
-        mbar_wait(kv_full(jj % C::ST), 0);
-        tc_fence_after();
-        issue_qk(0, jj % C::ST, jj & 1);
-        issue_qk(1, jj % C::ST, jj & 1);
+        if (release_kv) tc_commit(kv_empty(s));  // K_j / V_j fully consumed once these MMAs retire
       }
-      for (int j = 0; j < nkt; ++j) {
-        const int s = j % C::ST;
-        const int jn = j + 2, sn = jn % C::ST;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          mbar_wait(p_full(i), j & 1);
-          if (i == 0) mbar_wait(v_ready(s), (j / C::ST) & 1);   // ones column of this V tile is in place
-          tc_fence_after();
-          issue_pv(i, s, j > 0);
-          if (jn < nkt) {
-            if (i == 0) {
-              mbar_wait(kv_full(sn), (jn / C::ST) & 1);
-              tc_fence_after();
-            }
-            issue_qk(i, sn, j & 1);               // S_{i, j&1} was drained by the softmax before it signalled p_full
-          }
-        }
-        tc_commit(kv_empty(s));                  // K_j / V_j fully consumed once these MMAs retire
-      }
-      tc_commit(o_full);
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    for (int jj = 0; jj < 2 && jj < nkt; ++jj) {     // Q K^T runs two key tiles ahead of the softmax
+      mbar_wait(kv_full(jj), 0);
+      tc_fence_after();
+      issue_qk(0, jj, jj & 1);
+      issue_qk(1, jj, jj & 1);
     }
+    uint32_t s = 0, sph = 0;                         // stage / phase of tile j
+    uint32_t sn = 2 % C::ST, nph = (2 / C::ST) & 1;  // stage / phase of tile j + 2
+    for (int j = 0; j < nkt; ++j) {
+      const bool more = j + 2 < nkt;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        mbar_wait(p_full(i), j & 1);
+        if (i == 0) mbar_wait(v_ready(s), sph);      // ones column of this V tile is in place
+        tc_fence_after();
+        issue_pv(i, s, j > 0, i == 1);
+        if (more) {
+          if (i == 0) {
+            mbar_wait(kv_full(sn), nph);
+            tc_fence_after();
+          }
+          issue_qk(i, sn, j & 1);                    // S_{i, j&1} was drained by the softmax before it signalled p_full
+        }
+      }
+      if (++s == (uint32_t)C::ST) { s = 0; sph ^= 1; }
+      if (++sn == (uint32_t)C::ST) { sn = 0; nph ^= 1; }
+    }
+    if (elect_one()) tc_commit(o_full);
+    __syncwarp();
   } else if (warp == 3) {
     // ================================================================ ones column: V[:, D] = 1 for every landed V tile
     constexpr int blk = D / 64, chunk = ((D % 64) * 2) / 16, within = ((D % 64) * 2) % 16;

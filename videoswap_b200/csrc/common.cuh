@@ -114,6 +114,19 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, 
       : "memory");
 }
 
+// One lane of a fully converged warp.  The single-issuer roles (TMA producer, tcgen05.mma issuer) run their loops with
+// the WHOLE warp and predicate only the issuing instructions on this, so that addresses / descriptors stay warp-uniform
+// (uniform registers) instead of being re-broadcast through ELECT / VOTE / R2UR sequences inside a divergent branch.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- thread-block clusters: multicast TMA (one L2 read lands in the shared memory of every CTA in `mask`, at the same
 // CTA-relative offset, and signals the mbarrier at the same offset in each of them) and cluster-wide barriers.
 __device__ __forceinline__ uint32_t cluster_ctarank() {

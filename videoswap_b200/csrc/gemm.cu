@@ -155,106 +155,84 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // The two single-issuer roles below run with the WHOLE warp (all values warp-uniform) and predicate only the issuing
+  // instructions on one elected lane.  ncu showed that with the loops inside `if (lane == 0)` the MMA warp spent ~95% of
+  // the kernel executing its own 129-instruction loop body (ELECT / VOTEU / R2UR.BROADCAST sequences re-materialising
+  // the descriptors in uniform registers) and capped the tensor pipe at 44%; the loops also carry no division / modulo.
   if (warp == 0) {
-    if (lane == 0) {
-      // ================================================================= TMA producer
-      uint32_t pr_s = 0, pr_ph = 0, npanel = 0;   // ring stage / phase, carried across tiles
-      int cur_n = -1;
-      for (int tile = t_begin; tile < t_end; tile += t_step) {
-        int m_tile, n_tile;
-        decode(tile, m_tile, n_tile);
-        int x0 = 0, y0 = 0, i0 = 0;
-        if (p.a_rank == 4) {
-          x0 = (m_tile % p.tiles_x) * p.TW;
-          y0 = ((m_tile / p.tiles_x) % p.tiles_y) * p.TH;
-          i0 = (m_tile / (p.tiles_x * p.tiles_y)) * p.TN;
+    // =================================================================== TMA producer
+    const int num_kb = p.num_kb, kb_per_tap = p.kb_per_tap, kb_src1 = p.kb_src1;
+    const bool conv = p.a_rank == 4;
+    const int tap0 = p.taps == 9 ? -1 : 0;
+    uint32_t pr_s = 0, pr_ph = 0;              // ring stage / phase, carried across tiles
+    for (int tile = t_begin; tile < t_end; tile += t_step) {
+      int m_tile, n_tile;
+      decode(tile, m_tile, n_tile);
+      int x0 = 0, y0 = 0, i0 = 0;
+      if (conv) {
+        x0 = (m_tile % p.tiles_x) * p.TW;
+        y0 = ((m_tile / p.tiles_x) % p.tiles_y) * p.TH;
+        i0 = (m_tile / (p.tiles_x * p.tiles_y)) * p.TN;
+      }
+      const int n0 = n_tile * BN;
+      const int bn_row = cl2 ? n0 + (int)crank * (BN / 2) : n0;
+      const uint32_t b_half = cl2 ? crank * (C::B_STAGE_BYTES / 2) : 0u;
+      const int m0 = m_tile * BM;
+      int kcoord = 0;                          // K coordinate into the weight panel (kb * 64)
+      int dy = tap0, dx = tap0;                // tap offsets, advanced like an odometer
+      int r = 0;                               // k-block inside the tap
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty_bar(pr_s), pr_ph ^ 1);
+        if (elect_one()) {
+          const uint32_t fb = full_bar(pr_s);
+          const uint32_t a_dst = smem_base + pr_s * C::STAGE_BYTES;
+          mbar_expect_tx(fb, C::STAGE_BYTES);
+          const bool first = r < kb_src1;
+          const CUtensorMap* tm = first ? &p.tmA : &p.tmA2;
+          const int c = (first ? r : r - kb_src1) * BK;
+          if (conv) tma_load_4d(a_dst, tm, fb, c, x0 + dx, y0 + dy, i0);
+          else tma_load_2d(a_dst, tm, fb, c, m0);
+          if (cl2) tma_load_2d_mc(a_dst + A_STAGE_BYTES + b_half, &p.tmB, fb, kcoord, bn_row, (uint16_t)0x3);   // my half -> both CTAs
+          else tma_load_2d(a_dst + A_STAGE_BYTES, &p.tmB, fb, kcoord, n0);
         }
-        if (wres && panel_key(tile) != cur_n) {   // (re)load the resident panel
-          if (npanel > 0) mbar_wait(bfree_bar, (npanel - 1) & 1);
-          mbar_expect_tx(bfull_bar, panel_bytes);
-          for (int kb = 0; kb < p.num_kb; ++kb) {
-            if (stat == 1) tma_load_2d(b_stage(0, kb), &p.tmB, bfull_bar, kb * BK, n_tile * BN);
-            else tma_load_2d(a_stage(0, kb), &p.tmA, bfull_bar, kb * BK, m_tile * BM);
-          }
-          cur_n = panel_key(tile);
-          ++npanel;
+        __syncwarp();
+        kcoord += BK;
+        if (++r == kb_per_tap) {               // next tap
+          r = 0;
+          if (++dx == 2) { dx = -1; ++dy; }
         }
-        // The k-block loop is ONE thread's dependent instruction chain, so it carries no division / modulo: stage,
-        // phase, tap offsets and channel coordinates are advanced incrementally.  (ncu: with `kb / kb_per_tap`, `tap / 3`
-        // and `it % stages` in here the loop cost ~600 cycles per k-block and capped the tensor pipe at 44%.)
-        const int n0 = n_tile * BN;
-        const int bn_row = cl2 ? n0 + (int)crank * (BN / 2) : n0;
-        const uint32_t b_half = cl2 ? crank * (C::B_STAGE_BYTES / 2) : 0u;
-        const int m0 = m_tile * BM;
-        int kcoord = 0;                          // K coordinate into the weight panel (kb * 64)
-        int dy = p.taps == 9 ? -1 : 0, dx = dy;  // tap offsets, advanced like an odometer
-        int r = 0;                               // k-block inside the tap
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          const int s = (int)pr_s;
-          mbar_wait(empty_bar(s), pr_ph ^ 1);
-          const uint32_t fb = full_bar(s);
-          mbar_expect_tx(fb, ring_bytes);
-          const uint32_t a_dst = a_stage(s, kb);
-          const uint32_t b_dst = b_stage(s, kb);
-          if (stat == 2) {                         // activations are resident: stream the weight tile only
-            tma_load_2d(b_dst, &p.tmB, fb, kcoord, n0);
-          } else {
-            const bool first = r < p.kb_src1;
-            const CUtensorMap* tm = first ? &p.tmA : &p.tmA2;
-            const int c = (first ? r : r - p.kb_src1) * BK;
-            if (p.a_rank == 4) tma_load_4d(a_dst, tm, fb, c, x0 + dx, y0 + dy, i0);
-            else tma_load_2d(a_dst, tm, fb, c, m0);
-            if (cl2) tma_load_2d_mc(b_dst + b_half, &p.tmB, fb, kcoord, bn_row, (uint16_t)0x3);   // my half, to both CTAs
-            else if (!wres) tma_load_2d(b_dst, &p.tmB, fb, kcoord, n0);
-          }
-          kcoord += BK;
-          if (++r == p.kb_per_tap) {               // next tap
-            r = 0;
-            if (++dx == 2) { dx = -1; ++dy; }
-          }
-          if (++pr_s == (uint32_t)nst) { pr_s = 0; pr_ph ^= 1; }
-        }
+        if (++pr_s == (uint32_t)nst) { pr_s = 0; pr_ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ================================================================= MMA issuer
-      constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
-      uint32_t mm_s = 0, mm_ph = 0, t = 0, npanel = 0;
-      int cur_n = -1;
-      for (int tile = t_begin; tile < t_end; tile += t_step, ++t) {
-        int m_tile, n_tile;
-        decode(tile, m_tile, n_tile);
-        if (wres && panel_key(tile) != cur_n) {
-          mbar_wait(bfull_bar, npanel & 1);
-          ++npanel;
-          cur_n = panel_key(tile);
-        }
-        const int acc = t & 1;
-        const uint32_t aph = (t >> 1) & 1;
-        mbar_wait(tempty_bar(acc), aph ^ 1);
+    // =================================================================== MMA issuer
+    constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+    const int num_kb = p.num_kb;
+    uint32_t mm_s = 0, mm_ph = 0, t = 0;
+    for (int tile = t_begin; tile < t_end; tile += t_step, ++t) {
+      const int acc = t & 1;
+      const uint32_t aph = (t >> 1) & 1;
+      mbar_wait(tempty_bar(acc), aph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(mm_s), mm_ph);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          const int s = (int)mm_s;
-          mbar_wait(full_bar(s), mm_ph);
-          tc_fence_after();
+        if (elect_one()) {
           // one descriptor per operand per k-block; the K = 16 sub-steps advance the 16-byte-unit address field by 2
-          const uint64_t ad = umma_desc_sw128_kmajor(a_stage(s, kb));
-          const uint64_t bd = umma_desc_sw128_kmajor(b_stage(s, kb));
+          const uint32_t a_addr = smem_base + mm_s * C::STAGE_BYTES;
+          const uint64_t ad = umma_desc_sw128_kmajor(a_addr);
+          const uint64_t bd = umma_desc_sw128_kmajor(a_addr + A_STAGE_BYTES);
           tc_mma_f16(d_tmem, ad, bd, idesc, kb != 0 ? 1u : 0u);
           tc_mma_f16(d_tmem, ad + 2, bd + 2, idesc, 1u);
           tc_mma_f16(d_tmem, ad + 4, bd + 4, idesc, 1u);
           tc_mma_f16(d_tmem, ad + 6, bd + 6, idesc, 1u);
-          if (cl2) tc_commit_mc(empty_bar(s), (uint16_t)0x3);   // the peer's producer also writes into this slot
-          else tc_commit(empty_bar(s));   // frees the smem slot once these MMAs have read it
-          if (++mm_s == (uint32_t)nst) { mm_s = 0; mm_ph ^= 1; }
+          if (cl2) tc_commit_mc(empty_bar(mm_s), (uint16_t)0x3);   // the peer's producer also writes into this slot
+          else tc_commit(empty_bar(mm_s));   // frees the smem slot once these MMAs have read it
+          if (kb == num_kb - 1) tc_commit(tfull_bar(acc));   // accumulator complete -> epilogue
         }
-        tc_commit(tfull_bar(acc));   // accumulator complete -> epilogue
-        if (wres) {                  // last tile of this n-tile on this CTA: the panel may be overwritten afterwards
-          const int nxt = tile + t_step;
-          if (nxt >= t_end || panel_key(nxt) != cur_n) tc_commit(bfree_bar);
-        }
+        __syncwarp();
+        if (++mm_s == (uint32_t)nst) { mm_s = 0; mm_ph ^= 1; }
       }
     }
   } else if (warp >= 4) {
@@ -559,12 +537,9 @@ int gemm_tc(cudaStream_t st, const GemmArgs& a) {
     }
   }
   // stationary modes (small K) and cluster mode (everything else with >= 2 M tiles) are mutually exclusive
+  // (The operand-stationary tile orders that were tried for K <= 320 -- weight panel or activation panel resident in
+  // shared memory -- measured no gain on the B200 and were removed from the kernel)
   p.b_resident = 0;
-  if (a.taps == 1 && !two && p.num_kb <= 5 && p.m_tiles >= 4 && (long long)p.m_tiles * p.n_tiles >= 2LL * num_sms()) {
-    const int opt = get_option("gemm_wres");            // 0 off, 1 weight panel resident, 2 activation panel resident
-    if (opt == 1) p.b_resident = 1;
-    else if (opt == 2 && p.n_tiles >= 2) p.b_resident = 2;
-  }
   p.stages = get_option("gemm_stages");
   p.cluster = (p.b_resident == 0 && p.m_tiles >= 2 && get_option("gemm_cluster") != 0) ? 2 : 1;
   {

@@ -84,6 +84,13 @@ class SparsePointAdapter(nn.Module):
         return out
 
 
+def _combine(eps, latents, guidance_scale, a_t, a_p, cfg):
+    """CFG combine + DDIM update: the fused CUDA kernel (no CPU path)."""
+    if not eps.is_cuda:
+        raise RuntimeError("the CFG + DDIM update runs on CUDA only")
+    return ops.cfg_ddim_step(eps, latents, guidance_scale, a_t, a_p, cfg=cfg)
+
+
 class VideoSwapPipeline:
     """The denoising loop of the reference pipeline on the native path.  BASELINE.json's `TuneAVideoPipeline` alias."""
 
@@ -108,16 +115,31 @@ class VideoSwapPipeline:
 
     @torch.no_grad()
     def step(self, latents: torch.Tensor, t: int, embeds: torch.Tensor, guidance_scale: float = 7.5,
-             residuals: Optional[List[torch.Tensor]] = None) -> torch.Tensor:
+             residuals: Optional[List[torch.Tensor]] = None, cfg_group=None) -> torch.Tensor:
         """One loop body (pipeline_videoswap.py:556-587): CFG batch duplication -> UNet -> CFG combine -> DDIM step.
         `embeds` is [2,...] (uncond first) when guidance_scale > 1 else [1,...]; `scheduler.set_timesteps` must have
         been called.  Returns the new latents."""
         cfg = guidance_scale > 1.0
+        a_t, a_p = self.scheduler.alphas(t)
+        if cfg and cfg_group is not None:
+            # CFG split over two ranks (SURVEY 8e): the uncond / cond halves are independent through the whole UNet
+            # (GroupNorm statistics are per batch element), so rank r runs batch element r only and the two 0.5 MB
+            # noise predictions are exchanged with ONE all-gather (NCCL over NVLink) right before the combine.
+            import torch.distributed as dist
+            r = dist.get_rank(cfg_group)
+            assert dist.get_world_size(cfg_group) == 2, "CFG split needs a process group of exactly two ranks"
+            res_r = None
+            if residuals is not None:
+                res_r = [x.chunk(2, dim=0)[r].contiguous() for x in residuals]
+            eps_r = self.unet(latents, t, encoder_hidden_states=embeds[r:r + 1], down_block_additional_residuals=res_r,
+                              return_dict=False)[0]
+            eps = torch.empty((2,) + tuple(eps_r.shape[1:]), dtype=eps_r.dtype, device=eps_r.device)
+            dist.all_gather_into_tensor(eps, eps_r.contiguous(), group=cfg_group)
+            return _combine(eps, latents, guidance_scale, a_t, a_p, True)
         x_in = torch.cat([latents] * 2) if cfg else latents
         x_in = self.scheduler.scale_model_input(x_in, t)
         eps = self.unet(x_in, t, encoder_hidden_states=embeds, down_block_additional_residuals=residuals, return_dict=False)[0]
-        a_t, a_p = self.scheduler.alphas(t)
-        return ops.cfg_ddim_step(eps, latents, guidance_scale, a_t, a_p, cfg=cfg)
+        return _combine(eps, latents, guidance_scale, a_t, a_p, cfg)
 
     @torch.no_grad()
     def __call__(self, prompt_embeds: torch.Tensor, latents: torch.Tensor, negative_prompt_embeds: Optional[torch.Tensor] = None,
