@@ -217,6 +217,9 @@ def main():
         a, b, c = C.c_double(), C.c_double(), C.c_longlong()
         _lib.call("vs_profile_collect", ci, C.byref(a), C.byref(b), C.byref(c))
         prof[name] = {"ms_per_step": a.value / K, "work_per_step": b.value / K, "launches_per_step": c.value / K}
+    if rank == 0:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        lib.vs_profile_dump(os.path.join(ROOT, "gpurun_out", f"profile_shapes_n{world}.csv").encode())
     lib.vs_profile_reset()
     finite = bool(torch.isfinite(lat).all().item())
     ms_eager = ms

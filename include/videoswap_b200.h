@@ -127,6 +127,7 @@ int vs_profile_enable(int on);
 int vs_profile_reset(void);
 int vs_profile_collect(int category, double* ms, double* work, long long* count);
 long long vs_launch_count(void);   /* kernels launched by this library since load */
+int vs_profile_dump(const char* path);   /* CSV: category, shape (m,n,k), work per launch, launches, total ms */
 /* Runtime options: "attn_tc" = 1 (default) uses the tcgen05/TMEM attention kernel for head dims 40/80, 0 forces the
  * mma.sync kernel (A/B testing of the two implementations). */
 int vs_set_option(const char* name, int value);

@@ -54,6 +54,7 @@ _SIGNATURES = {
     "vs_profile_collect": (_I, [_I, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "vs_launch_count": (C.c_longlong, []),
     "vs_set_option": (_I, [C.c_char_p, _I]),
+    "vs_profile_dump": (_I, [C.c_char_p]),
     "vs_cfg_ddim_step": (_I, [_P, _P, _P, _I, _SZ, _I, _F, _F, _F, _P]),
     "vs_cfg_ddim_step_dev": (_I, [_P, _P, _P, _I, _SZ, _I, _F, _P, _P]),
     "vs_adapter_level": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _I, _I, _I, _I, _F, _I, _F, _P, _P]),

@@ -115,6 +115,10 @@ extern "C" int vs_profile_collect(int category, double* ms, double* work, long l
   return prof_collect(category, ms, work, count);
 }
 extern "C" long long vs_launch_count(void) { return launch_count(); }
+extern "C" int vs_profile_dump(const char* path) {
+  VS_REQUIRE(path != nullptr, "vs_profile_dump: null path");
+  return prof_dump(path);
+}
 extern "C" int vs_set_option(const char* name, int value) {
   VS_REQUIRE(name != nullptr, "vs_set_option: null name");
   return set_option(name, value);

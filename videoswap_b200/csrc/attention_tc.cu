@@ -377,7 +377,7 @@ int launch(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, 
   a.o = o; a.ldo = ldo; a.o_bs = o_bs; a.nq = nq; a.nk = nk; a.kv_div = kv_div;
   a.scale_log2 = 1.4426950408889634f / sqrtf((float)D);
   dim3 grid((nq + 2 * TQ - 1) / (2 * TQ), heads, batch);
-  ProfScope prof(st, PC_ATTN, 4.0 * batch * heads * (double)nq * nk * D);
+  ProfScope prof(st, PC_ATTN, 4.0 * batch * heads * (double)nq * nk * D, 1, nq, nk, D);
   attn_tc_kernel<D><<<grid, ATT_THREADS, C::SMEM, st>>>(a);
   VS_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -39,13 +39,14 @@ int num_sms();
 // profiling categories (work = algorithmic FLOPs for tensor kernels, algorithmic bytes for HBM-bound kernels)
 enum ProfCat { PC_GEMM = 0, PC_CONV = 1, PC_ATTN = 2, PC_TATTN = 3, PC_GROUPNORM = 4, PC_LAYERNORM = 5, PC_OTHER = 6, PC_COUNT = 7 };
 struct ProfScope {
-  ProfScope(cudaStream_t st, int cat, double work, int nlaunch = 1);
+  ProfScope(cudaStream_t st, int cat, double work, int nlaunch = 1, long long m = 0, int n = 0, int k = 0);
   ~ProfScope();
   cudaStream_t st_; int idx_;
 };
 void prof_enable(bool on);
 void prof_reset();
 int prof_collect(int cat, double* ms, double* work, long long* count);
+int prof_dump(const char* path);   // per-(category, shape) aggregate of the recorded launches as CSV
 long long launch_count();
 void count_launch(int n);
 

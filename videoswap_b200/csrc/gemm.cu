@@ -554,7 +554,7 @@ int gemm_tc(cudaStream_t st, const GemmArgs& a) {
               (!a.residual || ((a.ldr % 8 == 0) && ((reinterpret_cast<uintptr_t>(a.residual) & 15) == 0)));
   if (!p.tma_epi) VS_REQUIRE(a.mode == EPI_LINEAR, "gemm_tc: GEGLU output needs 32-column aligned, 16-byte strided rows");
   // weight-stationary mode: plain GEMM, the whole K extent of the weight panel fits next to the A ring, enough M tiles
-  ProfScope prof(st, a.taps == 9 ? PC_CONV : PC_GEMM, 2.0 * a.M * (double)a.N * Ktot);
+  ProfScope prof(st, a.taps == 9 ? PC_CONV : PC_GEMM, 2.0 * a.M * (double)a.N * Ktot, 1, a.M, a.N, Ktot);
   switch (bn) {
     case 64: return launch<64>(st, p);
     case 128: return launch<128>(st, p);

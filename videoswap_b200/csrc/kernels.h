@@ -39,7 +39,7 @@ constexpr int kGegluGranule = 64;            // value/gate column interleave gra
 // reference: imgs_per_set = F; per-frame GroupNorm: imgs_per_set = 1).  Input may be a virtual channel concat.
 // sums: [nstat, groups, 2] fp32 (sum, sum of squares); zeroed inside groupnorm_stats.
 int groupnorm_stats(cudaStream_t st, const __half* x1, int c1, const __half* x2, int c2, int nimg, int hw,
-                    int imgs_per_set, int groups, float* sums);
+                    int imgs_per_set, int groups, float* sums, bool zero_first = true);
 int groupnorm_apply(cudaStream_t st, const __half* x1, int c1, const __half* x2, int c2, int nimg, int hw,
                     int imgs_per_set, int groups, const float* sums, float eps, const float* gamma,
                     const float* beta, bool silu, __half* out);

@@ -216,11 +216,12 @@ __global__ void __launch_bounds__(256) ln5_kernel(const __half* __restrict__ x, 
 #pragma unroll
   for (int i = 0; i < 5; ++i) {
     const int c = (sub + i * LPR) * 8;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      g2[i][j] = __floats2half2_rn(gamma[c + 2 * j], gamma[c + 2 * j + 1]);
-      b2[i][j] = __floats2half2_rn(beta[c + 2 * j], beta[c + 2 * j + 1]);
-    }
+    const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma + c)), gb = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+    const float4 ba = __ldg(reinterpret_cast<const float4*>(beta + c)), bb = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+    g2[i][0] = __floats2half2_rn(ga.x, ga.y); g2[i][1] = __floats2half2_rn(ga.z, ga.w);
+    g2[i][2] = __floats2half2_rn(gb.x, gb.y); g2[i][3] = __floats2half2_rn(gb.z, gb.w);
+    b2[i][0] = __floats2half2_rn(ba.x, ba.y); b2[i][1] = __floats2half2_rn(ba.z, ba.w);
+    b2[i][2] = __floats2half2_rn(bb.x, bb.y); b2[i][3] = __floats2half2_rn(bb.z, bb.w);
   }
   const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -280,13 +281,13 @@ __global__ void __launch_bounds__(256) ln5_kernel(const __half* __restrict__ x, 
 }  // namespace
 
 int groupnorm_stats(cudaStream_t st, const __half* x1, int c1, const __half* x2, int c2, int nimg, int hw,
-                    int imgs_per_set, int groups, float* sums) {
+                    int imgs_per_set, int groups, float* sums, bool zero_first) {
   GnParams p{};
   dim3 grid;
   int threads;
   if (int e = gn_fill(p, grid, threads, x1, c1, x2, c2, nimg, hw, imgs_per_set, groups)) return e;
   p.sums = sums;
-  VS_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * groups * (nimg / imgs_per_set), st));
+  if (zero_first) VS_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * groups * (nimg / imgs_per_set), st));
   ProfScope prof(st, PC_GROUPNORM, 2.0 * nimg * (double)hw * (c1 + c2));   // bytes read
   gn_stats_kernel<<<grid, threads, groups * 2 * sizeof(float), st>>>(p);
   VS_CHECK_CUDA(cudaGetLastError());
@@ -302,7 +303,7 @@ int groupnorm_apply(cudaStream_t st, const __half* x1, int c1, const __half* x2,
   if (int e = gn_fill(p, grid, threads, x1, c1, x2, c2, nimg, hw, imgs_per_set, groups)) return e;
   p.sums = const_cast<float*>(sums);
   p.gamma = gamma; p.beta = beta; p.eps = eps; p.silu = silu ? 1 : 0; p.out = out;
-  ProfScope prof(st, PC_GROUPNORM, 4.0 * nimg * (double)hw * (c1 + c2));   // bytes read + written
+  ProfScope prof(st, PC_GROUPNORM, 4.0 * nimg * (double)hw * (c1 + c2), 1, (long long)nimg * hw, c1 + c2, imgs_per_set);
   gn_apply_kernel<<<grid, threads, 0, st>>>(p);
   VS_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -316,10 +317,11 @@ int layernorm(cudaStream_t st, const __half* x, int rows, int C, const float* ga
   const int blocks = (rows + wpb - 1) / wpb;
   if (hw <= 0) hw = 1;
   if (F <= 0) F = 1;
-  ProfScope prof(st, PC_LAYERNORM, 4.0 * rows * (double)C);
+  ProfScope prof(st, PC_LAYERNORM, 4.0 * rows * (double)C, 1, rows, C, pe ? 1 : 0);
   if (C == 320 || C == 640 || C == 1280) {
     const int lpr = C / 40, rpw = 32 / lpr;
-    long long need = ((long long)rows + rpw * 8 - 1) / (rpw * 8);     // blocks of 8 warps
+    long long need = ((long long)rows + rpw * 8 * 4 - 1) / (rpw * 8 * 4);   // blocks of 8 warps, >= 4 row groups per warp
+    if (need < 1) need = 1;
     const long long cap = (long long)num_sms() * 8;
     const int grid = (int)(need < cap ? need : cap);
     if (lpr == 8) ln5_kernel<8><<<grid, 256, 0, st>>>(x, rows, gamma, beta, pe, hw, F, out);

@@ -90,20 +90,20 @@ namespace vs {
 
 static std::atomic<long long> g_launches{0};
 static bool g_prof_on = false;
-struct ProfEntry { cudaEvent_t a, b; int cat; double work; };
+struct ProfEntry { cudaEvent_t a, b; int cat; double work; long long m; int n, k; };
 static std::vector<ProfEntry> g_prof;
 static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_pool;
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(); }
 
-ProfScope::ProfScope(cudaStream_t st, int cat, double work, int nlaunch) : st_(st), idx_(-1) {
+ProfScope::ProfScope(cudaStream_t st, int cat, double work, int nlaunch, long long m, int n, int k) : st_(st), idx_(-1) {
   count_launch(nlaunch);
   if (!g_prof_on) return;
   ProfEntry e;
   if (!g_pool.empty()) { e.a = g_pool.back().first; e.b = g_pool.back().second; g_pool.pop_back(); }
   else { cudaEventCreate(&e.a); cudaEventCreate(&e.b); }
-  e.cat = cat; e.work = work;
+  e.cat = cat; e.work = work; e.m = m; e.n = n; e.k = k;
   cudaEventRecord(e.a, st);
   idx_ = (int)g_prof.size();
   g_prof.push_back(e);
@@ -126,6 +126,28 @@ int get_option(const char* name) {
   if (strcmp(name, "gemm_wres") == 0) return g_opt_gemm_wres;
   if (strcmp(name, "gemm_cluster") == 0) return g_opt_gemm_cluster;
   if (strcmp(name, "gemm_stages") == 0) return g_opt_gemm_stages;
+  return 0;
+}
+
+int prof_dump(const char* path) {
+  struct Agg { int cat; long long m; int n, k; double work, ms; long long count; };
+  std::vector<Agg> aggs;
+  for (auto& e : g_prof) {
+    if (cudaEventSynchronize(e.b) != cudaSuccess) { set_error("profile: event sync failed"); return 1; }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e.a, e.b);
+    Agg* hit = nullptr;
+    for (auto& a : aggs)
+      if (a.cat == e.cat && a.m == e.m && a.n == e.n && a.k == e.k && a.work == e.work) { hit = &a; break; }
+    if (!hit) { aggs.push_back(Agg{e.cat, e.m, e.n, e.k, e.work, 0.0, 0}); hit = &aggs.back(); }
+    hit->ms += ms;
+    hit->count += 1;
+  }
+  FILE* f = fopen(path, "w");
+  if (!f) { set_error("cannot open %s", path); return 2; }
+  fprintf(f, "category,m,n,k,work_per_launch,launches,total_ms\n");
+  for (auto& a : aggs) fprintf(f, "%d,%lld,%d,%d,%.6g,%lld,%.4f\n", a.cat, a.m, a.n, a.k, a.work, a.count, a.ms);
+  fclose(f);
   return 0;
 }
 

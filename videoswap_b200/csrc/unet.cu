@@ -319,7 +319,11 @@ struct Ctx {
   vs_unet* h; cudaStream_t st;
   int B, F, NI, H, W;      // W/H are the CURRENT resolution during the walk
   const __half* ehs; int ehs_tokens, ehs_layers;
+  int gn_idx = 0;          // GroupNorm call counter: every call owns a slice of F_SUMS, all zeroed by ONE memset per forward
 };
+
+constexpr int kMaxGroupNorms = 128;
+inline float* next_sums(Ctx& c) { return c.h->F_SUMS + (size_t)(c.gn_idx++ % kMaxGroupNorms) * ((size_t)c.NI * 64); }
 
 #define RUN(expr) do { if (int _e = (expr)) return _e; } while (0)
 
@@ -354,11 +358,13 @@ int resnet(Ctx& c, const Resnet& r, const __half* in1, int C1, const __half* in2
   const int hw = c.H * c.W, G = h->cfg.norm_num_groups;
   const float eps = h->cfg.norm_eps;
   VS_REQUIRE(C1 + C2 == r.cin, "internal: resnet input channels %d+%d != %d", C1, C2, r.cin);
-  RUN(groupnorm_stats(c.st, in1, C1, in2, C2, c.NI, hw, c.F, G, h->F_SUMS));
-  RUN(groupnorm_apply(c.st, in1, C1, in2, C2, c.NI, hw, c.F, G, h->F_SUMS, eps, r.n1.g, r.n1.b, true, h->XN));
+  float* sums = next_sums(c);
+  RUN(groupnorm_stats(c.st, in1, C1, in2, C2, c.NI, hw, c.F, G, sums, false));
+  RUN(groupnorm_apply(c.st, in1, C1, in2, C2, c.NI, hw, c.F, G, sums, eps, r.n1.g, r.n1.b, true, h->XN));
   RUN(conv(c, h->XN, r.cin, r.c1, h->F_TPROJ + r.temb_off, nullptr, h->T));
-  RUN(groupnorm_stats(c.st, h->T, r.cout, nullptr, 0, c.NI, hw, c.F, G, h->F_SUMS));
-  RUN(groupnorm_apply(c.st, h->T, r.cout, nullptr, 0, c.NI, hw, c.F, G, h->F_SUMS, eps, r.n2.g, r.n2.b, true, h->XN));
+  sums = next_sums(c);
+  RUN(groupnorm_stats(c.st, h->T, r.cout, nullptr, 0, c.NI, hw, c.F, G, sums, false));
+  RUN(groupnorm_apply(c.st, h->T, r.cout, nullptr, 0, c.NI, hw, c.F, G, sums, eps, r.n2.g, r.n2.b, true, h->XN));
   const __half* residual = in1;
   if (r.has_sc) {
     GemmArgs g;
@@ -384,8 +390,9 @@ int geglu_ff(Ctx& c, const __half* tn, int M, int C, const __half* w1, const flo
 int transformer(Ctx& c, const Transformer& t, __half* x) {
   vs_unet* h = c.h;
   const int hw = c.H * c.W, C = t.C, M = c.NI * hw, heads = h->cfg.num_heads, d = C / heads;
-  RUN(groupnorm_stats(c.st, x, C, nullptr, 0, c.NI, hw, 1, h->cfg.norm_num_groups, h->F_SUMS));
-  RUN(groupnorm_apply(c.st, x, C, nullptr, 0, c.NI, hw, 1, h->cfg.norm_num_groups, h->F_SUMS, 1e-6f, t.norm.g, t.norm.b, false, h->XN));
+  float* sums = next_sums(c);
+  RUN(groupnorm_stats(c.st, x, C, nullptr, 0, c.NI, hw, 1, h->cfg.norm_num_groups, sums, false));
+  RUN(groupnorm_apply(c.st, x, C, nullptr, 0, c.NI, hw, 1, h->cfg.norm_num_groups, sums, 1e-6f, t.norm.g, t.norm.b, false, h->XN));
   RUN(linear(c, h->XN, M, t.proj_in, nullptr, h->T));
   // self-attention
   RUN(layernorm(c.st, h->T, M, C, t.ln1.g, t.ln1.b, nullptr, 1, 1, h->TN));
@@ -423,8 +430,9 @@ int motion(Ctx& c, const Motion& m, int level, __half* x) {
   vs_unet* h = c.h;
   const int hw = c.H * c.W, C = m.C, M = c.NI * hw;
   VS_REQUIRE(c.F <= h->cfg.pe_max_len, "video_length %d exceeds temporal_position_encoding_max_len %d", c.F, h->cfg.pe_max_len);
-  RUN(groupnorm_stats(c.st, x, C, nullptr, 0, c.NI, hw, 1, 32, h->F_SUMS));
-  RUN(groupnorm_apply(c.st, x, C, nullptr, 0, c.NI, hw, 1, 32, h->F_SUMS, 1e-6f, m.norm.g, m.norm.b, false, h->XN));
+  float* sums = next_sums(c);
+  RUN(groupnorm_stats(c.st, x, C, nullptr, 0, c.NI, hw, 1, 32, sums, false));
+  RUN(groupnorm_apply(c.st, x, C, nullptr, 0, c.NI, hw, 1, 32, sums, 1e-6f, m.norm.g, m.norm.b, false, h->XN));
   RUN(linear(c, h->XN, M, m.proj_in, nullptr, h->T));
   for (int i = 0; i < 2; ++i) {
     RUN(layernorm(c.st, h->T, M, C, m.ln[i].g, m.ln[i].b, h->pe[level], hw, c.F, h->TN));
@@ -478,7 +486,7 @@ int ensure_workspace(vs_unet* h, int B, int F, int H, int W) {
   for (auto& r : req) total += align_up(r.second * 2);
   const int temb = boc[0] * 4;
   const size_t fl = align_up(4 * 64) + align_up((size_t)B * boc[0] * 4) + 2 * align_up((size_t)B * temb * 4) +
-                    align_up((size_t)B * h->tproj_n * 4) + align_up((size_t)NI * 64 * 2 * 4);
+                    align_up((size_t)B * h->tproj_n * 4) + align_up((size_t)kMaxGroupNorms * NI * 64 * 4);
   total += fl;
   VS_CHECK_CUDA(cudaMalloc(&h->ws, total));
   h->ws_bytes = total;
@@ -532,6 +540,7 @@ extern "C" int vs_unet_forward(vs_unet* h, void* stream, const void* d_sample, i
   const int temb = boc[0] * 4, lpb = cf.layers_per_block;
   Ctx c{h, st, B, F, B * F, H, W, (const __half*)d_ehs, ehs_tokens, ehs_layers};
 
+  VS_CHECK_CUDA(cudaMemsetAsync(h->F_SUMS, 0, (size_t)kMaxGroupNorms * c.NI * 64 * sizeof(float), st));
   // ---- time embedding (unet.py:376-397): Timesteps -> Linear -> SiLU -> Linear; then every resnet's projection of
   //      SiLU(emb) in one stacked tiny-M linear (resnet.py:171-172)
   RUN(timestep_embedding(st, d_timesteps, B, boc[0], h->F_TE0));
@@ -637,8 +646,9 @@ extern "C" int vs_unet_forward(vs_unet* h, void* stream, const void* d_sample, i
   }
   VS_REQUIRE(c.H == H && c.W == W, "input H/W (%d,%d) must be multiples of 8 (the reference's forward_upsample_size path is not implemented)", H, W);
   // ---- out: GroupNorm(5-D) + SiLU + conv_out
-  RUN(groupnorm_stats(st, cur, curC, nullptr, 0, c.NI, H * W, F, cf.norm_num_groups, h->F_SUMS));
-  RUN(groupnorm_apply(st, cur, curC, nullptr, 0, c.NI, H * W, F, cf.norm_num_groups, h->F_SUMS, cf.norm_eps, h->norm_out.g, h->norm_out.b, true, h->XN));
+  float* osums = next_sums(c);
+  RUN(groupnorm_stats(st, cur, curC, nullptr, 0, c.NI, H * W, F, cf.norm_num_groups, osums, false));
+  RUN(groupnorm_apply(st, cur, curC, nullptr, 0, c.NI, H * W, F, cf.norm_num_groups, osums, cf.norm_eps, h->norm_out.g, h->norm_out.b, true, h->XN));
   {
     GemmArgs g;
     g.A = h->XN; g.K1 = curC; g.lda1 = curC; g.Bw = h->conv_out.w; g.taps = 9; g.nimg = c.NI; g.H = H; g.W = W;
