@@ -147,6 +147,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the CUDA-graph replay")
     ap.add_argument("--frames", type=int, default=FRAMES)
+    ap.add_argument("--option", action="append", default=[], help="kernel A/B switch name=value (vs_set_option)")
+    ap.add_argument("--tag", default="", help="suffix of the per-shape profile CSV")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -182,6 +184,9 @@ def main():
         return pipe.step(lat, ts[i % len(ts)], embeds, 7.5, list(residuals))
 
     lib = _lib.lib()
+    for opt in args.option:
+        name, val = opt.split("=")
+        _lib.call("vs_set_option", name.encode(), int(val))
     lat = lat0
     for i in range(W):
         lat = step(lat, i)
@@ -219,7 +224,7 @@ def main():
         prof[name] = {"ms_per_step": a.value / K, "work_per_step": b.value / K, "launches_per_step": c.value / K}
     if rank == 0:
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        lib.vs_profile_dump(os.path.join(ROOT, "gpurun_out", f"profile_shapes_n{world}.csv").encode())
+        lib.vs_profile_dump(os.path.join(ROOT, "gpurun_out", f"profile_shapes_n{world}{args.tag}.csv").encode())
     lib.vs_profile_reset()
     finite = bool(torch.isfinite(lat).all().item())
     ms_eager = ms

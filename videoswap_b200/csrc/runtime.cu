@@ -112,20 +112,25 @@ ProfScope::~ProfScope() {
   if (idx_ >= 0) cudaEventRecord(g_prof[idx_].b, st_);
 }
 
-static int g_opt_attn_tc = 1, g_opt_gemm_wres = 2, g_opt_gemm_cluster = 0, g_opt_gemm_stages = 0;
+// A/B switches of the kernels (name, value).  Defaults are the shipped configuration.
+struct Option { const char* name; int value; };
+static Option g_options[] = {
+    {"attn_tc", 1},        // tcgen05 attention for d = 40 / 80 (0 = mma.sync kernel)
+    {"gemm_wres", 0},      // unused (kept so old scripts do not fail)
+    {"gemm_cluster", 0},   // CTA pairs multicasting the weight tile
+    {"gemm_stages", 0},    // smem ring depth limit (0 = all)
+    {"gemm_order", 0},     // persistent tile order: 0 = n fastest, 1 = m fastest
+    {"exp_a", 0}, {"exp_b", 0}, {"exp_c", 0},   // scratch switches for experiments
+};
 int set_option(const char* name, int value) {
-  if (strcmp(name, "attn_tc") == 0) { g_opt_attn_tc = value; return 0; }
-  if (strcmp(name, "gemm_wres") == 0) { g_opt_gemm_wres = value; return 0; }
-  if (strcmp(name, "gemm_cluster") == 0) { g_opt_gemm_cluster = value; return 0; }
-  if (strcmp(name, "gemm_stages") == 0) { g_opt_gemm_stages = value; return 0; }
+  for (Option& o : g_options)
+    if (strcmp(name, o.name) == 0) { o.value = value; return 0; }
   set_error("unknown option '%s'", name);
   return 2;
 }
 int get_option(const char* name) {
-  if (strcmp(name, "attn_tc") == 0) return g_opt_attn_tc;
-  if (strcmp(name, "gemm_wres") == 0) return g_opt_gemm_wres;
-  if (strcmp(name, "gemm_cluster") == 0) return g_opt_gemm_cluster;
-  if (strcmp(name, "gemm_stages") == 0) return g_opt_gemm_stages;
+  for (const Option& o : g_options)
+    if (strcmp(name, o.name) == 0) return o.value;
   return 0;
 }
 
