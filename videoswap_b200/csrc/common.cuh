@@ -232,7 +232,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
          | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }   // 2 MUFU + 3 FP32
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 // Exact-erf GELU with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below fp16 resolution):
 // erf(z) = 1 - (a1 t + a2 t^2 + ... + a5 t^5) exp(-z^2), t = 1 / (1 + p z), z >= 0.  Two MUFU ops + ~12 FP32 ops.

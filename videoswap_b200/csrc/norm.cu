@@ -225,55 +225,69 @@ __global__ void __launch_bounds__(256) ln5_kernel(const __half* __restrict__ x, 
   }
   const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long r0 = warp_global * RPW; r0 < rows; r0 += nwarps * RPW) {
-    const long long row = r0 + rw;
-    const bool active = row < rows;
-    const __half* xr = x + (active ? row : 0) * C;
-    uint4 v[5];
+  // Two row groups per iteration (2 x 5 independent 16-byte loads in flight per thread) hide the HBM latency that the
+  // shuffle reductions would otherwise expose.
+  for (long long r0 = warp_global * (2 * RPW); r0 < rows; r0 += nwarps * (2 * RPW)) {
+    long long row[2];
+    bool active[2];
+    uint4 v[2][5];
 #pragma unroll
-    for (int i = 0; i < 5; ++i) v[i] = *reinterpret_cast<const uint4*>(xr + (sub + i * LPR) * 8);
-    float s = 0.f;
+    for (int u = 0; u < 2; ++u) {
+      row[u] = r0 + u * RPW + rw;
+      active[u] = row[u] < rows;
+      const __half* xr = x + (active[u] ? row[u] : 0) * C;
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); s += f.x + f.y; }
+      for (int i = 0; i < 5; ++i) v[u][i] = *reinterpret_cast<const uint4*>(xr + (sub + i * LPR) * 8);
     }
 #pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s * (1.f / C);
-    float q = 0.f;
+    for (int u = 0; u < 2; ++u) {
+      float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
+      for (int i = 0; i < 5; ++i) {
+        const __half2* h = reinterpret_cast<const __half2*>(&v[u][i]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(h[j]);
-        q += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+        for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); s += f.x + f.y; }
       }
-    }
 #pragma unroll
-    for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float rstd = rsqrtf(q * (1.f / C) + 1e-5f);
-    if (!active) continue;
-    const float* per = pe ? pe + (long long)((row / hw) % F) * C : nullptr;
-    __half* orow = out + row * C;
+      for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s * (1.f / C);
+      float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < 5; ++i) {
-      const int c = (sub + i * LPR) * 8;
-      const __half2* h = reinterpret_cast<const __half2*>(&v[i]);
-      uint4 o;
-      __half2* oh = reinterpret_cast<__half2*>(&o);
+      for (int i = 0; i < 5; ++i) {
+        const __half2* h = reinterpret_cast<const __half2*>(&v[u][i]);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(h[j]);
-        const float2 gg = __half22float2(g2[i][j]), bb = __half22float2(b2[i][j]);
-        float y0 = (f.x - mean) * rstd * gg.x + bb.x;
-        float y1 = (f.y - mean) * rstd * gg.y + bb.y;
-        if (per) { y0 += per[c + 2 * j]; y1 += per[c + 2 * j + 1]; }
-        oh[j] = __floats2half2_rn(y0, y1);
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h[j]);
+          q += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+        }
       }
-      *reinterpret_cast<uint4*>(orow + c) = o;
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = rsqrtf(q * (1.f / C) + 1e-5f);
+      if (!active[u]) continue;
+      const float* per = pe ? pe + (long long)((row[u] / hw) % F) * C : nullptr;
+      __half* orow = out + row[u] * C;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const int c = (sub + i * LPR) * 8;
+        const __half2* h = reinterpret_cast<const __half2*>(&v[u][i]);
+        float pv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (per) {
+          const float4 pa = __ldg(reinterpret_cast<const float4*>(per + c)), pb = __ldg(reinterpret_cast<const float4*>(per + c + 4));
+          pv[0] = pa.x; pv[1] = pa.y; pv[2] = pa.z; pv[3] = pa.w; pv[4] = pb.x; pv[5] = pb.y; pv[6] = pb.z; pv[7] = pb.w;
+        }
+        uint4 o;
+        __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h[j]);
+          const float2 gg = __half22float2(g2[i][j]), bb = __half22float2(b2[i][j]);
+          const float y0 = (f.x - mean) * rstd * gg.x + bb.x + pv[2 * j];
+          const float y1 = (f.y - mean) * rstd * gg.y + bb.y + pv[2 * j + 1];
+          oh[j] = __floats2half2_rn(y0, y1);
+        }
+        *reinterpret_cast<uint4*>(orow + c) = o;
+      }
     }
   }
 }
@@ -320,7 +334,7 @@ int layernorm(cudaStream_t st, const __half* x, int rows, int C, const float* ga
   ProfScope prof(st, PC_LAYERNORM, 4.0 * rows * (double)C, 1, rows, C, pe ? 1 : 0);
   if (C == 320 || C == 640 || C == 1280) {
     const int lpr = C / 40, rpw = 32 / lpr;
-    long long need = ((long long)rows + rpw * 8 * 4 - 1) / (rpw * 8 * 4);   // blocks of 8 warps, >= 4 row groups per warp
+    long long need = ((long long)rows + rpw * 8 * 4 - 1) / (rpw * 8 * 4);   // blocks of 8 warps, >= 2 double row groups per warp
     if (need < 1) need = 1;
     const long long cap = (long long)num_sms() * 8;
     const int grid = (int)(need < cap ? need : cap);
