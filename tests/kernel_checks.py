@@ -250,15 +250,19 @@ def with_option(name, value, fn, restore):
 
 
 CHECKS = {
-    # 2-CTA cluster mode (weight tile shared by TMA multicast): odd tile counts, concat, conv, epilogue variants
-    "cluster_gemm": with_option("gemm_cluster", 1, lambda: check_gemm(1024, 1280, 1280, residual=True, seed=7), 0),
-    "cluster_gemm_odd_m": with_option("gemm_cluster", 1, lambda: check_gemm(128 * 5 + 9, 640, 640, seed=8), 0),
-    "cluster_gemm_bn128": with_option("gemm_cluster", 1, lambda: check_gemm(700, 768, 640, bn=128, seed=9), 0),
-    "cluster_geglu": with_option("gemm_cluster", 1, lambda: check_geglu(M=1000, C=640, seed=32), 0),
-    "cluster_concat": with_option("gemm_cluster", 1, check_gemm_concat, 0),
-    "cluster_conv": with_option("gemm_cluster", 1, lambda: check_conv3x3(rowvec=True, residual=True), 0),
-    "cluster_conv_odd": with_option("gemm_cluster", 1, lambda: _conv_odd(3, 7, 12, 320, 320, 55), 0),
-    "cluster_conv_w64": with_option("gemm_cluster", 1, lambda: check_conv3x3(n=2, H=64, W=64, ci=64, co=160), 0),
+    # BN = 256 tiles (picked by the wave x feed model for wide N / many rows), with every epilogue specialisation
+    "gemm_bn256": lambda: check_gemm(8192, 3840, 640, seed=7),
+    "gemm_bn256_res": lambda: check_gemm(128 * 150 + 9, 1280, 320, residual=True, seed=8),
+    "gemm_bn256_forced_tail": lambda: check_gemm(700, 768, 640, bn=256, seed=9),
+    "conv_bn256": lambda: check_conv3x3(n=16, H=32, W=32, ci=320, co=1280, rowvec=True, residual=True),
+    # tile counts that leave one epilogue warpgroup (accumulator stage) without work on some CTAs
+    "gemm_one_tile": lambda: check_gemm(100, 128, 64, seed=10),
+    "gemm_149_tiles": lambda: check_gemm(128 * 149, 128, 128, residual=True, seed=11),
+    # tcgen05 attention variants kept for A/B measurements: two threads per query row, FMA-pipe exponentials
+    "self_attn_d40_split2": with_option("attn_split", 2, lambda: check_self_attention(B=2, N=600, C=320, seed=121), 1),
+    "self_attn_d80_split2": with_option("attn_split", 2, lambda: check_self_attention(B=2, N=300, C=640, seed=123), 1),
+    "cross_attn_split2": with_option("attn_split", 2, lambda: check_cross_attention(B=2, Fr=2, N=300, C=320, seed=131), 1),
+    "self_attn_d40_poly": with_option("attn_poly", 1, lambda: check_self_attention(B=2, N=600, C=320, seed=121), 0),
     "gemm_bn160": lambda: check_gemm(512, 320, 320),
     "gemm_bn128_tail": lambda: check_gemm(300, 768, 320, bn=128),
     "gemm_bn64": lambda: check_gemm(130, 64, 128, bn=64),
@@ -266,9 +270,9 @@ CHECKS = {
     "gemm_small_m": lambda: check_gemm(77, 640, 768),
     "gemm_big_k": lambda: check_gemm(256, 320, 5120),
     "gemm_many_tiles": lambda: check_gemm(128 * 150 + 5, 320, 64),
-    "gemm_wres_qkv": lambda: check_gemm(40000, 960, 320, residual=True, seed=5),      # weight-stationary mode
-    "gemm_wres_k64": lambda: check_gemm(128 * 300 + 77, 640, 64, bias=False, seed=6),
-    "geglu_wres": lambda: check_geglu(M=20000, C=320, seed=31),
+    "gemm_qkv_rows": lambda: check_gemm(40000, 960, 320, residual=True, seed=5),
+    "gemm_k64": lambda: check_gemm(128 * 300 + 77, 640, 64, bias=False, seed=6),
+    "geglu_rows": lambda: check_geglu(M=20000, C=320, seed=31),
     "gemm_concat": check_gemm_concat,
     "gemm_rowvec": check_gemm_rowvec,
     "geglu": check_geglu,

@@ -116,6 +116,8 @@ ProfScope::~ProfScope() {
 struct Option { const char* name; int value; };
 static Option g_options[] = {
     {"attn_tc", 1},        // tcgen05 attention for d = 40 / 80 (0 = mma.sync kernel)
+    {"attn_poly", 0},      // != 0: 2 of every 8 exponentials on the FMA pipe instead of MUFU (measured: no gain)
+    {"attn_split", 1},     // threads per query row in the tcgen05 attention softmax (1 or 2; measured equal)
     {"gemm_wres", 0},      // unused (kept so old scripts do not fail)
     {"gemm_cluster", 0},   // CTA pairs multicasting the weight tile
     {"gemm_stages", 0},    // smem ring depth limit (0 = all)
