@@ -204,8 +204,10 @@ def main():
     n0 = lib.vs_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    torch.cuda.nvtx.range_push("vs_timed_eager")      # lets `ncu --nvtx --nvtx-include vs_timed_eager/` pick this region
     for i in range(K):
         lat = step(lat, W + i)
+    torch.cuda.nvtx.range_pop()
     e1.record()
     torch.cuda.synchronize()
     launches = lib.vs_launch_count() - n0

@@ -468,7 +468,8 @@ int ensure_workspace(vs_unet* h, int B, int F, int H, int W) {
   want(&h->XN, maxCat);
   want(&h->T, maxC); want(&h->TN, maxC); want(&h->QKV, 3 * maxC); want(&h->ATT, maxC); want(&h->HH, 4 * maxC);
   want(&h->SC, maxC); want(&h->P0, maxC); want(&h->P1, maxC);
-  want(&h->SCR, std::max(NI * hw[1] * 9 * boc[0], 4 * maxC));     // im2col (stride-2) / nearest-upsample scratch
+  want(&h->SCR, std::max(std::max(NI * hw[1] * 9 * boc[0], 4 * maxC), (NI * hw[0] + boc[0]) * 64));   // im2col (stride-2) /
+                // nearest-upsample scratch / conv_in patch rows
   want(&h->KV, (size_t)B * 128 * 2 * boc[3]);
   want(&h->RES, maxC);
   want(&h->OUT, NI * hw[0] * 8);
@@ -551,7 +552,7 @@ extern "C" int vs_unet_forward(vs_unet* h, void* stream, const void* d_sample, i
   // ---- conv_in
   RUN(ncfhw_to_nhwc(st, d_sample, io_f32, B, cf.in_channels, F, H, W, h->XIN));
   int si = 0;
-  RUN(conv_in_3x3(st, h->XIN, c.NI, H, W, cf.in_channels, h->conv_in_w, h->conv_in_b, boc[0], h->skip[si]));
+  RUN(conv_in_3x3(st, h->XIN, c.NI, H, W, cf.in_channels, h->conv_in_w, h->conv_in_b, boc[0], h->skip[si], h->SCR));
   RUN(tap(c, "conv_in", h->skip[si], boc[0]));
   const __half* cur = h->skip[si];
   int curC = boc[0];
