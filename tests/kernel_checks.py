@@ -255,6 +255,18 @@ CHECKS = {
     "gemm_bn256_res": lambda: check_gemm(128 * 150 + 9, 1280, 320, residual=True, seed=8),
     "gemm_bn256_forced_tail": lambda: check_gemm(700, 768, 640, bn=256, seed=9),
     "conv_bn256": lambda: check_conv3x3(n=16, H=32, W=32, ci=320, co=1280, rowvec=True, residual=True),
+    # CTA pairs (cta_group::2) are the default for >= 2 row tiles: odd row-tile counts (dummy second tile), ragged M,
+    # and the single-CTA kernels behind the "gemm_pair" = 0 switch
+    "gemm_pair_odd_m": lambda: check_gemm(128 * 3, 640, 1280, residual=True, seed=12),
+    "gemm_pair_ragged_m": lambda: check_gemm(128 * 5 + 9, 1280, 1024, seed=13),
+    "gemm_pair_small_k": with_option("gemm_pair", 2, lambda: check_gemm(128 * 7 + 3, 960, 320, seed=14), 1),
+    "geglu_pair_small_k": with_option("gemm_pair", 2, lambda: check_geglu(M=1000, C=320, seed=33), 1),
+    "conv_pair_odd": lambda: _conv_odd(3, 7, 12, 320, 320, 56),
+    "single_gemm": with_option("gemm_pair", 0, lambda: check_gemm(1024, 1280, 1280, residual=True, seed=7), 1),
+    "single_gemm_bn256": with_option("gemm_pair", 0, lambda: check_gemm(8192, 3840, 640, seed=7), 1),
+    "single_geglu": with_option("gemm_pair", 0, lambda: check_geglu(M=1000, C=640, seed=32), 1),
+    "single_conv": with_option("gemm_pair", 0, lambda: check_conv3x3(rowvec=True, residual=True), 1),
+    "single_concat": with_option("gemm_pair", 0, check_gemm_concat, 1),
     # tile counts that leave one epilogue warpgroup (accumulator stage) without work on some CTAs
     "gemm_one_tile": lambda: check_gemm(100, 128, 64, seed=10),
     "gemm_149_tiles": lambda: check_gemm(128 * 149, 128, 128, residual=True, seed=11),

@@ -62,9 +62,9 @@ struct GemmParams {
   int stages;        // 0 = all, else limits the smem ring depth (pipeline-depth experiments)
 };
 
-template <int BN>
+template <int BN, bool PAIR = false>
 struct Cfg {
-  static constexpr int B_STAGE_BYTES = BN * BK * 2;
+  static constexpr int B_STAGE_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;   // a CTA pair splits the weight tile along N
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES_RAW = (SMEM_LIMIT - 2048 - EPI_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -79,9 +79,12 @@ __device__ __forceinline__ uint32_t sw64_off(int row, int chunk) {   // byte off
   return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
 }
 
-template <int BN, int EPI>
+// PAIR: two CTAs of a cluster (an SM pair) compute a 256 x BN tile with cta_group::2 MMAs: each loads its own 128 rows
+// of A and HALF of the weight tile, so the L2 -> SM operand feed per flop -- the bound of the main loop -- drops by a
+// third (BN = 256: 32 KB instead of 48 KB per 512 tensor cycles and CTA).
+template <int BN, int EPI, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, PAIR>;
   constexpr bool GEGLU = (EPI & EPI_F_GEGLU) != 0, HAS_RES = (EPI & EPI_F_RES) != 0, HAS_RV = (EPI & EPI_F_RV) != 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -97,11 +100,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;        // 0 = leader (issues the MMAs)
+  const int total_tiles = (PAIR ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;   // PAIR: tiles of 256 rows
   const int nst = (p.stages > 0 && p.stages < C::STAGES) ? p.stages : C::STAGES;   // ring depth (debug knob: "gemm_stages")
   // Tile order: n fastest, tiles round-robin over the CTAs (CTAs running at the same time share the A row panel and a
   // few weight tiles in L2).  m-fastest and operand-stationary orders measured 3-40% slower.
-  const int t_begin = (int)blockIdx.x, t_step = (int)gridDim.x;
+  const int t_begin = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, t_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmA);
@@ -115,13 +119,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128);             // one epilogue warpgroup per accumulator stage
+      mbar_init(tempty_bar(a), PAIR ? 256 : 128);   // one epilogue warpgroup per accumulator stage (of each CTA)
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  if (warp == 2) {
+    if (PAIR) tmem_alloc_pair(tmem_slot, C::TMEM_COLS);
+    else tmem_alloc(tmem_slot, C::TMEM_COLS);
+  }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();                  // the peer's barriers are initialised before any remote arrive / TMA credit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -136,14 +144,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     const int tap0 = p.taps == 9 ? -1 : 0;
     uint32_t pr_s = 0, pr_ph = 0;              // ring stage / phase, carried across tiles
     for (int tile = t_begin; tile < total_tiles; tile += t_step) {
-      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      const int mt = tile / p.n_tiles, n_tile = tile - mt * p.n_tiles;
+      const int m_tile = PAIR ? 2 * mt + (int)crank : mt;      // may be == m_tiles (odd count): an all-out-of-bounds tile
       int x0 = 0, y0 = 0, i0 = 0;
       if (conv) {
         x0 = (m_tile % p.tiles_x) * p.TW;
         y0 = ((m_tile / p.tiles_x) % p.tiles_y) * p.TH;
         i0 = (m_tile / (p.tiles_x * p.tiles_y)) * p.TN;
       }
-      const int n0 = n_tile * BN;
+      const int n0 = n_tile * BN + (PAIR ? (int)crank * (BN / 2) : 0);   // PAIR: this CTA's half of the weight tile
       const int m0 = m_tile * BM;
       int kcoord = 0;                          // K coordinate into the weight panel (kb * 64)
       int dy = tap0, dx = tap0;                // tap offsets, advanced like an odometer
@@ -153,13 +162,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         if (elect_one()) {
           const uint32_t fb = full_bar(pr_s);
           const uint32_t a_dst = smem_base + pr_s * C::STAGE_BYTES;
-          mbar_expect_tx(fb, C::STAGE_BYTES);
           const bool first = r < kb_src1;
           const CUtensorMap* tm = first ? &p.tmA : &p.tmA2;
           const int c = (first ? r : r - kb_src1) * BK;
-          if (conv) tma_load_4d(a_dst, tm, fb, c, x0 + dx, y0 + dy, i0);
-          else tma_load_2d(a_dst, tm, fb, c, m0);
-          tma_load_2d(a_dst + A_STAGE_BYTES, &p.tmB, fb, kcoord, n0);
+          if (PAIR) {                          // both CTAs' bytes are credited to the LEADER's full barrier
+            const uint32_t fbl = mapa_shared(fb, 0);
+            if (crank == 0) mbar_expect_tx(fb, 2 * C::STAGE_BYTES);
+            if (conv) tma_load_4d_pair(a_dst, tm, fbl, c, x0 + dx, y0 + dy, i0);
+            else tma_load_2d_pair(a_dst, tm, fbl, c, m0);
+            tma_load_2d_pair(a_dst + A_STAGE_BYTES, &p.tmB, fbl, kcoord, n0);
+          } else {
+            mbar_expect_tx(fb, C::STAGE_BYTES);
+            if (conv) tma_load_4d(a_dst, tm, fb, c, x0 + dx, y0 + dy, i0);
+            else tma_load_2d(a_dst, tm, fb, c, m0);
+            tma_load_2d(a_dst + A_STAGE_BYTES, &p.tmB, fb, kcoord, n0);
+          }
         }
         __syncwarp();
         kcoord += BK;
@@ -170,9 +187,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         if (++pr_s == (uint32_t)nst) { pr_s = 0; pr_ph ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    // =================================================================== MMA issuer
-    constexpr uint32_t idesc = umma_idesc_f16(BM, BN);
+  } else if (warp == 1 && crank == 0) {
+    // =================================================================== MMA issuer (PAIR: the leader CTA only)
+    constexpr uint32_t idesc = umma_idesc_f16(PAIR ? 2 * BM : BM, BN);
     const int num_kb = p.num_kb;
     uint32_t mm_s = 0, mm_ph = 0, t = 0;
     for (int tile = t_begin; tile < total_tiles; tile += t_step, ++t) {
@@ -189,12 +206,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           const uint32_t a_addr = smem_base + mm_s * C::STAGE_BYTES;
           const uint64_t ad = umma_desc_sw128_kmajor(a_addr);
           const uint64_t bd = umma_desc_sw128_kmajor(a_addr + A_STAGE_BYTES);
-          tc_mma_f16(d_tmem, ad, bd, idesc, kb != 0 ? 1u : 0u);
-          tc_mma_f16(d_tmem, ad + 2, bd + 2, idesc, 1u);
-          tc_mma_f16(d_tmem, ad + 4, bd + 4, idesc, 1u);
-          tc_mma_f16(d_tmem, ad + 6, bd + 6, idesc, 1u);
-          tc_commit(empty_bar(mm_s));        // frees the smem slot once these MMAs have read it
-          if (kb == num_kb - 1) tc_commit(tfull_bar(acc));   // accumulator complete -> epilogue
+          if (PAIR) {
+            tc_mma_f16_pair(d_tmem, ad, bd, idesc, kb != 0 ? 1u : 0u);
+            tc_mma_f16_pair(d_tmem, ad + 2, bd + 2, idesc, 1u);
+            tc_mma_f16_pair(d_tmem, ad + 4, bd + 4, idesc, 1u);
+            tc_mma_f16_pair(d_tmem, ad + 6, bd + 6, idesc, 1u);
+            tc_commit_pair(empty_bar(mm_s), (uint16_t)0x3);   // frees the slot in BOTH CTAs
+            if (kb == num_kb - 1) tc_commit_pair(tfull_bar(acc), (uint16_t)0x3);
+          } else {
+            tc_mma_f16(d_tmem, ad, bd, idesc, kb != 0 ? 1u : 0u);
+            tc_mma_f16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+            tc_mma_f16(d_tmem, ad + 4, bd + 4, idesc, 1u);
+            tc_mma_f16(d_tmem, ad + 6, bd + 6, idesc, 1u);
+            tc_commit(empty_bar(mm_s));        // frees the smem slot once these MMAs have read it
+            if (kb == num_kb - 1) tc_commit(tfull_bar(acc));   // accumulator complete -> epilogue
+          }
         }
         __syncwarp();
         if (++mm_s == (uint32_t)nst) { mm_s = 0; mm_ph ^= 1; }
@@ -214,8 +240,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
     uint32_t epi_buf = 0;                   // staging ping-pong
     uint32_t aph = 0;
+    const uint32_t tempty_arrive = PAIR ? mapa_shared(tempty_bar(acc), 0) : tempty_bar(acc);   // PAIR: the leader's barrier
     for (int tile = t_begin + grp * t_step; tile < total_tiles; tile += 2 * t_step, aph ^= 1) {
-      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      const int mt = tile / p.n_tiles, n_tile = tile - mt * p.n_tiles;
+      const int m_tile = PAIR ? 2 * mt + (int)crank : mt;
       int pix;                              // output pixel (row of the GEMM) of this thread, -1 = outside the problem
       if (p.a_rank == 4) {
         const int x0 = (m_tile % p.tiles_x) * p.TW;
@@ -223,7 +251,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         const int i0 = (m_tile / (p.tiles_x * p.tiles_y)) * p.TN;
         const int ti = row >> p.thw_log, rem = row & ((1 << p.thw_log) - 1);
         const int y = y0 + (rem >> p.tw_log), x = x0 + (rem & (p.TW - 1)), img = i0 + ti;
-        pix = ((img < p.nimg) && (y < p.H) && (x < p.W)) ? (img * p.H + y) * p.W + x : -1;
+        pix = ((m_tile < p.m_tiles) && (img < p.nimg) && (y < p.H) && (x < p.W)) ? (img * p.H + y) * p.W + x : -1;
       } else {
         pix = m_tile * BM + row;
         if (pix >= p.M) pix = -1;
@@ -278,7 +306,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           }
           if (s == nsub - 1) {              // accumulator fully read: hand the stage back to the MMA warp before the stores
             tc_fence_before();
-            mbar_arrive(tempty_bar(acc));
+            if (PAIR) mbar_arrive_cluster(tempty_arrive);
+            else mbar_arrive(tempty_bar(acc));
           }
           uint4 rcur[4];
           if (HAS_RES) {
@@ -362,16 +391,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           }
         }
         tc_fence_before();
-        mbar_arrive(tempty_bar(acc));
+        if (PAIR) mbar_arrive_cluster(tempty_arrive);
+        else mbar_arrive(tempty_bar(acc));
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();                  // nobody leaves while its peer may still signal it or read its smem
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (PAIR) tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+    else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -394,29 +426,47 @@ ConvTile pick_conv_tile(int nimg, int H, int W) {
   return best;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool PAIR>
 int launch(cudaStream_t st, const GemmParams& p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, PAIR>;
   static bool configured = false;
   if (!configured) {
-    VS_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    VS_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     configured = true;
+  }
+  if (PAIR) {
+    const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
+    const int max_clusters = num_sms() / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (pairs < max_clusters ? pairs : max_clusters));
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, PAIR>, p));
+    return 0;
   }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_tc_kernel<BN, EPI><<<grid, GEMM_THREADS, C::SMEM_BYTES, st>>>(p);
+  gemm_tc_kernel<BN, EPI, PAIR><<<grid, GEMM_THREADS, C::SMEM_BYTES, st>>>(p);
   VS_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-template <int BN>
+template <int BN, bool PAIR>
 int launch_linear(cudaStream_t st, const GemmParams& p) {
   const int epi = (p.residual ? EPI_F_RES : 0) | (p.rowvec ? EPI_F_RV : 0);
   switch (epi) {
-    case 0: return launch<BN, 0>(st, p);
-    case EPI_F_RES: return launch<BN, EPI_F_RES>(st, p);
-    case EPI_F_RV: return launch<BN, EPI_F_RV>(st, p);
-    default: return launch<BN, EPI_F_RES | EPI_F_RV>(st, p);
+    case 0: return launch<BN, 0, PAIR>(st, p);
+    case EPI_F_RES: return launch<BN, EPI_F_RES, PAIR>(st, p);
+    case EPI_F_RV: return launch<BN, EPI_F_RV, PAIR>(st, p);
+    default: return launch<BN, EPI_F_RES | EPI_F_RV, PAIR>(st, p);
   }
 }
 
@@ -520,10 +570,15 @@ int gemm_tc(cudaStream_t st, const GemmArgs& a) {
   }
   VS_REQUIRE(bn == 64 || bn == 128 || bn == 160 || bn == 256, "gemm_tc: unsupported BLOCK_N %d", bn);
   p.n_tiles = (a.N + bn - 1) / bn;
+  // CTA pairs (cta_group::2) where the main loop dominates (K >= 768): measured -5..-13% there, but +5..+12% on the
+  // epilogue-bound K <= 640 shapes (two CTAs in lockstep, remote barrier arrivals).  "gemm_pair": 0 = never (A/B
+  // switch), 2 = whenever there are two row tiles.
+  const int pair_opt = get_option("gemm_pair");
+  const bool pair = pair_opt != 0 && p.m_tiles >= 2 && bn >= 128 && (p.num_kb >= 12 || pair_opt == 2);
   {
     const uint64_t dims[2] = {(uint64_t)Ktot, (uint64_t)a.N};
     const uint64_t str[1] = {(uint64_t)Ktot * 2};
-    const uint32_t box[2] = {BK, (uint32_t)bn};
+    const uint32_t box[2] = {BK, (uint32_t)(pair ? bn / 2 : bn)};   // a CTA pair: each CTA fetches half of the weight tile
     if (make_tmap_f16(&p.tmB, a.Bw, 2, dims, str, box, 1)) return 3;
   }
   // staged (transposed, coalesced) epilogue whenever the output geometry allows it: 16-byte strides, whole 32-column
@@ -535,12 +590,19 @@ int gemm_tc(cudaStream_t st, const GemmArgs& a) {
              (!a.rowvec || ((reinterpret_cast<uintptr_t>(a.rowvec) & 15) == 0 && p.ldrv % 4 == 0));
   if (!p.staged) VS_REQUIRE(a.mode == EPI_LINEAR, "gemm_tc: GEGLU output needs 32-column aligned, 16-byte strided rows");
   ProfScope prof(st, a.taps == 9 ? PC_CONV : PC_GEMM, 2.0 * a.M * (double)a.N * Ktot, 1, a.M, a.N, Ktot);
-  if (a.mode == EPI_GEGLU) return launch<128, EPI_F_GEGLU>(st, p);
+  if (a.mode == EPI_GEGLU) return pair ? launch<256, EPI_F_GEGLU, true>(st, p) : launch<256, EPI_F_GEGLU, false>(st, p);
+  if (pair) {
+    switch (bn) {
+      case 128: return launch_linear<128, true>(st, p);
+      case 256: return launch_linear<256, true>(st, p);
+      default: return launch_linear<160, true>(st, p);
+    }
+  }
   switch (bn) {
-    case 64: return launch_linear<64>(st, p);
-    case 128: return launch_linear<128>(st, p);
-    case 256: return launch_linear<256>(st, p);
-    default: return launch_linear<160>(st, p);
+    case 64: return launch_linear<64, false>(st, p);
+    case 128: return launch_linear<128, false>(st, p);
+    case 256: return launch_linear<256, false>(st, p);
+    default: return launch_linear<160, false>(st, p);
   }
 }
 

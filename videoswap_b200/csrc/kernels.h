@@ -32,7 +32,7 @@ struct GemmArgs {
   int force_bn = 0;                           // 0 = auto
 };
 int gemm_tc(cudaStream_t st, const GemmArgs& a);
-constexpr int kGegluGranule = 64;            // value/gate column interleave granule (= BLOCK_N/2 of the GEGLU GEMM)
+constexpr int kGegluGranule = 128;           // value/gate column interleave granule (= BLOCK_N/2 of the GEGLU GEMM)
 
 // ---- normalisation -------------------------------------------------------------------------------------------
 // GroupNorm over `nstat` statistics sets; set s covers `imgs_per_set` consecutive images (5-D GroupNorm of the

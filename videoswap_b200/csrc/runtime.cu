@@ -119,7 +119,8 @@ static Option g_options[] = {
     {"attn_poly", 0},      // != 0: 2 of every 8 exponentials on the FMA pipe instead of MUFU (measured: no gain)
     {"attn_split", 1},     // threads per query row in the tcgen05 attention softmax (1 or 2; measured equal)
     {"gemm_wres", 0},      // unused (kept so old scripts do not fail)
-    {"gemm_cluster", 0},   // CTA pairs multicasting the weight tile
+    {"gemm_pair", 1},      // CTA pairs (cta_group::2, 256-row tiles) for GEMM / conv with >= 2 row tiles
+    {"gemm_cluster", 0},   // unused (old multicast experiment)
     {"gemm_stages", 0},    // smem ring depth limit (0 = all)
     {"gemm_order", 0},     // persistent tile order: 0 = n fastest, 1 = m fastest
     {"exp_a", 0}, {"exp_b", 0}, {"exp_c", 0},   // scratch switches for experiments

@@ -9,7 +9,7 @@ import torch
 
 from . import _lib
 
-GEGLU_GRANULE = 64
+GEGLU_GRANULE = 128
 EPI_LINEAR, EPI_GEGLU = 0, 1
 
 
