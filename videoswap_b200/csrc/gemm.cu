@@ -36,7 +36,8 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int GEMM_THREADS = 384;                   // 4 control warps + 2 epilogue warpgroups
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int EPI_COLS = 32;                        // output columns per epilogue sub-tile (64 B of fp16: SWIZZLE_64B)
-constexpr int EPI_BYTES = 8 * 4096;                 // per epilogue warp: two ping-pong 2 KB staging buffers
+constexpr int EPI_WARP_BYTES = 3072;                // per epilogue warp: 2 KB transpose staging + 1 KB bias slice
+constexpr int EPI_BYTES = 8 * EPI_WARP_BYTES;
 enum { EPI_F_GEGLU = 1, EPI_F_RES = 2, EPI_F_RV = 4 };   // compile-time epilogue features
 
 struct GemmParams {
@@ -75,6 +76,11 @@ struct Cfg {
   static_assert(STAGES >= 3, "pipeline too shallow");
 };
 
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ uint32_t sw64_off(int row, int chunk) {   // byte offset inside a [32 x 64 B] SWIZZLE_64B tile
   return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
 }
@@ -233,12 +239,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     const int row = q * 32 + lane;          // row of the tile handled by this thread
     const int grp = (warp - 4) >> 2;
     const int acc = grp;
-    const uint32_t stage0 = epi_base + (warp - 4) * 4096;
+    const uint32_t out_stage = epi_base + (warp - 4) * EPI_WARP_BYTES, bias_stage = out_stage + 2048;
     const int tr = lane >> 2, tch = lane & 3;   // transposed mapping: 8 rows x four 16-byte chunks per instruction
     const bool has_bias = p.bias != nullptr;
     const bool staged = p.staged != 0;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
-    uint32_t epi_buf = 0;                   // staging ping-pong
     uint32_t aph = 0;
     const uint32_t tempty_arrive = PAIR ? mapa_shared(tempty_bar(acc), 0) : tempty_bar(acc);   // PAIR: the leader's barrier
     for (int tile = t_begin + grp * t_step; tile < total_tiles; tile += 2 * t_step, aph ^= 1) {
@@ -275,6 +280,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                                    : make_uint4(0, 0, 0, 0);
         };
         if (HAS_RES) load_res(0);
+        // The tile's bias vector goes to this warp's own shared-memory slice while the accumulator is still being
+        // computed; the sub-tiles then read it as broadcast LDS.  (Read with __ldg inside the sub-tile loop, the epilogue
+        // warps of the K = 320 GEMMs spent 31% of their time waiting for those loads.)
+        if (has_bias) {
+          __syncwarp();                     // the previous tile's readers are done
+#pragma unroll
+          for (int c = lane; c < BN / 4; c += 32) {
+            const int n = n0 + 4 * c;
+            const float4 b = n + 3 < p.N ? __ldg(reinterpret_cast<const float4*>(p.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(bias_stage + 16 * c), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+          }
+          __syncwarp();
+        }
         mbar_wait(tfull_bar(acc), aph);
         tc_fence_after();
 #pragma unroll 1
@@ -287,12 +305,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
               uint32_t g[32];
               tmem_ld32(taddr + BN / 2 + s * EPI_COLS, g);
               tmem_ld_wait();
-              const float* bv = p.bias + n0 + s * EPI_COLS;
-              const float* bg = bv + BN / 2;
+              const uint32_t bv = bias_stage + s * EPI_COLS * 4, bg = bv + (BN / 2) * 4;
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(bv + j));
-                const float4 c = __ldg(reinterpret_cast<const float4*>(bg + j));
+                const float4 b = lds_f4(bv + j * 4);
+                const float4 c = lds_f4(bg + j * 4);
                 f[j] = (__uint_as_float(v[j]) + b.x) * gelu_sig(__uint_as_float(g[j]) + c.x);
                 f[j + 1] = (__uint_as_float(v[j + 1]) + b.y) * gelu_sig(__uint_as_float(g[j + 1]) + c.y);
                 f[j + 2] = (__uint_as_float(v[j + 2]) + b.z) * gelu_sig(__uint_as_float(g[j + 2]) + c.z);
@@ -317,10 +334,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           }
           if (!GEGLU) {
             if (has_bias) {
-              const float* bp = p.bias + n0 + s * EPI_COLS;
+              const uint32_t bp = bias_stage + s * EPI_COLS * 4;
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(bp + j));
+                const float4 b = lds_f4(bp + j * 4);
                 f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
               }
             }
@@ -332,11 +349,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
               }
             }
           }
-          // thread = row -> lanes along columns: transpose this warp's 32 x 32 block through its own staging buffer
-          // (ping-pong: the __syncwarp of the next sub-tile orders the reuse).  TMA stores were tried first: they queue
-          // behind the producer's prefetched loads in the same engine and their completion wait serialised the epilogue.
-          const uint32_t out_stage = stage0 + epi_buf;
-          epi_buf ^= 2048u;
+          // thread = row -> lanes along columns: transpose this warp's 32 x 32 block through its own staging buffer.
+          // TMA stores were tried first: they queue behind the producer's prefetched loads in the same engine and their
+          // completion wait serialised the epilogue.
+          __syncwarp();                       // the previous sub-tile's readers of the staging buffer are done
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint32_t pk[4];
