@@ -295,9 +295,25 @@ def main():
         value = world * K / (ms / 1e3)
         e2e = world * K / (ms_e2e / 1e3)
         tensor_cats = ["gemm", "conv3x3", "attention"]
-        dom = max(tensor_cats, key=lambda n: prof[n]["ms_per_step"])
-        d = prof[dom]
+        # dominant kernel: gemm_tc_kernel -- one template serves the GEMMs and the implicit-GEMM 3x3 convs, so its launches
+        # of both categories are pooled: achieved = algorithmic FLOPs per launch / average launch duration
+        g_ms = prof["gemm"]["ms_per_step"] + prof["conv3x3"]["ms_per_step"]
+        g_work = prof["gemm"]["work_per_step"] + prof["conv3x3"]["work_per_step"]
+        g_n = prof["gemm"]["launches_per_step"] + prof["conv3x3"]["launches_per_step"]
+        if g_ms >= prof["attention"]["ms_per_step"]:
+            dom_name, d = "gemm_tc_kernel (GEMM + implicit-GEMM 3x3 conv)", {"ms_per_step": g_ms, "work_per_step": g_work, "launches_per_step": g_n}
+        else:
+            dom_name, d = "attn_tc_kernel", prof["attention"]
         ach = d["work_per_step"] / (d["ms_per_step"] / 1e3) / 1e12 if d["ms_per_step"] > 0 else 0.0
+        traffic, traffic_src = None, None
+        summ = os.path.join(ROOT, "profiles", "r01_launches_summary.json")
+        if os.path.exists(summ):      # DRAM bytes per launch of the same kernel from the committed ncu capture of one step
+            with open(summ) as f:
+                ks = json.load(f)["kernels"]
+            sel = [v for k, v in ks.items() if k.startswith(dom_name.split(" ")[0])]
+            if sel:
+                traffic = sum((v["dram_read_MB"] + v["dram_write_MB"]) * 1e6 for v in sel) / sum(v["launches"] for v in sel)
+                traffic_src = "profiles/r01_launches_summary.json (ncu dram__bytes_read.sum + dram__bytes_write.sum, cold L2)"
         kernels = {}
         for n, p_ in prof.items():
             if p_["ms_per_step"] <= 0:
@@ -324,9 +340,11 @@ def main():
                     "d2h_bytes_per_step": h_out.numel() * 2},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": {"gemm": "gemm_tc_kernel (GEMM)", "conv3x3": "gemm_tc_kernel (implicit-GEMM 3x3 conv)",
-                                    "attention": "attn_kernel"}[dom], "bound": "tensor", "achieved": ach, "peak": pk["tflops"],
-                         "unit": "TFLOP/s", "frac": ach / pk["tflops"], "traffic": None, "peak_source": pk["source"]},
+            "roofline": {"kernel": dom_name, "bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s",
+                         "frac": ach / pk["tflops"], "traffic": traffic, "traffic_source": traffic_src,
+                         "launches_per_step": d["launches_per_step"],
+                         "flops_per_launch": d["work_per_step"] / max(d["launches_per_step"], 1),
+                         "avg_launch_us": 1e3 * d["ms_per_step"] / max(d["launches_per_step"], 1), "peak_source": pk["source"]},
             "kernels": kernels, "finite": finite,
         }
         if world == 1 and not args.no_cpu_baseline:

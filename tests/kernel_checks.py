@@ -272,8 +272,8 @@ CHECKS = {
     "gemm_149_tiles": lambda: check_gemm(128 * 149, 128, 128, residual=True, seed=11),
     # tcgen05 attention variants kept for A/B measurements: two threads per query row, FMA-pipe exponentials
     "self_attn_d40_split2": with_option("attn_split", 2, lambda: check_self_attention(B=2, N=600, C=320, seed=121), 1),
-    "self_attn_d80_split2": with_option("attn_split", 2, lambda: check_self_attention(B=2, N=300, C=640, seed=123), 1),
     "cross_attn_split2": with_option("attn_split", 2, lambda: check_cross_attention(B=2, Fr=2, N=300, C=320, seed=131), 1),
+    "self_attn_d40_late_handoff": with_option("attn_handoff", 0, lambda: check_self_attention(B=2, N=600, C=320, seed=121), 1),
     "self_attn_d40_poly": with_option("attn_poly", 1, lambda: check_self_attention(B=2, N=600, C=320, seed=121), 0),
     "gemm_bn160": lambda: check_gemm(512, 320, 320),
     "gemm_bn128_tail": lambda: check_gemm(300, 768, 320, bn=128),

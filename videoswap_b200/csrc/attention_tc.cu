@@ -8,11 +8,13 @@
 //   warp 2      TMEM allocator
 //   warps 4-7   softmax warpgroup of query tile 0 (thread = one query row, reads S with tcgen05.ld)
 //   warps 8-11  softmax warpgroup of query tile 1
-// S is DOUBLE-BUFFERED per query tile in TMEM and the issuer runs Q K^T two key tiles ahead, so a softmax warpgroup
-// never waits for a tensor-core round trip: it goes from the exponentials of tile j straight to tile j+1 (the kernel is
-// bound by the 16 ex2/clk/SM MUFU rate at d = 40, not by the MMAs -- see DESIGN.md).  The softmax keeps a *stale*
-// running maximum and only rescales O (tcgen05.ld/st round trip) when the true maximum grew by more than 2^8.
-// P is written to shared memory in the 128-byte-swizzled K-major layout the MMA consumes.
+// S is DOUBLE-BUFFERED per query tile in TMEM and the issuer runs Q K^T two key tiles ahead; P is double-buffered in
+// shared memory, so a softmax warpgroup never waits for a tensor-core round trip.  The two softmax warpgroups PING-PONG
+// on the MUFU pipe through two 256-thread named barriers (one computes exponentials while the other loads / reduces /
+// packs / stores) -- at d = 40 the kernel is bound by the 16 ex2/clk/SM MUFU rate and the latency of each warp's serial
+// tile, not by the MMAs.  The softmax keeps a *stale* running maximum and only rescales O (tcgen05.ld/st
+// round trip) when the true maximum grew by more than 2^8.  P is written to shared memory in the 128-byte-swizzled
+// K-major layout the MMA consumes; the row sum comes out of the P V MMA through a column of ones written into V.
 //
 // Replaces diffusers AttnProcessor2_0 / EDLoRA_AttnProcessor.__call__ (reference utils/edlora_util.py:47-65,
 // models/animatediff_models/attention.py:229-241).
@@ -39,8 +41,8 @@ struct TCfg {
   static constexpr int KV_BLOCK_BYTES = BKV * 128;
   static constexpr int KV_STAGE_BYTES = 2 * NCB * KV_BLOCK_BYTES;     // K then V
   static constexpr int P_TILE_BYTES = TQ * 128;
-  static constexpr int XCH_BYTES = 2 * 4 * TQ * 4;                      // row-maximum exchange slots (SPLIT == 2)
-  static constexpr int SMEM = Q_BYTES + ST * KV_STAGE_BYTES + 2 * P_TILE_BYTES + XCH_BYTES + 1024 + 256;
+  static constexpr int XCH_BYTES = (D <= 64) ? 2 * 4 * TQ * 4 : 0;      // row-maximum exchange slots (SPLIT == 2, d = 40 only)
+  static constexpr int SMEM = Q_BYTES + ST * KV_STAGE_BYTES + 4 * P_TILE_BYTES + XCH_BYTES + 1024 + 256;   // P double-buffered
   static constexpr int O_STRIDE = (DPO <= 64) ? 64 : 128;             // TMEM column stride between O_0 and O_1
   static constexpr int S_COL = 0, O_COL = 4 * BKV;                    // S_{i,b} at (2 i + b) * BKV
   static constexpr int TMEM_COLS = 512;
@@ -101,25 +103,25 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, 
 }
 
 // POLY of every 8 exponentials are evaluated on the FMA pipe (poly_exp2); SPLIT = threads per query row (1 or 2)
-template <int D, int POLY, int SPLIT>
+template <int D, int POLY, int SPLIT, int HO>   // HO: key chunk (of 8) after which the MUFU pipe is handed over
 __global__ void __launch_bounds__(128 + 128 * 2 * SPLIT, 1) attn_tc_kernel(const __grid_constant__ TAttnArgs p) {
   using C = TCfg<D>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t q_s = base;                                   // [2 tiles][NCB][128 rows x 128 B]
   const uint32_t kv_s = q_s + C::Q_BYTES;                      // [ST][K: NCB blocks | V: NCB blocks]
-  const uint32_t p_s = kv_s + C::ST * C::KV_STAGE_BYTES;       // [2 tiles][128 rows x 128 B]
-  const uint32_t xch_s = p_s + 2 * C::P_TILE_BYTES;             // [2 parities][2 tiles][2 halves][128 rows] fp32
+  const uint32_t p_s = kv_s + C::ST * C::KV_STAGE_BYTES;       // [2 tiles][2 buffers][128 rows x 128 B]
+  const uint32_t xch_s = p_s + 4 * C::P_TILE_BYTES;             // [2 parities][2 tiles][2 halves][128 rows] fp32
   const uint32_t bars = xch_s + C::XCH_BYTES;
   const uint32_t q_full = bars;
   auto kv_full = [&](int s) { return bars + 8u * (1 + s); };
   auto kv_empty = [&](int s) { return bars + 8u * (1 + C::ST + s); };
   auto s_full = [&](int i, int b) { return bars + 8u * (1 + 2 * C::ST + 2 * i + b); };
-  auto p_full = [&](int i) { return bars + 8u * (5 + 2 * C::ST + i); };
-  auto p_empty = [&](int i) { return bars + 8u * (7 + 2 * C::ST + i); };
-  const uint32_t o_full = bars + 8u * (9 + 2 * C::ST);
-  auto v_ready = [&](int s) { return bars + 8u * (10 + 2 * C::ST + s); };      // ones column written into V stage s
-  const uint32_t tmem_slot = bars + 8u * (10 + 3 * C::ST);
+  auto p_full = [&](int i, int b) { return bars + 8u * (5 + 2 * C::ST + 2 * i + b); };
+  auto p_empty = [&](int i, int b) { return bars + 8u * (9 + 2 * C::ST + 2 * i + b); };
+  const uint32_t o_full = bars + 8u * (13 + 2 * C::ST);
+  auto v_ready = [&](int s) { return bars + 8u * (14 + 2 * C::ST + s); };      // ones column written into V stage s
+  const uint32_t tmem_slot = bars + 8u * (14 + 3 * C::ST);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -131,8 +133,11 @@ __global__ void __launch_bounds__(128 + 128 * 2 * SPLIT, 1) attn_tc_kernel(const
     mbar_init(q_full, 1);
     for (int s = 0; s < C::ST; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); mbar_init(v_ready(s), 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(s_full(i, 0), 1); mbar_init(s_full(i, 1), 1);
-      mbar_init(p_full(i), 128 * SPLIT); mbar_init(p_empty(i), 1);
+      for (int bb = 0; bb < 2; ++bb) {
+        mbar_init(s_full(i, bb), 1);
+        mbar_init(p_full(i, bb), 128 * SPLIT);
+        mbar_init(p_empty(i, bb), 1);
+      }
     }
     mbar_init(o_full, 1);
     fence_barrier_init();
@@ -189,15 +194,15 @@ __global__ void __launch_bounds__(128 + 128 * 2 * SPLIT, 1) attn_tc_kernel(const
       }
       __syncwarp();
     };
-    auto issue_pv = [&](int i, uint32_t s, bool acc, bool release_kv) {
+    auto issue_pv = [&](int i, uint32_t s, int pb, bool acc, bool release_kv) {
       if (elect_one()) {
-        const uint32_t pa = p_s + i * C::P_TILE_BYTES;
+        const uint32_t pa = p_s + (2 * i + pb) * C::P_TILE_BYTES;
         const uint32_t va = kv_s + s * C::KV_STAGE_BYTES + C::NCB * C::KV_BLOCK_BYTES;
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k)
           tc_mma_f16(tmem + C::O_COL + i * C::O_STRIDE, umma_desc_sw128_kmajor(pa + k * 32),
                      umma_desc_sw128_mnmajor(va + k * 16 * 128, C::KV_BLOCK_BYTES), idesc_pv, (acc || k != 0) ? 1u : 0u);
-        tc_commit(p_empty(i));                   // P_i consumed, O_i quiescent once this retires
+        tc_commit(p_empty(i, pb));               // this P buffer consumed, O_i quiescent once this retires
         if (release_kv) tc_commit(kv_empty(s));  // K_j / V_j fully consumed once these MMAs retire
       }
       __syncwarp();
@@ -215,10 +220,10 @@ __global__ void __launch_bounds__(128 + 128 * 2 * SPLIT, 1) attn_tc_kernel(const
       const bool more = j + 2 < nkt;
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        mbar_wait(p_full(i), j & 1);
+        mbar_wait(p_full(i, j & 1), (j >> 1) & 1);
         if (i == 0) mbar_wait(v_ready(s), sph);      // ones column of this V tile is in place
         tc_fence_after();
-        issue_pv(i, s, j > 0, i == 1);
+        issue_pv(i, s, j & 1, j > 0, i == 1);
         if (more) {
           if (i == 0) {
             mbar_wait(kv_full(sn), nph);
@@ -262,10 +267,16 @@ __global__ void __launch_bounds__(128 + 128 * 2 * SPLIT, 1) attn_tc_kernel(const
     const int row = quarter * 32 + lane;         // query row inside the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const uint32_t o_addr = tmem + lane_addr + C::O_COL + i * C::O_STRIDE;
-    const uint32_t p_row = p_s + i * C::P_TILE_BYTES + row * 128;
+    const uint32_t p_row0 = p_s + 2 * i * C::P_TILE_BYTES + row * 128;
     const uint32_t xch_mine = xch_s + ((i * 2 + half) * TQ + row) * 4, xch_peer = xch_s + ((i * 2 + (half ^ 1)) * TQ + row) * 4;
     const float sc = p.scale_log2;
     float m_used = -INFINITY;
+    // Ping-pong of the two softmax warpgroups on the MUFU pipe (SPLIT == 1): a warpgroup enters its exponential phase only
+    // when the other one has left its own (256-thread named barriers 9 + i: sync = "my turn", arrive = "your turn"), so one
+    // does load / max / pack / store work while the other saturates the 16 ex2/clk/SM pipe.  P is double-buffered so that
+    // nothing else is on the critical path.
+    constexpr bool PP = SPLIT == 1;
+    if (PP && i == 1) named_bar_arrive(9 + 0, 256);   // warpgroup 0 goes first
     for (int j = 0; j < nkt; ++j) {
       mbar_wait(s_full(i, j & 1), (j >> 1) & 1);
       tc_fence_after();
@@ -298,15 +309,12 @@ __global__ void __launch_bounds__(128 + 128 * 2 * SPLIT, 1) attn_tc_kernel(const
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xch_peer + jb) : "memory");
         mx = fmaxf(mx, other);
       }
-      // P_i(j-1) has been consumed and O_i is quiescent once p_empty flips (issued a whole softmax ago: no real wait)
-      if (j > 0) {
-        mbar_wait(p_empty(i), (j - 1) & 1);
-        tc_fence_after();
-      }
       // ---- lazy rescale: only when the maximum moved by more than 2^8 (always true on the first tile: m_used=-inf);
       // the accumulator column chunks are split between the threads sharing the row
       const bool need = (mx - m_used) * sc > 8.f;
       if (j > 0 && __any_sync(0xffffffffu, need)) {
+        mbar_wait(p_empty(i, (j - 1) & 1), ((j - 1) >> 1) & 1);       // O_i quiescent: the previous P V has retired
+        tc_fence_after();
         const float alpha = need ? exp2f((m_used - mx) * sc) : 1.f;   // also rescales the row-sum column O[:, D]
 #pragma unroll 1
         for (int c0 = half * 16; c0 < C::DPO; c0 += 16 * SPLIT) {
@@ -321,6 +329,9 @@ __global__ void __launch_bounds__(128 + 128 * 2 * SPLIT, 1) attn_tc_kernel(const
       }
       if (need) m_used = mx;
       const float ms = m_used * sc;
+      if (j >= 2) mbar_wait(p_empty(i, j & 1), ((j - 2) >> 1) & 1);   // this P buffer was consumed two key tiles ago
+      const uint32_t p_row = p_row0 + (j & 1) * C::P_TILE_BYTES;
+      if (PP) named_bar_sync(9 + i, 256);                               // my turn on the MUFU pipe
       // ---- P = exp2(S*scale - m) -> fp16 -> swizzled shared memory (A operand of the P V MMA); exp2(-inf) = 0 masks
 #pragma unroll
       for (int c8 = 0; c8 < HK / 8; ++c8) {        // one 16-byte chunk (8 keys) at a time
@@ -336,11 +347,14 @@ __global__ void __launch_bounds__(128 + 128 * 2 * SPLIT, 1) attn_tc_kernel(const
         const uint32_t dst = p_row + (((half * (HK / 8) + c8) ^ (row & 7)) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
                      : "memory");
+        // hand the MUFU pipe to the other warpgroup a little before the last exponentials (its wake-up takes a while)
+        if (PP && c8 == HO) named_bar_arrive(9 + (i ^ 1), 256);
       }
       fence_proxy_async();                     // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       tc_fence_before();
-      mbar_arrive(p_full(i));
+      mbar_arrive(p_full(i, j & 1));
     }
+    if (PP && i == 0) named_bar_sync(9 + 0, 256);    // absorb the other warpgroup's last hand-over
     // ---- epilogue: O / l -> fp16 -> HBM (column chunks split between the threads sharing the row)
     mbar_wait(o_full, 0);
     tc_fence_after();
@@ -381,13 +395,13 @@ __global__ void __launch_bounds__(128 + 128 * 2 * SPLIT, 1) attn_tc_kernel(const
   }
 }
 
-template <int D, int POLY, int SPLIT>
+template <int D, int POLY, int SPLIT, int HO>
 int launch(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv, __half* o, int ldo,
            int batch, int nq, int nk, int heads, long long q_bs, long long kv_bs, long long o_bs, int kv_div) {
   using C = TCfg<D>;
   static bool configured = false;
   if (!configured) {
-    VS_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D, POLY, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    VS_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D, POLY, SPLIT, HO>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     configured = true;
   }
   TAttnArgs a;
@@ -411,7 +425,7 @@ int launch(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, 
   a.scale_log2 = 1.4426950408889634f / sqrtf((float)D);
   dim3 grid((nq + 2 * TQ - 1) / (2 * TQ), heads, batch);
   ProfScope prof(st, PC_ATTN, 4.0 * batch * heads * (double)nq * nk * D, 1, nq, nk, D);
-  attn_tc_kernel<D, POLY, SPLIT><<<grid, 128 + 128 * 2 * SPLIT, C::SMEM, st>>>(a);
+  attn_tc_kernel<D, POLY, SPLIT, HO><<<grid, 128 + 128 * 2 * SPLIT, C::SMEM, st>>>(a);
   VS_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -425,14 +439,18 @@ int attention_tc(cudaStream_t st, const __half* q, int ldq, const __half* k, int
   if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8)) return -1;
   if ((q_bs % 8) || (kv_bs % 8)) return -1;
 #define VS_ATT_ARGS st, q, ldq, k, ldk, v, ldv, o, ldo, batch, nq, nk, heads, q_bs, kv_bs, o_bs, kv_div
-  const int poly = get_option("attn_poly"), split = get_option("attn_split");
+  // A/B switches (runtime.cu): attn_poly (FMA-pipe exponentials), attn_split (two threads per row, d = 40 only),
+  // attn_handoff (0 = hand the MUFU pipe over only after the last exponential).  Measured on one box, interleaved
+  // repetitions, L0 self-attention: hand-over after chunk 6 of 8: 1549 us, after the last: 1607 us, poly: 1703 us.
+  const int poly = get_option("attn_poly"), split = get_option("attn_split"), early = get_option("attn_handoff");
   if (d == 40) {
-    if (split == 2) return poly ? launch<40, 2, 2>(VS_ATT_ARGS) : launch<40, 0, 2>(VS_ATT_ARGS);
-    return poly ? launch<40, 2, 1>(VS_ATT_ARGS) : launch<40, 0, 1>(VS_ATT_ARGS);
+    if (split == 2) return launch<40, 0, 2, 7>(VS_ATT_ARGS);
+    if (poly) return launch<40, 2, 1, 6>(VS_ATT_ARGS);
+    return early ? launch<40, 0, 1, 6>(VS_ATT_ARGS) : launch<40, 0, 1, 7>(VS_ATT_ARGS);
   }
   if (d == 80) {
-    if (split == 2) return poly ? launch<80, 2, 2>(VS_ATT_ARGS) : launch<80, 0, 2>(VS_ATT_ARGS);
-    return poly ? launch<80, 2, 1>(VS_ATT_ARGS) : launch<80, 0, 1>(VS_ATT_ARGS);
+    if (poly) return launch<80, 2, 1, 6>(VS_ATT_ARGS);
+    return early ? launch<80, 0, 1, 6>(VS_ATT_ARGS) : launch<80, 0, 1, 7>(VS_ATT_ARGS);
   }
 #undef VS_ATT_ARGS
   return -1;
