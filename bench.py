@@ -147,6 +147,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of the CUDA-graph replay")
     ap.add_argument("--frames", type=int, default=FRAMES)
+    ap.add_argument("--latent-h", type=int, default=LATENT, help="latent height (extra configs, e.g. 56 for 448x768 video)")
+    ap.add_argument("--latent-w", type=int, default=LATENT, help="latent width (e.g. 96)")
     ap.add_argument("--option", action="append", default=[], help="kernel A/B switch name=value (vs_set_option)")
     ap.add_argument("--tag", default="", help="suffix of the per-shape profile CSV")
     args = ap.parse_args()
@@ -175,10 +177,11 @@ def main():
     pipe.scheduler.set_timesteps(50)
     ts = pipe.scheduler.timesteps
     g = torch.Generator(device=dev).manual_seed(100 + rank)
-    lat0 = torch.randn((1, 4, Fr, LATENT, LATENT), device=dev, generator=g).half()
+    LH, LW = args.latent_h, args.latent_w
+    lat0 = torch.randn((1, 4, Fr, LH, LW), device=dev, generator=g).half()
     embeds = torch.randn((2, 16, 77, 768), device=dev, generator=g).half()
     boc = model.cfg.block_out_channels
-    residuals = [(0.1 * torch.randn((2 * Fr, c, LATENT >> l, LATENT >> l), device=dev, generator=g)).half() for l, c in enumerate(boc)]
+    residuals = [(0.1 * torch.randn((2 * Fr, c, LH >> l, LW >> l), device=dev, generator=g)).half() for l, c in enumerate(boc)]
 
     def step(lat, i):
         return pipe.step(lat, ts[i % len(ts)], embeds, 7.5, list(residuals))
@@ -329,13 +332,14 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
             "data": "synthetic",
-            "config": {"workload": f"{Fr}-frame 512x512 (latent [1,4,{Fr},64,64]), CFG 7.5 (UNet batch 2), ED-LoRA embeds "
+            "config": {"workload": f"{Fr}-frame {8 * LH}x{8 * LW} (latent [1,4,{Fr},{LH},{LW}]), CFG 7.5 (UNet batch 2), ED-LoRA embeds "
                                    f"[2,16,77,768], adapter residuals active, DDIM step; one video per GPU",
                        "timing": "CUDA events; working set (2.55 GB weights + activations) >> 126 MB L2, no flush needed; "
                                  "`value`/`e2e` replay the step as a CUDA graph, the per-kernel profile comes from an eager pass "
                                  "of the same K steps with per-launch events",
                        "eager_ms_per_step": round(ms_eager / K, 3), "cuda_graph": gstep is not None,
-                       "whole_step_tflops": round(FLOP_PER_STEP * (Fr / FRAMES) * (K / (ms / 1e3)) / 1e12, 1)},
+                       "whole_step_tflops": (round(FLOP_PER_STEP * (Fr / FRAMES) * (K / (ms / 1e3)) / 1e12, 1)
+                                             if (LH, LW) == (LATENT, LATENT) else None)},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h_lat.numel() * 2 + h_emb.numel() * 2,
                     "d2h_bytes_per_step": h_out.numel() * 2},
             "gpu_launches": int(launches),

@@ -16,7 +16,8 @@ def test_unet_matches_reference_golden():
 
 
 @pytest.mark.parametrize("kw", [dict(B=1, Fr=2, hw=8, edlora=True), dict(B=2, Fr=3, hw=16, edlora=True, residuals=True),
-                                dict(B=1, Fr=16, hw=8, edlora=False, t=1)])
+                                dict(B=1, Fr=16, hw=8, edlora=False, t=1),
+                                dict(B=1, Fr=2, hw=8, w=24, edlora=True, residuals=True)])   # non-square (56x96-like aspect)
 def test_unet_matches_oracle(kw):
     r = U.unet_vs_oracle(**kw)
     assert r["finite"] and r["psnr"] >= PSNR_MIN, r

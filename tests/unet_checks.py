@@ -43,14 +43,15 @@ def nhwc_tap_to_ncfhw(t, B):
     return t.float().cpu().reshape(B, n // B, h, w, c).permute(0, 4, 1, 2, 3)
 
 
-def unet_vs_oracle(B=1, Fr=2, hw=8, edlora=True, residuals=False, t=981, taps=False):
+def unet_vs_oracle(B=1, Fr=2, hw=8, edlora=True, residuals=False, t=981, taps=False, w=None):
     m, sd = get_model()
-    x = randn((B, 4, Fr, hw, hw), 2)
+    w = hw if w is None else w                      # non-square latents (the reference's usual 448x768 -> 56x96)
+    x = randn((B, 4, Fr, hw, w), 2)
     ehs = randn((B, 16, 77, 768), 3) if edlora else randn((B, 77, 768), 3)
     res = None
     if residuals:
         boc = m.cfg.block_out_channels
-        res = [0.5 * randn((B * Fr, c, max(hw >> l, 1), max(hw >> l, 1)), 10 + l) for l, c in enumerate(boc)]
+        res = [0.5 * randn((B * Fr, c, max(hw >> l, 1), max(w >> l, 1)), 10 + l) for l, c in enumerate(boc)]
     x16, e16 = x.half(), ehs.half()
     res16 = [r.half() for r in res] if res else None
     otaps, ntaps = ({}, {}) if taps else (None, None)
