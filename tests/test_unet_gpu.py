@@ -17,10 +17,23 @@ def test_unet_matches_reference_golden():
 
 @pytest.mark.parametrize("kw", [dict(B=1, Fr=2, hw=8, edlora=True), dict(B=2, Fr=3, hw=16, edlora=True, residuals=True),
                                 dict(B=1, Fr=16, hw=8, edlora=False, t=1),
-                                dict(B=1, Fr=2, hw=8, w=24, edlora=True, residuals=True)])   # non-square (56x96-like aspect)
+                                dict(B=1, Fr=2, hw=8, w=24, edlora=True, residuals=True),    # non-square (56x96-like aspect)
+                                dict(B=1, Fr=1, hw=8, edlora=True),                          # C1: single frame
+                                dict(B=1, Fr=24, hw=8, edlora=False)])                       # longest clip of the PE table
 def test_unet_matches_oracle(kw):
     r = U.unet_vs_oracle(**kw)
     assert r["finite"] and r["psnr"] >= PSNR_MIN, r
+
+
+def test_fp32_latents_take_the_same_path():
+    """The reference keeps latents in the scheduler's dtype; fp32 in -> fp32 out, same kernels (io_f32 = 1)."""
+    m, _ = U.get_model()
+    x = U.randn((1, 4, 2, 8, 8), 41)
+    e = U.randn((1, 77, 768), 42).half().cuda()
+    o16 = m(x.half().cuda(), 501, e, return_dict=False)[0]
+    o32 = m(x.half().float().cuda(), 501, e, return_dict=False)[0]
+    assert o32.dtype == torch.float32 and o16.dtype == torch.float16
+    assert U.psnr(o32, o16.float().cpu()) >= 60.0
 
 
 def test_frame_count_beyond_pe_table_raises():
