@@ -128,8 +128,11 @@ int vs_profile_reset(void);
 int vs_profile_collect(int category, double* ms, double* work, long long* count);
 long long vs_launch_count(void);   /* kernels launched by this library since load */
 int vs_profile_dump(const char* path);   /* CSV: category, shape (m,n,k), work per launch, launches, total ms */
-/* Runtime options: "attn_tc" = 1 (default) uses the tcgen05/TMEM attention kernel for head dims 40/80, 0 forces the
- * mma.sync kernel (A/B testing of the two implementations). */
+/* Runtime A/B switches (defaults = the shipped configuration; unknown names are an error):
+ *   "attn_tc"      1  tcgen05/TMEM attention kernel for head dims 40/80; 0 forces the mma.sync kernel
+ *   "attn_handoff" 1  softmax warpgroups hand the MUFU pipe over after 7 of 8 key chunks; 0 = after the last one
+ *   "gemm_pair"    1  CTA pairs (cta_group::2, 256-row tiles) for K >= 768; 0 = never; 2 = whenever >= 2 row tiles
+ *   "gemm_stages"  0  limit of the shared-memory ring depth of the GEMM (0 = as many as fit) */
 int vs_set_option(const char* name, int value);
 
 #ifdef __cplusplus

@@ -270,11 +270,8 @@ CHECKS = {
     # tile counts that leave one epilogue warpgroup (accumulator stage) without work on some CTAs
     "gemm_one_tile": lambda: check_gemm(100, 128, 64, seed=10),
     "gemm_149_tiles": lambda: check_gemm(128 * 149, 128, 128, residual=True, seed=11),
-    # tcgen05 attention variants kept for A/B measurements: two threads per query row, FMA-pipe exponentials
-    "self_attn_d40_split2": with_option("attn_split", 2, lambda: check_self_attention(B=2, N=600, C=320, seed=121), 1),
-    "cross_attn_split2": with_option("attn_split", 2, lambda: check_cross_attention(B=2, Fr=2, N=300, C=320, seed=131), 1),
+    # tcgen05 attention variants kept for A/B measurements: late hand-over of the MUFU pipe
     "self_attn_d40_late_handoff": with_option("attn_handoff", 0, lambda: check_self_attention(B=2, N=600, C=320, seed=121), 1),
-    "self_attn_d40_poly": with_option("attn_poly", 1, lambda: check_self_attention(B=2, N=600, C=320, seed=121), 0),
     "gemm_bn160": lambda: check_gemm(512, 320, 320),
     "gemm_bn128_tail": lambda: check_gemm(300, 768, 320, bn=128),
     "gemm_bn64": lambda: check_gemm(130, 64, 128, bn=64),

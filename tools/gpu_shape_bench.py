@@ -58,15 +58,14 @@ def main():
         ms = timeit(lambda: ops.gemm(A, W, bias=b, residual=R, mode=mode))
         res[name] = {"ms": ms, "tflops": 2.0 * M * N * K / ms / 1e9, "count": cnt, "ms_total": ms * cnt, "shape": [M, N, K]}
         print(name, res[name], flush=True)
-        # A/B: 2-CTA cluster mode with the weight tile multicast (stationary modes off so that it applies to every K)
-        ops.set_option("gemm_wres", 0)
-        ops.set_option("gemm_cluster", 1)
+        # A/B: CTA pairs (cta_group::2) forced on / off
+        ops.set_option("gemm_pair", 2)
         ms2 = timeit(lambda: ops.gemm(A, W, bias=b, residual=R, mode=mode))
-        ops.set_option("gemm_cluster", 0)
+        ops.set_option("gemm_pair", 0)
         ms3 = timeit(lambda: ops.gemm(A, W, bias=b, residual=R, mode=mode))
-        ops.set_option("gemm_wres", 2)
-        res[f"{name}_cluster"] = {"ms": ms2, "tflops": 2.0 * M * N * K / ms2 / 1e9, "ms_plain": ms3}
-        print(f"{name}_cluster", res[f"{name}_cluster"], flush=True)
+        ops.set_option("gemm_pair", 1)
+        res[f"{name}_pair"] = {"ms_pair": ms2, "ms_single": ms3, "tflops_pair": 2.0 * M * N * K / ms2 / 1e9}
+        print(f"{name}_pair", res[f"{name}_pair"], flush=True)
     # ---- convs
     for name, n, H, ci, co, cnt in [("conv_L0_320", NI, 64, 320, 320, 8), ("conv_L0_960_320", NI, 64, 960, 320, 1),
                                     ("conv_L0_640_320", NI, 64, 640, 320, 2), ("conv_L1_640", NI, 32, 640, 640, 8),
@@ -77,12 +76,12 @@ def main():
         w = ops.pack_conv3x3((torch.randn(co, ci, 3, 3, device=DEV) / math.sqrt(9 * ci)).half())
         b = torch.randn(co, device=DEV)
         ms = timeit(lambda: ops.conv3x3(x, w, bias=b))
-        ops.set_option("gemm_cluster", 1)
+        ops.set_option("gemm_pair", 0)
         ms2 = timeit(lambda: ops.conv3x3(x, w, bias=b))
-        ops.set_option("gemm_cluster", 0)
+        ops.set_option("gemm_pair", 1)
         fl = 2.0 * n * H * H * co * 9 * ci
-        res[name] = {"ms": ms, "tflops": fl / ms / 1e9, "count": cnt, "ms_total": ms * cnt, "ms_cluster": ms2,
-                     "tflops_cluster": fl / ms2 / 1e9}
+        res[name] = {"ms": ms, "tflops": fl / ms / 1e9, "count": cnt, "ms_total": ms * cnt, "ms_single_cta": ms2,
+                     "tflops_single_cta": fl / ms2 / 1e9}
         print(name, res[name], flush=True)
     # ---- attention
     for li, (C, hw) in enumerate(levels):

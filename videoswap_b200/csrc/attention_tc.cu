@@ -41,8 +41,7 @@ struct TCfg {
   static constexpr int KV_BLOCK_BYTES = BKV * 128;
   static constexpr int KV_STAGE_BYTES = 2 * NCB * KV_BLOCK_BYTES;     // K then V
   static constexpr int P_TILE_BYTES = TQ * 128;
-  static constexpr int XCH_BYTES = (D <= 64) ? 2 * 4 * TQ * 4 : 0;      // row-maximum exchange slots (SPLIT == 2, d = 40 only)
-  static constexpr int SMEM = Q_BYTES + ST * KV_STAGE_BYTES + 4 * P_TILE_BYTES + XCH_BYTES + 1024 + 256;   // P double-buffered
+  static constexpr int SMEM = Q_BYTES + ST * KV_STAGE_BYTES + 4 * P_TILE_BYTES + 1024 + 256;   // P double-buffered
   static constexpr int O_STRIDE = (DPO <= 64) ? 64 : 128;             // TMEM column stride between O_0 and O_1
   static constexpr int S_COL = 0, O_COL = 4 * BKV;                    // S_{i,b} at (2 i + b) * BKV
   static constexpr int TMEM_COLS = 512;
@@ -71,18 +70,6 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// 2^x on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f with the 1.5 * 2^23 trick, cubic minimax of
-// 2^f on [-0.5, 0.5] (relative error 7.6e-5, a fifth of an fp16 ulp), exponent added with one integer LEA.  The softmax
-// is bound by the 16 ex2/clk/SM MUFU pipe, so a fraction of the exponentials of every key tile goes this way.
-__device__ __forceinline__ float poly_exp2(float x) {
-  x = fmaxf(x, -125.f);
-  const float t = x + 12582912.f;
-  const float f = x - (t - 12582912.f);
-  float p = fmaf(f, 0.05520551f, 0.24261396f);
-  p = fmaf(p, f, 0.69325476f);
-  p = fmaf(p, f, 0.99992773f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float r;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
@@ -102,17 +89,15 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, 
   return d;
 }
 
-// POLY of every 8 exponentials are evaluated on the FMA pipe (poly_exp2); SPLIT = threads per query row (1 or 2)
-template <int D, int POLY, int SPLIT, int HO>   // HO: key chunk (of 8) after which the MUFU pipe is handed over
-__global__ void __launch_bounds__(128 + 128 * 2 * SPLIT, 1) attn_tc_kernel(const __grid_constant__ TAttnArgs p) {
+template <int D, int HO>   // HO: key chunk (0..7) after which a softmax warpgroup hands the MUFU pipe over
+__global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_constant__ TAttnArgs p) {
   using C = TCfg<D>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t q_s = base;                                   // [2 tiles][NCB][128 rows x 128 B]
   const uint32_t kv_s = q_s + C::Q_BYTES;                      // [ST][K: NCB blocks | V: NCB blocks]
   const uint32_t p_s = kv_s + C::ST * C::KV_STAGE_BYTES;       // [2 tiles][2 buffers][128 rows x 128 B]
-  const uint32_t xch_s = p_s + 4 * C::P_TILE_BYTES;             // [2 parities][2 tiles][2 halves][128 rows] fp32
-  const uint32_t bars = xch_s + C::XCH_BYTES;
+  const uint32_t bars = p_s + 4 * C::P_TILE_BYTES;
   const uint32_t q_full = bars;
   auto kv_full = [&](int s) { return bars + 8u * (1 + s); };
   auto kv_empty = [&](int s) { return bars + 8u * (1 + C::ST + s); };
@@ -135,7 +120,7 @@ __global__ void __launch_bounds__(128 + 128 * 2 * SPLIT, 1) attn_tc_kernel(const
     for (int i = 0; i < 2; ++i) {
       for (int bb = 0; bb < 2; ++bb) {
         mbar_init(s_full(i, bb), 1);
-        mbar_init(p_full(i, bb), 128 * SPLIT);
+        mbar_init(p_full(i, bb), 128);
         mbar_init(p_empty(i, bb), 1);
       }
     }
@@ -255,69 +240,51 @@ __global__ void __launch_bounds__(128 + 128 * 2 * SPLIT, 1) attn_tc_kernel(const
     }
   } else if (warp >= 4) {
     // ================================================================ softmax warpgroups + epilogue
-    // SPLIT == 2: two threads (in different warps of the same TMEM lane quarter) share a query row, each owning 32 of
-    // the 64 keys of every tile; the row maximum is exchanged through shared memory under a 64-thread named barrier.
-    // Sixteen softmax warps (4 per scheduler) instead of eight: the softmax is bound by the latency of each warp's
-    // serial tile (ld -> max -> exp -> pack -> store -> arrive), not by a pipe, and the extra warps fill the gaps.
-    constexpr int HK = BKV / SPLIT;              // keys per thread and tile
-    const int idx = warp - 4;
-    const int i = (idx >> 2) & 1;                // query tile handled by this warpgroup
-    const int half = idx >> 3;                   // key half (always 0 for SPLIT == 1)
+    const int i = (warp - 4) >> 2;               // query tile handled by this warpgroup
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;         // query row inside the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
     const uint32_t o_addr = tmem + lane_addr + C::O_COL + i * C::O_STRIDE;
     const uint32_t p_row0 = p_s + 2 * i * C::P_TILE_BYTES + row * 128;
-    const uint32_t xch_mine = xch_s + ((i * 2 + half) * TQ + row) * 4, xch_peer = xch_s + ((i * 2 + (half ^ 1)) * TQ + row) * 4;
     const float sc = p.scale_log2;
     float m_used = -INFINITY;
-    // Ping-pong of the two softmax warpgroups on the MUFU pipe (SPLIT == 1): a warpgroup enters its exponential phase only
-    // when the other one has left its own (256-thread named barriers 9 + i: sync = "my turn", arrive = "your turn"), so one
-    // does load / max / pack / store work while the other saturates the 16 ex2/clk/SM pipe.  P is double-buffered so that
-    // nothing else is on the critical path.
-    constexpr bool PP = SPLIT == 1;
-    if (PP && i == 1) named_bar_arrive(9 + 0, 256);   // warpgroup 0 goes first
+    // Ping-pong of the two softmax warpgroups on the MUFU pipe: a warpgroup enters its exponential phase only when the
+    // other one is (almost) through its own (256-thread named barriers 9 + i: sync = "my turn", arrive = "your turn"), so
+    // one does load / max / pack / store work while the other keeps the 16 ex2/clk/SM pipe busy.  P is double-buffered so
+    // that nothing else is on the critical path.
+    if (i == 1) named_bar_arrive(9 + 0, 256);    // warpgroup 0 goes first
     for (int j = 0; j < nkt; ++j) {
       mbar_wait(s_full(i, j & 1), (j >> 1) & 1);
       tc_fence_after();
-      const int kbase = j * BKV + half * HK;
-      // ---- this thread's part of the S row lives in registers: one TMEM round trip per tile
-      uint32_t sv[HK];
-      const uint32_t s_addr = tmem + lane_addr + C::S_COL + (2 * i + (j & 1)) * BKV + half * HK;
+      const int kbase = j * BKV;
+      // ---- the S row of this tile lives in registers: one TMEM round trip per tile
+      uint32_t sv[BKV];
+      const uint32_t s_addr = tmem + lane_addr + C::S_COL + (2 * i + (j & 1)) * BKV;
       tmem_ld32(s_addr, sv);
-      if (HK == 64) tmem_ld32(s_addr + 32, sv + 32);
+      tmem_ld32(s_addr + 32, sv + 32);
       tmem_ld_wait();
-      if (kbase + HK > p.nk) {   // keys beyond nk were zero-filled by TMA: mask them (last tile only)
+      if (kbase + BKV > p.nk) {   // keys beyond nk were zero-filled by TMA: mask them (last tile only)
 #pragma unroll
-        for (int t = 0; t < HK; ++t)
+        for (int t = 0; t < BKV; ++t)
           if (kbase + t >= p.nk) sv[t] = 0xff800000u;   // -inf
       }
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-      for (int t = 0; t < HK; t += 8) {            // FMNMX3: two new elements per instruction, four independent chains
+      for (int t = 0; t < BKV; t += 8) {           // FMNMX3: two new elements per instruction, four independent chains
         mx0 = fmax3(mx0, __uint_as_float(sv[t]), __uint_as_float(sv[t + 1]));
         mx1 = fmax3(mx1, __uint_as_float(sv[t + 2]), __uint_as_float(sv[t + 3]));
         mx2 = fmax3(mx2, __uint_as_float(sv[t + 4]), __uint_as_float(sv[t + 5]));
         mx3 = fmax3(mx3, __uint_as_float(sv[t + 6]), __uint_as_float(sv[t + 7]));
       }
-      float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      if (SPLIT == 2) {                            // row maximum over both key halves (slots double-buffered by tile parity)
-        const uint32_t jb = (uint32_t)(j & 1) * (4 * TQ * 4);
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(xch_mine + jb), "f"(mx) : "memory");
-        named_bar_sync(1 + i * 4 + quarter, 64);
-        float other;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(xch_peer + jb) : "memory");
-        mx = fmaxf(mx, other);
-      }
-      // ---- lazy rescale: only when the maximum moved by more than 2^8 (always true on the first tile: m_used=-inf);
-      // the accumulator column chunks are split between the threads sharing the row
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      // ---- lazy rescale: only when the maximum moved by more than 2^8 (always true on the first tile: m_used=-inf)
       const bool need = (mx - m_used) * sc > 8.f;
       if (j > 0 && __any_sync(0xffffffffu, need)) {
         mbar_wait(p_empty(i, (j - 1) & 1), ((j - 1) >> 1) & 1);       // O_i quiescent: the previous P V has retired
         tc_fence_after();
         const float alpha = need ? exp2f((m_used - mx) * sc) : 1.f;   // also rescales the row-sum column O[:, D]
 #pragma unroll 1
-        for (int c0 = half * 16; c0 < C::DPO; c0 += 16 * SPLIT) {
+        for (int c0 = 0; c0 < C::DPO; c0 += 16) {
           uint32_t v[16];
           tmem_ld16(o_addr + c0, v);
           tmem_ld_wait();
@@ -331,31 +298,30 @@ __global__ void __launch_bounds__(128 + 128 * 2 * SPLIT, 1) attn_tc_kernel(const
       const float ms = m_used * sc;
       if (j >= 2) mbar_wait(p_empty(i, j & 1), ((j - 2) >> 1) & 1);   // this P buffer was consumed two key tiles ago
       const uint32_t p_row = p_row0 + (j & 1) * C::P_TILE_BYTES;
-      if (PP) named_bar_sync(9 + i, 256);                               // my turn on the MUFU pipe
+      named_bar_sync(9 + i, 256);                                       // my turn on the MUFU pipe
       // ---- P = exp2(S*scale - m) -> fp16 -> swizzled shared memory (A operand of the P V MMA); exp2(-inf) = 0 masks
 #pragma unroll
-      for (int c8 = 0; c8 < HK / 8; ++c8) {        // one 16-byte chunk (8 keys) at a time
+      for (int c8 = 0; c8 < BKV / 8; ++c8) {       // one 16-byte chunk (8 keys) at a time
         uint32_t pk[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const float x0 = __uint_as_float(sv[c8 * 8 + 2 * u]) * sc - ms, x1 = __uint_as_float(sv[c8 * 8 + 2 * u + 1]) * sc - ms;
-          const float e0 = (2 * u < POLY) ? poly_exp2(x0) : fast_exp2(x0);
-          const float e1 = (2 * u + 1 < POLY) ? poly_exp2(x1) : fast_exp2(x1);
+          const float e0 = fast_exp2(__uint_as_float(sv[c8 * 8 + 2 * u]) * sc - ms);
+          const float e1 = fast_exp2(__uint_as_float(sv[c8 * 8 + 2 * u + 1]) * sc - ms);
           const __half2 h = __floats2half2_rn(e0, e1);   // the row sum is formed by the MMA from these rounded values
           pk[u] = *reinterpret_cast<const uint32_t*>(&h);
         }
-        const uint32_t dst = p_row + (((half * (HK / 8) + c8) ^ (row & 7)) << 4);
+        const uint32_t dst = p_row + ((c8 ^ (row & 7)) << 4);
         asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
                      : "memory");
         // hand the MUFU pipe to the other warpgroup a little before the last exponentials (its wake-up takes a while)
-        if (PP && c8 == HO) named_bar_arrive(9 + (i ^ 1), 256);
+        if (c8 == HO) named_bar_arrive(9 + (i ^ 1), 256);
       }
       fence_proxy_async();                     // generic-proxy smem writes -> visible to the tensor-core (async) proxy
       tc_fence_before();
       mbar_arrive(p_full(i, j & 1));
     }
-    if (PP && i == 0) named_bar_sync(9 + 0, 256);    // absorb the other warpgroup's last hand-over
-    // ---- epilogue: O / l -> fp16 -> HBM (column chunks split between the threads sharing the row)
+    if (i == 0) named_bar_sync(9 + 0, 256);      // absorb the other warpgroup's last hand-over
+    // ---- epilogue: O / l -> fp16 -> HBM
     mbar_wait(o_full, 0);
     tc_fence_after();
     const int qrow = q0 + i * TQ + row;
@@ -368,7 +334,7 @@ __global__ void __launch_bounds__(128 + 128 * 2 * SPLIT, 1) attn_tc_kernel(const
     }
     __half* orow = p.o + b * p.o_bs + (long long)qrow * p.ldo + head * D;
 #pragma unroll 1
-    for (int c0 = half * 16; c0 < C::DPO; c0 += 16 * SPLIT) {
+    for (int c0 = 0; c0 < C::DPO; c0 += 16) {
       uint32_t v[16];
       tmem_ld16(o_addr + c0, v);
       tmem_ld_wait();
@@ -395,13 +361,13 @@ __global__ void __launch_bounds__(128 + 128 * 2 * SPLIT, 1) attn_tc_kernel(const
   }
 }
 
-template <int D, int POLY, int SPLIT, int HO>
+template <int D, int HO>
 int launch(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv, __half* o, int ldo,
            int batch, int nq, int nk, int heads, long long q_bs, long long kv_bs, long long o_bs, int kv_div) {
   using C = TCfg<D>;
   static bool configured = false;
   if (!configured) {
-    VS_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D, POLY, SPLIT, HO>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    VS_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D, HO>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     configured = true;
   }
   TAttnArgs a;
@@ -425,7 +391,7 @@ int launch(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, 
   a.scale_log2 = 1.4426950408889634f / sqrtf((float)D);
   dim3 grid((nq + 2 * TQ - 1) / (2 * TQ), heads, batch);
   ProfScope prof(st, PC_ATTN, 4.0 * batch * heads * (double)nq * nk * D, 1, nq, nk, D);
-  attn_tc_kernel<D, POLY, SPLIT, HO><<<grid, 128 + 128 * 2 * SPLIT, C::SMEM, st>>>(a);
+  attn_tc_kernel<D, HO><<<grid, ATT_THREADS, C::SMEM, st>>>(a);
   VS_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -439,19 +405,11 @@ int attention_tc(cudaStream_t st, const __half* q, int ldq, const __half* k, int
   if ((ldq % 8) || (ldk % 8) || (ldv % 8) || (ldo % 8)) return -1;
   if ((q_bs % 8) || (kv_bs % 8)) return -1;
 #define VS_ATT_ARGS st, q, ldq, k, ldk, v, ldv, o, ldo, batch, nq, nk, heads, q_bs, kv_bs, o_bs, kv_div
-  // A/B switches (runtime.cu): attn_poly (FMA-pipe exponentials), attn_split (two threads per row, d = 40 only),
-  // attn_handoff (0 = hand the MUFU pipe over only after the last exponential).  Measured on one box, interleaved
-  // repetitions, L0 self-attention: hand-over after chunk 6 of 8: 1549 us, after the last: 1607 us, poly: 1703 us.
-  const int poly = get_option("attn_poly"), split = get_option("attn_split"), early = get_option("attn_handoff");
-  if (d == 40) {
-    if (split == 2) return launch<40, 0, 2, 7>(VS_ATT_ARGS);
-    if (poly) return launch<40, 2, 1, 6>(VS_ATT_ARGS);
-    return early ? launch<40, 0, 1, 6>(VS_ATT_ARGS) : launch<40, 0, 1, 7>(VS_ATT_ARGS);
-  }
-  if (d == 80) {
-    if (poly) return launch<80, 2, 1, 6>(VS_ATT_ARGS);
-    return early ? launch<80, 0, 1, 6>(VS_ATT_ARGS) : launch<80, 0, 1, 7>(VS_ATT_ARGS);
-  }
+  // "attn_handoff" (A/B switch): 1 = the softmax ping-pong hands the MUFU pipe over after key chunk 6 of 8 (L0 self-
+  // attention 1549 us), 0 = after the last exponential (1607 us; interleaved repetitions on one box).
+  const bool early = get_option("attn_handoff") != 0;
+  if (d == 40) return early ? launch<40, 6>(VS_ATT_ARGS) : launch<40, 7>(VS_ATT_ARGS);
+  if (d == 80) return early ? launch<80, 6>(VS_ATT_ARGS) : launch<80, 7>(VS_ATT_ARGS);
 #undef VS_ATT_ARGS
   return -1;
 }

@@ -116,15 +116,9 @@ ProfScope::~ProfScope() {
 struct Option { const char* name; int value; };
 static Option g_options[] = {
     {"attn_tc", 1},        // tcgen05 attention for d = 40 / 80 (0 = mma.sync kernel)
-    {"attn_poly", 0},      // != 0: 2 of every 8 exponentials on the FMA pipe instead of MUFU (measured: no gain)
-    {"attn_split", 1},     // threads per query row in the tcgen05 attention softmax (1 or 2; measured equal)
     {"attn_handoff", 1},   // 1: the softmax ping-pong hands the MUFU pipe over after 7 of 8 key chunks, 0: after the last
-    {"gemm_wres", 0},      // unused (kept so old scripts do not fail)
-    {"gemm_pair", 1},      // CTA pairs (cta_group::2, 256-row tiles) for GEMM / conv with >= 2 row tiles
-    {"gemm_cluster", 0},   // unused (old multicast experiment)
+    {"gemm_pair", 1},      // CTA pairs (cta_group::2, 256-row tiles): 1 = for K >= 768, 0 = never, 2 = whenever possible
     {"gemm_stages", 0},    // smem ring depth limit (0 = all)
-    {"gemm_order", 0},     // persistent tile order: 0 = n fastest, 1 = m fastest
-    {"exp_a", 0}, {"exp_b", 0}, {"exp_c", 0},   // scratch switches for experiments
 };
 int set_option(const char* name, int value) {
   for (Option& o : g_options)
