@@ -118,6 +118,8 @@ __device__ __forceinline__ void load_rows(uint32_t dst, const __half* src, int l
 template <int D>
 __global__ void __launch_bounds__(128) attn_kernel(const AttnParams p) {
   using C = ACfg<D>;
+  pdl_trigger();
+  pdl_wait();
   constexpr int DP = C::DP, LDSB = C::LDS * 2, NT = C::BKV / 8, ON = DP / 8;
   extern __shared__ __align__(16) uint8_t smem[];
   const uint32_t q_s = smem_u32(smem);
@@ -221,9 +223,7 @@ int launch_attn(cudaStream_t st, const AttnParams& p, int batch, int heads) {
   }
   dim3 grid((p.nq + C::BQ - 1) / C::BQ, heads, batch);
   ProfScope prof(st, PC_ATTN, 4.0 * batch * heads * (double)p.nq * p.nk * D);
-  attn_kernel<D><<<grid, 128, C::SMEM, st>>>(p);
-  VS_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  return launch_pdl(attn_kernel<D>, grid, dim3(128), C::SMEM, st, 1, p);
 }
 
 // ================================================================================================ temporal
@@ -236,6 +236,8 @@ struct TAttnParams {
 
 template <int D, int FP>   // FP = frames padded to 16 or 32
 __global__ void __launch_bounds__(128) tattn_kernel(const TAttnParams p) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int DP = (D + 15) / 16 * 16, LDS = DP + 8, LDSB = LDS * 2, CH = DP / 8;
   constexpr int MT = FP / 16, NT = FP / 8, ON = DP / 8;
   extern __shared__ __align__(16) uint8_t smem[];
@@ -321,9 +323,7 @@ int launch_tattn(cudaStream_t st, const TAttnParams& p) {
   }
   const long long blocks = (p.items + 3) / 4;
   ProfScope prof(st, PC_TATTN, 8.0 * p.B * p.F * (double)p.HW * p.C);   // bytes: read 3C + write C fp16 per token
-  tattn_kernel<D, FP><<<(unsigned)blocks, 128, SMEM, st>>>(p);
-  VS_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  return launch_pdl(tattn_kernel<D, FP>, dim3((unsigned)blocks), dim3(128), SMEM, st, 1, p);
 }
 
 }  // namespace

@@ -132,6 +132,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_ptr;
+  pdl_trigger();
+  pdl_wait();                                    // set-up above overlaps the previous kernel's tail
 
   // Single-issuer roles run with the whole warp (uniform values) and predicate the issuing instructions on one elected
   // lane -- see the note in gemm.cu.
@@ -391,9 +393,7 @@ int launch(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, 
   a.scale_log2 = 1.4426950408889634f / sqrtf((float)D);
   dim3 grid((nq + 2 * TQ - 1) / (2 * TQ), heads, batch);
   ProfScope prof(st, PC_ATTN, 4.0 * batch * heads * (double)nq * nk * D, 1, nq, nk, D);
-  attn_tc_kernel<D, HO><<<grid, ATT_THREADS, C::SMEM, st>>>(a);
-  VS_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  return launch_pdl(attn_tc_kernel<D, HO>, grid, dim3(ATT_THREADS), C::SMEM, st, 1, a);
 }
 
 }  // namespace

@@ -35,6 +35,38 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
                   const uint32_t* box, int swizzle /* 0 none, 1 = 128B, 2 = 64B, 3 = 32B */);
 
 int num_sms();
+int get_option(const char* name);
+
+#ifdef __CUDACC__
+// Launches `kernel` with the programmatic-stream-serialization attribute (see pdl_wait() below) and, for cluster_x > 1,
+// a cluster dimension.  Only for kernels that call pdl_wait() before their first global-memory access.
+template <typename... KArgs, typename... Args>
+int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (get_option("pdl") != 0) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  VS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+  return 0;
+}
+#endif
 
 // profiling categories (work = algorithmic FLOPs for tensor kernels, algorithmic bytes for HBM-bound kernels)
 enum ProfCat { PC_GEMM = 0, PC_CONV = 1, PC_ATTN = 2, PC_TATTN = 3, PC_GROUPNORM = 4, PC_LAYERNORM = 5, PC_OTHER = 6, PC_COUNT = 7 };
@@ -138,6 +170,13 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+
+// ---- programmatic dependent launch.  A kernel launched with launch_pdl() may start while its predecessor in the stream
+// is still draining: everything before pdl_wait() (barrier init, TMEM allocation, descriptor prefetch) overlaps the
+// predecessor's tail; pdl_wait() returns once the predecessor grid has completed and its memory is visible, so NO global
+// memory may be read or written before it.  pdl_trigger() lets the successor start being scheduled.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {

@@ -137,6 +137,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   __syncthreads();
   if (PAIR) cluster_sync_all();                  // the peer's barriers are initialised before any remote arrive / TMA credit
   tc_fence_after();
+  pdl_trigger();                                 // the next kernel may start its own set-up
+  pdl_wait();                                    // everything above overlapped the previous kernel's tail; its data is visible now
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   // The two single-issuer roles below run with the WHOLE warp (all values warp-uniform) and predicate only the issuing
@@ -453,26 +455,12 @@ int launch(cudaStream_t st, const GemmParams& p) {
   if (PAIR) {
     const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
     const int max_clusters = num_sms() / 2;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * (pairs < max_clusters ? pairs : max_clusters));
-    cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = C::SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    VS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, PAIR>, p));
-    return 0;
+    return launch_pdl(gemm_tc_kernel<BN, EPI, PAIR>, dim3(2 * (pairs < max_clusters ? pairs : max_clusters)), dim3(GEMM_THREADS),
+                      C::SMEM_BYTES, st, 2, p);
   }
   const int total = p.m_tiles * p.n_tiles;
-  const int grid = total < num_sms() ? total : num_sms();
-  gemm_tc_kernel<BN, EPI, PAIR><<<grid, GEMM_THREADS, C::SMEM_BYTES, st>>>(p);
-  VS_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  return launch_pdl(gemm_tc_kernel<BN, EPI, PAIR>, dim3(total < num_sms() ? total : num_sms()), dim3(GEMM_THREADS), C::SMEM_BYTES,
+                    st, 1, p);
 }
 
 template <int BN, bool PAIR>

@@ -37,6 +37,8 @@ __global__ void gn_stats_kernel(const GnParams p) {
   extern __shared__ float sh[];   // [groups][2]
   for (int i = threadIdx.x; i < p.groups * 2; i += blockDim.x) sh[i] = 0.f;
   __syncthreads();
+  pdl_trigger();
+  pdl_wait();
   const int set = blockIdx.y;
   const int cv = threadIdx.x % p.CV, r = threadIdx.x / p.CV;
   const int ga = (cv * 8) / p.cpg, gb = (cv * 8 + 7) / p.cpg;
@@ -73,6 +75,8 @@ __global__ void gn_stats_kernel(const GnParams p) {
 }
 
 __global__ void gn_apply_kernel(const GnParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int set = blockIdx.y;
   const int cv = threadIdx.x % p.CV, r = threadIdx.x / p.CV;
   float a[8], b[8];
@@ -223,6 +227,8 @@ __global__ void __launch_bounds__(256) ln5_kernel(const __half* __restrict__ x, 
     b2[i][0] = __floats2half2_rn(ba.x, ba.y); b2[i][1] = __floats2half2_rn(ba.z, ba.w);
     b2[i][2] = __floats2half2_rn(bb.x, bb.y); b2[i][3] = __floats2half2_rn(bb.z, bb.w);
   }
+  pdl_trigger();
+  pdl_wait();          // gamma / beta above are weights (not produced by the previous kernel)
   const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   // Two row groups per iteration (2 x 5 independent 16-byte loads in flight per thread) hide the HBM latency that the
@@ -303,9 +309,7 @@ int groupnorm_stats(cudaStream_t st, const __half* x1, int c1, const __half* x2,
   p.sums = sums;
   if (zero_first) VS_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * groups * (nimg / imgs_per_set), st));
   ProfScope prof(st, PC_GROUPNORM, 2.0 * nimg * (double)hw * (c1 + c2));   // bytes read
-  gn_stats_kernel<<<grid, threads, groups * 2 * sizeof(float), st>>>(p);
-  VS_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  return launch_pdl(gn_stats_kernel, grid, dim3(threads), groups * 2 * sizeof(float), st, 1, p);
 }
 
 int groupnorm_apply(cudaStream_t st, const __half* x1, int c1, const __half* x2, int c2, int nimg, int hw,
@@ -318,9 +322,7 @@ int groupnorm_apply(cudaStream_t st, const __half* x1, int c1, const __half* x2,
   p.sums = const_cast<float*>(sums);
   p.gamma = gamma; p.beta = beta; p.eps = eps; p.silu = silu ? 1 : 0; p.out = out;
   ProfScope prof(st, PC_GROUPNORM, 4.0 * nimg * (double)hw * (c1 + c2), 1, (long long)nimg * hw, c1 + c2, imgs_per_set);
-  gn_apply_kernel<<<grid, threads, 0, st>>>(p);
-  VS_CHECK_CUDA(cudaGetLastError());
-  return 0;
+  return launch_pdl(gn_apply_kernel, grid, dim3(threads), 0, st, 1, p);
 }
 
 int layernorm(cudaStream_t st, const __half* x, int rows, int C, const float* gamma, const float* beta, const float* pe,
@@ -338,11 +340,10 @@ int layernorm(cudaStream_t st, const __half* x, int rows, int C, const float* ga
     if (need < 1) need = 1;
     const long long cap = (long long)num_sms() * 8;
     const int grid = (int)(need < cap ? need : cap);
-    if (lpr == 8) ln5_kernel<8><<<grid, 256, 0, st>>>(x, rows, gamma, beta, pe, hw, F, out);
-    else if (lpr == 16) ln5_kernel<16><<<grid, 256, 0, st>>>(x, rows, gamma, beta, pe, hw, F, out);
-    else ln5_kernel<32><<<grid, 256, 0, st>>>(x, rows, gamma, beta, pe, hw, F, out);
-    VS_CHECK_CUDA(cudaGetLastError());
-    return 0;
+    const long long rows_ll = rows;
+    if (lpr == 8) return launch_pdl(ln5_kernel<8>, dim3(grid), dim3(256), 0, st, 1, x, rows_ll, gamma, beta, pe, hw, F, out);
+    if (lpr == 16) return launch_pdl(ln5_kernel<16>, dim3(grid), dim3(256), 0, st, 1, x, rows_ll, gamma, beta, pe, hw, F, out);
+    return launch_pdl(ln5_kernel<32>, dim3(grid), dim3(256), 0, st, 1, x, rows_ll, gamma, beta, pe, hw, F, out);
   }
   switch (vpl) {
     case 1: ln_kernel<1><<<blocks, threads, 0, st>>>(x, rows, C, gamma, beta, pe, hw, F, out); break;
