@@ -110,6 +110,13 @@ int vs_groupnorm(void* stream, const void* d_x1, int c1, const void* d_x2, int c
                  int groups, float eps, const float* d_gamma, const float* d_beta, int silu, float* d_sums, void* d_out);
 int vs_layernorm(void* stream, const void* d_x, int rows, int C, const float* d_gamma, const float* d_beta,
                  const float* d_pe, int hw, int F, void* d_out);
+/* LayerNorm(x) (+ pe[(row / hw) % frames]) followed by a linear layer (mode 0) or GEGLU projection (mode 1, packed
+ * weights), with the norm folded into ONE GEMM on the raw input (motion_module.py:224-228,294 + the q/k/v projection;
+ * attention.py:229-256).  C in {320, 640, 1280}.  Scratch: d_wf [N, C] fp16, d_u / d_c [N] fp32, d_cpe [pe_len, N] fp32
+ * (only with d_pe), d_stats [M, 2] fp32.  The UNet forward uses the same kernels with the folding done at load time. */
+int vs_ln_linear(void* stream, const void* d_x, int M, int C, const void* d_w, const float* d_bias, int N,
+                 const float* d_gamma, const float* d_beta, const float* d_pe, int pe_len, int hw, int frames, int mode,
+                 void* d_wf, float* d_u, float* d_c, float* d_cpe, float* d_stats, void* d_out);
 int vs_attention(void* stream, const void* d_q, int ldq, const void* d_k, int ldk, const void* d_v, int ldv, void* d_o,
                  int ldo, int batch, int nq, int nk, int heads, int d, long long q_bstride, long long kv_bstride,
                  long long o_bstride, int kv_div);
@@ -132,7 +139,9 @@ int vs_profile_dump(const char* path);   /* CSV: category, shape (m,n,k), work p
  *   "attn_tc"      1  tcgen05/TMEM attention kernel for head dims 40/80; 0 forces the mma.sync kernel
  *   "attn_handoff" 1  softmax warpgroups hand the MUFU pipe over after 7 of 8 key chunks; 0 = after the last one
  *   "gemm_pair"    1  CTA pairs (cta_group::2, 256-row tiles) for K >= 768; 0 = never; 2 = whenever >= 2 row tiles
- *   "gemm_stages"  0  limit of the shared-memory ring depth of the GEMM (0 = as many as fit) */
+ *   "gemm_stages"  0  limit of the shared-memory ring depth of the GEMM (0 = as many as fit)
+ *   "ln_fold"      1  LayerNorms folded into the consuming GEMM; 0 = stand-alone LayerNorm kernel
+ *   "pdl"          1  programmatic dependent launch between the hot kernels; 0 = plain stream order */
 int vs_set_option(const char* name, int value);
 
 #ifdef __cplusplus

@@ -181,6 +181,32 @@ def check_layernorm(rows=1000, C=320, pe=False, seed=110):
     return _res(out, ref)
 
 
+def check_ln_linear(rows=2000, C=320, N=960, pe=False, geglu=False, seed=115, hw=8):
+    """LayerNorm (+ temporal PE) folded into the consuming GEMM vs LayerNorm -> linear / GEGLU in fp32."""
+    x = (_rand((rows, C), seed) * 2 + 0.7).half()
+    gamma = (1 + 0.1 * _rand((C,), seed + 1)).float()
+    beta = (0.1 * _rand((C,), seed + 2)).float()
+    Fr = 5
+    table = _rand((24, C), seed + 3).float() if pe else None
+    rows = (rows // (Fr * hw)) * Fr * hw
+    x = x[:rows].contiguous()
+    W = _rand((N, C), seed + 4, 1 / math.sqrt(C)).half()
+    b = _rand((N,), seed + 5).float() if geglu else None
+    y = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
+    if pe:
+        y = y + table[(torch.arange(rows, device=DEV) // hw) % Fr]
+    ref = y @ W.float().t()
+    if geglu:
+        ref = ref + b
+        h = N // 2
+        ref = ref[:, :h] * F.gelu(ref[:, h:])
+        Wp, bp = ops.pack_geglu(W, b.half())
+        out = ops.ln_linear(x, Wp, gamma, beta, bias=bp, mode=ops.EPI_GEGLU)
+    else:
+        out = ops.ln_linear(x, W, gamma, beta, pe=table, hw=hw, frames=Fr)
+    return _res(out, ref)
+
+
 # ---------------------------------------------------------------------------------------------------- attention
 def _mha_ref(q, k, v, heads):
     B, nq, C = q.shape
@@ -300,6 +326,11 @@ CHECKS = {
     "gn5d_concat": lambda: check_groupnorm(c1=640, c2=320),
     "gn_frame": lambda: check_groupnorm(per_frame=True, silu=False, eps=1e-6),
     "gn5d_1280": lambda: check_groupnorm(B=1, Fr=2, H=4, W=4, c1=1280, c2=1280),
+    "ln_fold_qkv_320": lambda: check_ln_linear(),
+    "ln_fold_qkv_pe_640": lambda: check_ln_linear(rows=1280, C=640, N=1920, pe=True, seed=116, hw=64),   # one frame per warp
+    "ln_fold_q_1280": lambda: check_ln_linear(rows=700, C=1280, N=1280, seed=117),
+    "ln_fold_geglu_320": lambda: check_ln_linear(rows=1500, C=320, N=2560, geglu=True, seed=118),
+    "ln_fold_pe_mixed_warps": lambda: check_ln_linear(rows=40 * 7, C=320, N=960, pe=True, seed=119),
     "ln_320": lambda: check_layernorm(C=320),
     "ln_1280_pe": lambda: check_layernorm(rows=640, C=1280, pe=True),
     "self_attn_d40": lambda: check_self_attention(C=320),

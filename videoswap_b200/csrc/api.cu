@@ -81,6 +81,18 @@ extern "C" int vs_layernorm(void* stream, const void* d_x, int rows, int C, cons
                             const float* d_pe, int hw, int F, void* d_out) {
   return layernorm((cudaStream_t)stream, (const __half*)d_x, rows, C, d_gamma, d_beta, d_pe, hw, F, (__half*)d_out);
 }
+extern "C" int vs_ln_linear(void* stream, const void* d_x, int M, int C, const void* d_w, const float* d_bias, int N,
+                            const float* d_gamma, const float* d_beta, const float* d_pe, int pe_len, int hw, int frames,
+                            int mode, void* d_wf, float* d_u, float* d_c, float* d_cpe, float* d_stats, void* d_out) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int e = ln_fold(st, (const __half*)d_w, N, C, d_gamma, d_beta, d_bias, d_pe, pe_len, (__half*)d_wf, d_u, d_c, d_cpe)) return e;
+  if (int e = ln_rowstats(st, (const __half*)d_x, M, C, d_stats)) return e;
+  GemmArgs g;
+  g.A = (const __half*)d_x; g.K1 = C; g.lda1 = C; g.Bw = (const __half*)d_wf; g.M = M; g.N = N; g.bias = d_c;
+  g.ln_stats = d_stats; g.ln_u = d_u; g.out = (__half*)d_out; g.ldc = mode == EPI_GEGLU ? N / 2 : N; g.mode = mode;
+  if (d_pe) { g.rowvec = d_cpe; g.ldrv = N; g.pix_per_batch = hw; g.rv_mod = frames; }
+  return gemm_tc(st, g);
+}
 extern "C" int vs_attention(void* stream, const void* d_q, int ldq, const void* d_k, int ldk, const void* d_v, int ldv,
                             void* d_o, int ldo, int batch, int nq, int nk, int heads, int d, long long q_bstride,
                             long long kv_bstride, long long o_bstride, int kv_div) {

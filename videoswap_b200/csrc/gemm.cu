@@ -36,9 +36,9 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int GEMM_THREADS = 384;                   // 4 control warps + 2 epilogue warpgroups
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int EPI_COLS = 32;                        // output columns per epilogue sub-tile (64 B of fp16: SWIZZLE_64B)
-constexpr int EPI_WARP_BYTES = 3072;                // per epilogue warp: 2 KB transpose staging + 1 KB bias slice
+constexpr int EPI_WARP_BYTES = 4096;                // per epilogue warp: 2 KB transpose staging + 1 KB bias + 1 KB LN-fold slice
 constexpr int EPI_BYTES = 8 * EPI_WARP_BYTES;
-enum { EPI_F_GEGLU = 1, EPI_F_RES = 2, EPI_F_RV = 4 };   // compile-time epilogue features
+enum { EPI_F_GEGLU = 1, EPI_F_RES = 2, EPI_F_RV = 4, EPI_F_LN = 8 };   // compile-time epilogue features
 
 struct GemmParams {
   CUtensorMap tmA, tmA2, tmB;
@@ -55,6 +55,9 @@ struct GemmParams {
   const float* rowvec;
   int ldrv;
   int pix_per_batch;
+  int rv_mod;        // row-vector index = (pix / pix_per_batch) % rv_mod when > 0 (per-frame vectors)
+  const float2* ln_stats;   // folded LayerNorm: per-row (rstd, -mean * rstd)
+  const float* ln_u;        // ... and per-column sum of the gamma-scaled weight row
   const __half* residual;
   int ldr;
   __half* out;
@@ -92,6 +95,9 @@ template <int BN, int EPI, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   using C = Cfg<BN, PAIR>;
   constexpr bool GEGLU = (EPI & EPI_F_GEGLU) != 0, HAS_RES = (EPI & EPI_F_RES) != 0, HAS_RV = (EPI & EPI_F_RV) != 0;
+  // LN: the A operand is the RAW input of a LayerNorm whose affine map is folded into the weights:
+  //   LN(x) W^T = rstd (x W'^T) - rstd mean u + c,  W' = W * gamma, u[n] = sum_k W'[n,k], c = beta W^T + bias (the `bias`)
+  constexpr bool LN = (EPI & EPI_F_LN) != 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t epi_base = smem_base + C::STAGES * C::STAGE_BYTES;
@@ -241,7 +247,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     const int row = q * 32 + lane;          // row of the tile handled by this thread
     const int grp = (warp - 4) >> 2;
     const int acc = grp;
-    const uint32_t out_stage = epi_base + (warp - 4) * EPI_WARP_BYTES, bias_stage = out_stage + 2048;
+    const uint32_t out_stage = epi_base + (warp - 4) * EPI_WARP_BYTES, bias_stage = out_stage + 2048, u_stage = bias_stage + 1024;
     const int tr = lane >> 2, tch = lane & 3;   // transposed mapping: 8 rows x four 16-byte chunks per instruction
     const bool has_bias = p.bias != nullptr;
     const bool staged = p.staged != 0;
@@ -270,7 +276,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         const int oc0 = n_tile * OC;                                        // first output column of this tile
         const int nsub = (p.N - n0 < BN ? (GEGLU ? (p.N - n0) / 2 : p.N - n0) : OC) / EPI_COLS;
         const float* rv = nullptr;
-        if (HAS_RV && pix >= 0) rv = p.rowvec + (long long)(pix / p.pix_per_batch) * p.ldrv + n0;
+        // Row vectors (time embedding per batch element, positional offsets per frame): the 32 rows of a warp nearly always
+        // share one vector, which is then folded into the warp's bias slice; mixed warps read theirs per sub-tile.
+        bool rv_uniform = false;
+        const float* rv_warp = nullptr;
+        if (HAS_RV) {
+          int ri = -1;
+          if (pix >= 0) {
+            ri = pix / p.pix_per_batch;
+            if (p.rv_mod > 0) ri %= p.rv_mod;
+            rv = p.rowvec + (long long)ri * p.ldrv + n0;
+          }
+          const unsigned live = __ballot_sync(0xffffffffu, pix >= 0);
+          if (live != 0u) {
+            const int r0 = __shfl_sync(0xffffffffu, ri, __ffs(live) - 1);
+            rv_uniform = __all_sync(0xffffffffu, pix < 0 || ri == r0);
+            rv_warp = p.rowvec + (long long)r0 * p.ldrv;
+          }
+        }
+        float la = 1.f, lb = 0.f;           // folded LayerNorm: row scale and row shift factor
+        if (LN && pix >= 0) {
+          const float2 st2 = __ldg(p.ln_stats + pix);
+          la = st2.x; lb = st2.y;
+        }
         int tpix[4];                        // pixels of the rows this lane stores after the transpose
 #pragma unroll
         for (int i = 0; i < 4; ++i) tpix[i] = __shfl_sync(0xffffffffu, pix, i * 8 + tr);
@@ -285,13 +313,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         // The tile's bias vector goes to this warp's own shared-memory slice while the accumulator is still being
         // computed; the sub-tiles then read it as broadcast LDS.  (Read with __ldg inside the sub-tile loop, the epilogue
         // warps of the K = 320 GEMMs spent 31% of their time waiting for those loads.)
-        if (has_bias) {
+        const bool stage_bias = has_bias || (HAS_RV && rv_uniform);
+        if (stage_bias) {
           __syncwarp();                     // the previous tile's readers are done
 #pragma unroll
           for (int c = lane; c < BN / 4; c += 32) {
             const int n = n0 + 4 * c;
-            const float4 b = n + 3 < p.N ? __ldg(reinterpret_cast<const float4*>(p.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 b = (has_bias && n + 3 < p.N) ? __ldg(reinterpret_cast<const float4*>(p.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (HAS_RV && rv_uniform && n + 3 < p.N) {
+              const float4 r4 = __ldg(reinterpret_cast<const float4*>(rv_warp + n));
+              b.x += r4.x; b.y += r4.y; b.z += r4.z; b.w += r4.w;
+            }
             asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(bias_stage + 16 * c), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+            if (LN) {
+              const float4 u4 = n + 3 < p.N ? __ldg(reinterpret_cast<const float4*>(p.ln_u + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+              asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(u_stage + 16 * c), "f"(u4.x), "f"(u4.y), "f"(u4.z), "f"(u4.w) : "memory");
+            }
           }
           __syncwarp();
         }
@@ -310,8 +347,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
               const uint32_t bv = bias_stage + s * EPI_COLS * 4, bg = bv + (BN / 2) * 4;
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
-                const float4 b = lds_f4(bv + j * 4);
-                const float4 c = lds_f4(bg + j * 4);
+                float4 b = lds_f4(bv + j * 4);
+                float4 c = lds_f4(bg + j * 4);
+                if (LN) {                        // value / gate pre-activations of the folded LayerNorm
+                  const float4 uv = lds_f4(bv + 1024 + j * 4), ug = lds_f4(bg + 1024 + j * 4);
+                  b.x = fmaf(lb, uv.x, b.x); b.y = fmaf(lb, uv.y, b.y); b.z = fmaf(lb, uv.z, b.z); b.w = fmaf(lb, uv.w, b.w);
+                  c.x = fmaf(lb, ug.x, c.x); c.y = fmaf(lb, ug.y, c.y); c.z = fmaf(lb, ug.z, c.z); c.w = fmaf(lb, ug.w, c.w);
+#pragma unroll
+                  for (int t = 0; t < 4; ++t) {
+                    v[j + t] = __float_as_uint(__uint_as_float(v[j + t]) * la);
+                    g[j + t] = __float_as_uint(__uint_as_float(g[j + t]) * la);
+                  }
+                }
                 f[j] = (__uint_as_float(v[j]) + b.x) * gelu_sig(__uint_as_float(g[j]) + c.x);
                 f[j + 1] = (__uint_as_float(v[j + 1]) + b.y) * gelu_sig(__uint_as_float(g[j + 1]) + c.y);
                 f[j + 2] = (__uint_as_float(v[j + 2]) + b.z) * gelu_sig(__uint_as_float(g[j + 2]) + c.z);
@@ -335,7 +382,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             if (s + 1 < nsub) load_res(s + 1);
           }
           if (!GEGLU) {
-            if (has_bias) {
+            if (LN) {                         // rstd * acc + (-mean rstd) * u + c in two FMAs per element
+              const uint32_t up = u_stage + s * EPI_COLS * 4, bp = bias_stage + s * EPI_COLS * 4;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 u4 = lds_f4(up + j * 4), b = lds_f4(bp + j * 4);
+                f[j] = fmaf(la, f[j], fmaf(lb, u4.x, b.x)); f[j + 1] = fmaf(la, f[j + 1], fmaf(lb, u4.y, b.y));
+                f[j + 2] = fmaf(la, f[j + 2], fmaf(lb, u4.z, b.z)); f[j + 3] = fmaf(la, f[j + 3], fmaf(lb, u4.w, b.w));
+              }
+            } else if (stage_bias) {
               const uint32_t bp = bias_stage + s * EPI_COLS * 4;
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
@@ -343,7 +398,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
               }
             }
-            if (HAS_RV && rv) {
+            if (HAS_RV && rv && !rv_uniform) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
                 const float4 b = __ldg(reinterpret_cast<const float4*>(rv + s * EPI_COLS + j));
@@ -465,8 +520,10 @@ int launch(cudaStream_t st, const GemmParams& p) {
 
 template <int BN, bool PAIR>
 int launch_linear(cudaStream_t st, const GemmParams& p) {
-  const int epi = (p.residual ? EPI_F_RES : 0) | (p.rowvec ? EPI_F_RV : 0);
+  const int epi = (p.residual ? EPI_F_RES : 0) | (p.rowvec ? EPI_F_RV : 0) | (p.ln_stats ? EPI_F_LN : 0);
   switch (epi) {
+    case EPI_F_LN: return launch<BN, EPI_F_LN, PAIR>(st, p);
+    case EPI_F_LN | EPI_F_RV: return launch<BN, EPI_F_LN | EPI_F_RV, PAIR>(st, p);
     case 0: return launch<BN, 0, PAIR>(st, p);
     case EPI_F_RES: return launch<BN, EPI_F_RES, PAIR>(st, p);
     case EPI_F_RV: return launch<BN, EPI_F_RV, PAIR>(st, p);
@@ -521,6 +578,10 @@ int gemm_tc(cudaStream_t st, const GemmArgs& a) {
   p.rowvec = a.rowvec;
   p.ldrv = a.ldrv > 0 ? a.ldrv : a.N;
   p.pix_per_batch = a.pix_per_batch > 0 ? a.pix_per_batch : 1;
+  p.rv_mod = a.rv_mod;
+  p.ln_stats = reinterpret_cast<const float2*>(a.ln_stats);
+  p.ln_u = a.ln_u;
+  if (a.ln_stats) VS_REQUIRE(a.ln_u != nullptr && a.bias != nullptr && a.residual == nullptr, "gemm_tc: folded LayerNorm needs u and c vectors and no residual");
   p.residual = a.residual;
   p.ldr = a.ldr;
   p.out = a.out;
@@ -593,8 +654,12 @@ int gemm_tc(cudaStream_t st, const GemmArgs& a) {
              (!a.bias || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0) &&
              (!a.rowvec || ((reinterpret_cast<uintptr_t>(a.rowvec) & 15) == 0 && p.ldrv % 4 == 0));
   if (!p.staged) VS_REQUIRE(a.mode == EPI_LINEAR, "gemm_tc: GEGLU output needs 32-column aligned, 16-byte strided rows");
+  if (a.ln_stats) VS_REQUIRE(p.staged && (reinterpret_cast<uintptr_t>(a.ln_u) & 15) == 0, "gemm_tc: folded LayerNorm needs the staged epilogue");
   ProfScope prof(st, a.taps == 9 ? PC_CONV : PC_GEMM, 2.0 * a.M * (double)a.N * Ktot, 1, a.M, a.N, Ktot);
-  if (a.mode == EPI_GEGLU) return pair ? launch<256, EPI_F_GEGLU, true>(st, p) : launch<256, EPI_F_GEGLU, false>(st, p);
+  if (a.mode == EPI_GEGLU) {
+    if (p.ln_stats) return pair ? launch<256, EPI_F_GEGLU | EPI_F_LN, true>(st, p) : launch<256, EPI_F_GEGLU | EPI_F_LN, false>(st, p);
+    return pair ? launch<256, EPI_F_GEGLU, true>(st, p) : launch<256, EPI_F_GEGLU, false>(st, p);
+  }
   if (pair) {
     switch (bn) {
       case 128: return launch_linear<128, true>(st, p);

@@ -26,6 +26,10 @@ struct GemmArgs {
   const float* rowvec = nullptr;              // [M / pix_per_batch, ldrv] fp32 (time-embedding add)
   int ldrv = 0;                               // row stride of rowvec (0 = N)
   int pix_per_batch = 1;
+  int rv_mod = 0;                             // > 0: row-vector index = (pix / pix_per_batch) % rv_mod (per-frame vectors)
+  // LayerNorm folded into this GEMM (A = the LayerNorm's RAW input, Bw = W * gamma, bias = beta W^T + b; see ln_fold):
+  const float* ln_stats = nullptr;            // [M, 2] fp32 per-row (rstd, -mean * rstd) from ln_rowstats
+  const float* ln_u = nullptr;                // [N] fp32 row sums of Bw
   const __half* residual = nullptr; int ldr = 0;
   __half* out = nullptr; int ldc = 0;
   int mode = EPI_LINEAR;
@@ -46,6 +50,13 @@ int groupnorm_apply(cudaStream_t st, const __half* x1, int c1, const __half* x2,
 // LayerNorm over the last dim of [rows, C]; optional temporal positional encoding pe[(row / hw) % F, :] added after.
 int layernorm(cudaStream_t st, const __half* x, int rows, int C, const float* gamma, const float* beta,
               const float* pe, int hw, int F, __half* out);
+
+// LayerNorm folded into the GEMM that consumes it (GemmArgs::ln_stats / ln_u): per-row statistics of the raw input and
+// the one-time transformation of the weights; C must be 320 / 640 / 1280 (ln_fold_supported).
+bool ln_fold_supported(int C);
+int ln_rowstats(cudaStream_t st, const __half* x, long long rows, int C, float* stats);   // stats [rows, 2] = (rstd, -mean rstd)
+int ln_fold(cudaStream_t st, const __half* w, int N, int K, const float* gamma, const float* beta, const float* bias,
+            const float* pe, int pe_len, __half* wf, float* u, float* c, float* cpe);   // see pointwise.cu
 
 // ---- attention -----------------------------------------------------------------------------------------------
 // Spatial self/cross attention, all heads: q[b, nq, h, d] (row stride ldq), k/v[b, nk, h, d] (ldk/ldv) -> o (ldo).

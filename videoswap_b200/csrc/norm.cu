@@ -298,7 +298,73 @@ __global__ void __launch_bounds__(256) ln5_kernel(const __half* __restrict__ x, 
   }
 }
 
+// Row statistics only, for a LayerNorm that is folded into the following GEMM (gemm.cu, EPI_F_LN): reads the row once,
+// writes (rstd, -mean * rstd); the normalised tensor is never materialised.  Same lane layout as ln5_kernel.
+template <int LPR>
+__global__ void __launch_bounds__(256) ln_stats_kernel(const __half* __restrict__ x, long long rows, float2* __restrict__ stats) {
+  constexpr int C = LPR * 40, RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane % LPR, rw = lane / LPR;
+  pdl_trigger();
+  pdl_wait();
+  const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r0 = warp_global * (2 * RPW); r0 < rows; r0 += nwarps * (2 * RPW)) {
+    uint4 v[2][5];
+    long long row[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      row[u] = r0 + u * RPW + rw;
+      const __half* xr = x + (row[u] < rows ? row[u] : 0) * C;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) v[u][i] = *reinterpret_cast<const uint4*>(xr + (sub + i * LPR) * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const __half2* h = reinterpret_cast<const __half2*>(&v[u][i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 f = __half22float2(h[j]); s += f.x + f.y; }
+      }
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s * (1.f / C);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const __half2* h = reinterpret_cast<const __half2*>(&v[u][i]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h[j]);
+          q += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+        }
+      }
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = rsqrtf(q * (1.f / C) + 1e-5f);
+      if (sub == 0 && row[u] < rows) stats[row[u]] = make_float2(rstd, -mean * rstd);
+    }
+  }
+}
+
 }  // namespace
+
+bool ln_fold_supported(int C) { return C == 320 || C == 640 || C == 1280; }
+
+int ln_rowstats(cudaStream_t st, const __half* x, long long rows, int C, float* stats) {
+  VS_REQUIRE(ln_fold_supported(C), "ln_rowstats: unsupported C=%d", C);
+  const int lpr = C / 40, rpw = 32 / lpr;
+  long long need = (rows + rpw * 8 * 4 - 1) / (rpw * 8 * 4);
+  if (need < 1) need = 1;
+  const long long cap = (long long)num_sms() * 8;
+  const int grid = (int)(need < cap ? need : cap);
+  ProfScope prof(st, PC_LAYERNORM, 2.0 * rows * (double)C, 1, rows, C, 2);
+  float2* s2 = reinterpret_cast<float2*>(stats);
+  if (lpr == 8) return launch_pdl(ln_stats_kernel<8>, dim3(grid), dim3(256), 0, st, 1, x, rows, s2);
+  if (lpr == 16) return launch_pdl(ln_stats_kernel<16>, dim3(grid), dim3(256), 0, st, 1, x, rows, s2);
+  return launch_pdl(ln_stats_kernel<32>, dim3(grid), dim3(256), 0, st, 1, x, rows, s2);
+}
 
 int groupnorm_stats(cudaStream_t st, const __half* x1, int c1, const __half* x2, int c2, int nimg, int hw,
                     int imgs_per_set, int groups, float* sums, bool zero_first) {

@@ -300,6 +300,55 @@ __global__ void f16_to_f32_kernel(const __half* __restrict__ x, size_t n, float*
     out[i] = __half2float(x[i]);
 }
 
+// Folds a LayerNorm (gamma, beta, optional additive positional table pe [pe_len, K]) into the linear layer W [N, K] that
+// consumes its output (one block per output row n):
+//   wf[n,k] = fp16(W[n,k] gamma[k]);  u[n] = sum_k float(wf[n,k]);  c[n] = sum_k beta[k] W[n,k] + bias[n];
+//   cpe[f,n] = sum_k pe[f,k] W[n,k].        (u is summed over the ROUNDED wf so that rstd (x wf^T - mean u) is exact.)
+constexpr int kMaxPe = 32;
+__global__ void __launch_bounds__(128) ln_fold_kernel(const __half* __restrict__ w, int N, int K, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, const float* __restrict__ bias,
+                                                      const float* __restrict__ pe, int pe_len, __half* __restrict__ wf,
+                                                      float* __restrict__ u, float* __restrict__ c, float* __restrict__ cpe) {
+  const int n = blockIdx.x;
+  float su = 0.f, sc = 0.f, sp[kMaxPe];
+#pragma unroll
+  for (int f = 0; f < kMaxPe; ++f) sp[f] = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float wv = __half2float(w[(size_t)n * K + k]);
+    const __half r = __float2half_rn(wv * gamma[k]);
+    wf[(size_t)n * K + k] = r;
+    su += __half2float(r);
+    sc = fmaf(beta[k], wv, sc);
+    if (pe) {
+#pragma unroll
+      for (int f = 0; f < kMaxPe; ++f)
+        if (f < pe_len) sp[f] = fmaf(pe[(size_t)f * K + k], wv, sp[f]);
+    }
+  }
+  __shared__ float red[4][kMaxPe + 2];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  auto wsum = [](float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  };
+  su = wsum(su); sc = wsum(sc);
+#pragma unroll
+  for (int f = 0; f < kMaxPe; ++f) sp[f] = wsum(sp[f]);
+  if (lane == 0) {
+    red[wid][0] = su; red[wid][1] = sc;
+#pragma unroll
+    for (int f = 0; f < kMaxPe; ++f) red[wid][2 + f] = sp[f];
+  }
+  __syncthreads();
+  if (threadIdx.x < kMaxPe + 2) {
+    const float t = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+    if (threadIdx.x == 0) u[n] = t;
+    else if (threadIdx.x == 1) c[n] = t + (bias ? bias[n] : 0.f);
+    else if (pe && (int)threadIdx.x - 2 < pe_len) cpe[(size_t)(threadIdx.x - 2) * N + n] = t;
+  }
+}
+
 inline unsigned capped(size_t n) {
   size_t b = (n + TPB - 1) / TPB;
   const size_t cap = (size_t)num_sms() * 16;
@@ -426,6 +475,15 @@ int pack_conv3x3(cudaStream_t st, const __half* w, int cout, int cin, __half* ou
 int pack_geglu(cudaStream_t st, const __half* w, const __half* b, int hidden, int K, int granule, __half* wout, float* bout) {
   VS_REQUIRE(hidden % granule == 0, "pack_geglu: hidden %% granule != 0");
   pack_geglu_kernel<<<capped((size_t)2 * hidden * K), TPB, 0, st>>>(w, b, hidden, K, granule, wout, bout);
+  count_launch(1);
+  VS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int ln_fold(cudaStream_t st, const __half* w, int N, int K, const float* gamma, const float* beta, const float* bias,
+            const float* pe, int pe_len, __half* wf, float* u, float* c, float* cpe) {
+  VS_REQUIRE(pe_len <= kMaxPe, "ln_fold: positional table longer than %d", kMaxPe);
+  VS_REQUIRE(!pe || cpe, "ln_fold: positional table without an output");
+  ln_fold_kernel<<<N, 128, 0, st>>>(w, N, K, gamma, beta, bias, pe, pe ? pe_len : 0, wf, u, c, cpe);
   count_launch(1);
   VS_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -119,6 +119,7 @@ static Option g_options[] = {
     {"attn_handoff", 1},   // 1: the softmax ping-pong hands the MUFU pipe over after 7 of 8 key chunks, 0: after the last
     {"gemm_pair", 1},      // CTA pairs (cta_group::2, 256-row tiles): 1 = for K >= 768, 0 = never, 2 = whenever possible
     {"gemm_stages", 0},    // smem ring depth limit (0 = all)
+    {"ln_fold", 1},        // LayerNorms folded into the GEMM that consumes them (0 = stand-alone LayerNorm kernel)
     {"pdl", 1},            // programmatic dependent launch between the hot kernels (0 = plain stream order)
 };
 int set_option(const char* name, int value) {

@@ -30,6 +30,9 @@ struct Loader {
 struct Lin { __half* w = nullptr; float* b = nullptr; int N = 0, K = 0; };
 struct Conv3 { __half* w = nullptr; float* b = nullptr; int co = 0, ci = 0; };
 struct Norm { float* g = nullptr; float* b = nullptr; int C = 0; };
+// A linear layer with the LayerNorm in front of it folded in (kernels.h ln_fold): gamma-scaled weights, row sums, offsets
+struct LnLin { __half* wf = nullptr; float* u = nullptr; float* c = nullptr; float* cpe = nullptr; };
+struct FoldJob { const __half* w; int N, K; const float* gamma; const float* beta; const float* bias; const float* pe; int pe_len; LnLin dst; };
 struct Resnet {
   Norm n1, n2; Conv3 c1, c2; Lin sc; bool has_sc = false; int cin = 0, cout = 0; int temb_off = 0;
 };
@@ -37,11 +40,13 @@ struct Transformer {
   int C = 0, layer = 0;
   Norm norm, ln1, ln2, ln3; Lin proj_in, proj_out, out1, out2, ff2;
   __half* wqkv = nullptr; __half* wq = nullptr; __half* wkv = nullptr; __half* ff1w = nullptr; float* ff1b = nullptr;
+  LnLin f_qkv, f_q, f_ff;               // ln1 -> QKV, ln2 -> to_q, ln3 -> GEGLU with the LayerNorm folded in
 };
 struct Motion {
   int C = 0;
   Norm norm, ln[2], ff_norm; Lin proj_in, proj_out, out[2], ff2;
   __half* wqkv[2] = {nullptr, nullptr}; __half* ff1w = nullptr; float* ff1b = nullptr;
+  LnLin f_qkv[2], f_ff;                 // (LN + temporal PE) -> QKV, ff_norm -> GEGLU folded
 };
 struct Layer { Resnet res; bool has_tr = false; Transformer tr; bool has_mo = false; Motion mo; };
 struct Block { std::vector<Layer> layers; bool has_sampler = false; Conv3 sampler; };
@@ -55,6 +60,7 @@ struct vs_unet {
   std::vector<void*> allocs;
   std::unordered_map<std::string, Loader> loaders;
   std::vector<std::string> names;
+  std::vector<FoldJob> folds;           // re-run after every weight load
 
   // parameters
   __half* conv_in_w = nullptr; float* conv_in_b = nullptr;
@@ -70,7 +76,7 @@ struct vs_unet {
   int wsB = 0, wsF = 0, wsH = 0, wsW = 0;
   __half *XIN, *XN, *T, *TN, *QKV, *ATT, *HH, *SC, *P0, *P1, *SCR, *KV, *RES, *OUT;
   std::vector<__half*> skip;            // 12 skip buffers
-  float *F_T, *F_TE0, *F_TE1, *F_EMB, *F_TPROJ, *F_SUMS;
+  float *F_T, *F_TE0, *F_TE1, *F_EMB, *F_TPROJ, *F_SUMS, *F_LNS;
 
   // debug taps
   bool taps_on = false;
@@ -100,6 +106,18 @@ struct vs_unet {
   Norm norm(const std::string& p, int C) { Norm n; n.C = C; n.g = f32(p + ".weight", C); n.b = f32(p + ".bias", C); return n; }
   Lin lin(const std::string& p, int N, int K, bool bias = true) {
     Lin l; l.N = N; l.K = K; l.w = f16(p + ".weight", (int64_t)N * K); if (bias) l.b = f32(p + ".bias", N); return l;
+  }
+  // LayerNorm `n` (+ positional table pe [pe_len, K]) folded into the linear layer w [N, K] (+ bias): the folded copy is
+  // re-derived from the unfolded weights after every vs_unet_load_weights (LoRA merges replace the weights).
+  LnLin fold(const __half* w, int N, int K, const Norm& n, const float* bias, const float* pe, int pe_len) {
+    LnLin f;
+    if (!ln_fold_supported(K)) return f;
+    f.wf = alloc<__half>((size_t)N * K);
+    f.u = alloc<float>(N);
+    f.c = alloc<float>(N);
+    if (pe) f.cpe = alloc<float>((size_t)pe_len * N);
+    folds.push_back(FoldJob{w, N, K, n.g, n.b, bias, pe, pe_len, f});
+    return f;
   }
   Conv3 conv3(const std::string& p, int co, int ci) {
     Conv3 c; c.co = co; c.ci = ci;
@@ -159,6 +177,9 @@ void build_transformer(vs_unet* h, Transformer& t, const std::string& p, int C, 
   build_ff(h, q + ".ff", C, t.ff1w, t.ff1b, t.ff2);
   t.ln3 = h->norm(q + ".norm3", C);
   t.proj_out = h->lin(p + ".proj_out", C, C);
+  t.f_qkv = h->fold(t.wqkv, 3 * C, C, t.ln1, nullptr, nullptr, 0);
+  t.f_q = h->fold(t.wq, C, C, t.ln2, nullptr, nullptr, 0);
+  t.f_ff = h->fold(t.ff1w, 8 * C, C, t.ln3, t.ff1b, nullptr, 0);
 }
 
 void build_motion(vs_unet* h, Motion& m, const std::string& p0, int C) {
@@ -176,6 +197,12 @@ void build_motion(vs_unet* h, Motion& m, const std::string& p0, int C) {
   build_ff(h, q + ".ff", C, m.ff1w, m.ff1b, m.ff2);
   m.ff_norm = h->norm(q + ".ff_norm", C);
   m.proj_out = h->lin(p + ".proj_out", C, C);
+  const float* pe = nullptr;            // the table depends on C only: any level with this channel count will do
+  for (int l = 0; l < 4; ++l) if (h->cfg.block_out_channels[l] == C) pe = h->pe[l];
+  if (pe && h->cfg.pe_max_len <= 32) {
+    for (int i = 0; i < 2; ++i) m.f_qkv[i] = h->fold(m.wqkv[i], 3 * C, C, m.ln[i], nullptr, pe, h->cfg.pe_max_len);
+    m.f_ff = h->fold(m.ff1w, 8 * C, C, m.ff_norm, m.ff1b, nullptr, 0);
+  }
 }
 
 int up_in_channels(const vs_unet_config& c, int i, int j, int* skip) {
@@ -206,6 +233,20 @@ extern "C" int vs_unet_create(const vs_unet_config* cfg, vs_unet** out) {
   h->cfg = *cfg;
   const int* boc = cfg->block_out_channels;
   const int temb = boc[0] * 4, ctx = cfg->cross_attention_dim, lpb = cfg->layers_per_block;
+  // temporal positional-encoding tables (closed form of motion_module.py:242-251)
+  for (int l = 0; l < 4; ++l) {
+    const int C = boc[l], L = cfg->pe_max_len;
+    std::vector<float> t((size_t)L * C);
+    for (int pos = 0; pos < L; ++pos)
+      for (int i2 = 0; i2 < C; i2 += 2) {
+        const float div = expf((float)i2 * (-logf(10000.0f) / (float)C));
+        t[(size_t)pos * C + i2] = sinf((float)pos * div);
+        if (i2 + 1 < C) t[(size_t)pos * C + i2 + 1] = cosf((float)pos * div);
+      }
+    h->pe[l] = h->alloc<float>((size_t)L * C);
+    if (!h->pe[l]) { delete h; return 1; }
+    cudaMemcpy(h->pe[l], t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice);
+  }
   h->conv_in_w = h->f16("conv_in.weight", (int64_t)boc[0] * cfg->in_channels * 9);
   h->conv_in_b = h->f32("conv_in.bias", boc[0]);
   h->te1 = h->lin("time_embedding.linear_1", temb, boc[0]);
@@ -260,20 +301,6 @@ extern "C" int vs_unet_create(const vs_unet_config* cfg, vs_unet** out) {
   h->norm_out = h->norm("conv_norm_out", boc[0]);
   h->conv_out = h->conv3("conv_out", cfg->out_channels, boc[0]);
   VS_REQUIRE(toff == tn, "internal: time_emb_proj stacking mismatch (%d vs %d)", toff, tn);
-  // temporal positional-encoding tables (closed form of motion_module.py:242-251)
-  for (int l = 0; l < 4; ++l) {
-    const int C = boc[l], L = cfg->pe_max_len;
-    std::vector<float> t((size_t)L * C);
-    for (int pos = 0; pos < L; ++pos)
-      for (int i2 = 0; i2 < C; i2 += 2) {
-        const float div = expf((float)i2 * (-logf(10000.0f) / (float)C));
-        t[(size_t)pos * C + i2] = sinf((float)pos * div);
-        if (i2 + 1 < C) t[(size_t)pos * C + i2 + 1] = cosf((float)pos * div);
-      }
-    h->pe[l] = h->alloc<float>((size_t)L * C);
-    if (!h->pe[l]) { delete h; return 1; }
-    cudaMemcpy(h->pe[l], t.data(), t.size() * sizeof(float), cudaMemcpyHostToDevice);
-  }
   for (void* p : h->allocs) if (!p) { delete h; return 1; }
   VS_CHECK_CUDA(cudaGetLastError());
   *out = h;
@@ -309,6 +336,8 @@ extern "C" int vs_unet_load_weights(vs_unet* h, void* stream, int n, const char*
     }
     if (e) return e;
   }
+  for (const FoldJob& f : h->folds)
+    if (int e = ln_fold(st, f.w, f.N, f.K, f.gamma, f.beta, f.bias, f.pe, f.pe_len, f.dst.wf, f.dst.u, f.dst.c, f.dst.cpe)) return e;
   return 0;
 }
 
@@ -379,6 +408,19 @@ int resnet(Ctx& c, const Resnet& r, const __half* in1, int C1, const __half* in2
   return 0;
 }
 
+// LayerNorm + linear with the norm folded into the GEMM: row statistics of the raw input, then ONE GEMM on the raw input
+// (no normalised tensor is written or read).  pe_frames > 0: per-frame positional offsets (temporal LayerNorm + PE).
+bool use_fold(const LnLin& f) { return f.wf != nullptr && get_option("ln_fold") != 0; }
+int ln_linear(Ctx& c, const __half* x, int M, int C, const LnLin& f, int N, int mode, int hw, int pe_frames, __half* out, int ldc) {
+  vs_unet* h = c.h;
+  RUN(ln_rowstats(c.st, x, M, C, h->F_LNS));
+  GemmArgs g;
+  g.A = x; g.K1 = C; g.lda1 = C; g.Bw = f.wf; g.M = M; g.N = N; g.bias = f.c; g.ln_stats = h->F_LNS; g.ln_u = f.u;
+  g.out = out; g.ldc = ldc; g.mode = mode;
+  if (pe_frames > 0) { g.rowvec = f.cpe; g.ldrv = N; g.pix_per_batch = hw; g.rv_mod = pe_frames; }
+  return gemm_tc(c.st, g);
+}
+
 int geglu_ff(Ctx& c, const __half* tn, int M, int C, const __half* w1, const float* b1, const Lin& ff2, __half* t) {
   vs_unet* h = c.h;
   GemmArgs g;
@@ -395,14 +437,22 @@ int transformer(Ctx& c, const Transformer& t, __half* x) {
   RUN(groupnorm_apply(c.st, x, C, nullptr, 0, c.NI, hw, 1, h->cfg.norm_num_groups, sums, 1e-6f, t.norm.g, t.norm.b, false, h->XN));
   RUN(linear(c, h->XN, M, t.proj_in, nullptr, h->T));
   // self-attention
-  RUN(layernorm(c.st, h->T, M, C, t.ln1.g, t.ln1.b, nullptr, 1, 1, h->TN));
-  { GemmArgs g; g.A = h->TN; g.K1 = C; g.lda1 = C; g.Bw = t.wqkv; g.M = M; g.N = 3 * C; g.out = h->QKV; g.ldc = 3 * C; RUN(gemm_tc(c.st, g)); }
+  if (use_fold(t.f_qkv)) {
+    RUN(ln_linear(c, h->T, M, C, t.f_qkv, 3 * C, EPI_LINEAR, hw, 0, h->QKV, 3 * C));
+  } else {
+    RUN(layernorm(c.st, h->T, M, C, t.ln1.g, t.ln1.b, nullptr, 1, 1, h->TN));
+    GemmArgs g; g.A = h->TN; g.K1 = C; g.lda1 = C; g.Bw = t.wqkv; g.M = M; g.N = 3 * C; g.out = h->QKV; g.ldc = 3 * C; RUN(gemm_tc(c.st, g));
+  }
   RUN(attention(c.st, h->QKV, 3 * C, h->QKV + C, 3 * C, h->QKV + 2 * C, 3 * C, h->ATT, C, c.NI, hw, hw, heads, d,
                 (long long)hw * 3 * C, (long long)hw * 3 * C, (long long)hw * C, 1));
   RUN(linear(c, h->ATT, M, t.out1, h->T, h->T));
   // cross-attention to the (ED-LoRA layer-selected) text embeddings; K/V were projected once per (batch, layer)
-  RUN(layernorm(c.st, h->T, M, C, t.ln2.g, t.ln2.b, nullptr, 1, 1, h->TN));
-  { GemmArgs g; g.A = h->TN; g.K1 = C; g.lda1 = C; g.Bw = t.wq; g.M = M; g.N = C; g.out = h->QKV; g.ldc = C; RUN(gemm_tc(c.st, g)); }
+  if (use_fold(t.f_q)) {
+    RUN(ln_linear(c, h->T, M, C, t.f_q, C, EPI_LINEAR, hw, 0, h->QKV, C));
+  } else {
+    RUN(layernorm(c.st, h->T, M, C, t.ln2.g, t.ln2.b, nullptr, 1, 1, h->TN));
+    GemmArgs g; g.A = h->TN; g.K1 = C; g.lda1 = C; g.Bw = t.wq; g.M = M; g.N = C; g.out = h->QKV; g.ldc = C; RUN(gemm_tc(c.st, g));
+  }
   {
     const int nk = c.ehs_tokens;
     const int ctx = h->cfg.cross_attention_dim;
@@ -420,8 +470,13 @@ int transformer(Ctx& c, const Transformer& t, __half* x) {
   }
   RUN(linear(c, h->ATT, M, t.out2, h->T, h->T));
   // feed-forward
-  RUN(layernorm(c.st, h->T, M, C, t.ln3.g, t.ln3.b, nullptr, 1, 1, h->TN));
-  RUN(geglu_ff(c, h->TN, M, C, t.ff1w, t.ff1b, t.ff2, h->T));
+  if (use_fold(t.f_ff)) {
+    RUN(ln_linear(c, h->T, M, C, t.f_ff, 8 * C, EPI_GEGLU, hw, 0, h->HH, 4 * C));
+    RUN(linear(c, h->HH, M, t.ff2, h->T, h->T));
+  } else {
+    RUN(layernorm(c.st, h->T, M, C, t.ln3.g, t.ln3.b, nullptr, 1, 1, h->TN));
+    RUN(geglu_ff(c, h->TN, M, C, t.ff1w, t.ff1b, t.ff2, h->T));
+  }
   RUN(linear(c, h->T, M, t.proj_out, x, x));
   return 0;
 }
@@ -435,13 +490,22 @@ int motion(Ctx& c, const Motion& m, int level, __half* x) {
   RUN(groupnorm_apply(c.st, x, C, nullptr, 0, c.NI, hw, 1, 32, sums, 1e-6f, m.norm.g, m.norm.b, false, h->XN));
   RUN(linear(c, h->XN, M, m.proj_in, nullptr, h->T));
   for (int i = 0; i < 2; ++i) {
-    RUN(layernorm(c.st, h->T, M, C, m.ln[i].g, m.ln[i].b, h->pe[level], hw, c.F, h->TN));
-    { GemmArgs g; g.A = h->TN; g.K1 = C; g.lda1 = C; g.Bw = m.wqkv[i]; g.M = M; g.N = 3 * C; g.out = h->QKV; g.ldc = 3 * C; RUN(gemm_tc(c.st, g)); }
+    if (use_fold(m.f_qkv[i])) {
+      RUN(ln_linear(c, h->T, M, C, m.f_qkv[i], 3 * C, EPI_LINEAR, hw, c.F, h->QKV, 3 * C));
+    } else {
+      RUN(layernorm(c.st, h->T, M, C, m.ln[i].g, m.ln[i].b, h->pe[level], hw, c.F, h->TN));
+      GemmArgs g; g.A = h->TN; g.K1 = C; g.lda1 = C; g.Bw = m.wqkv[i]; g.M = M; g.N = 3 * C; g.out = h->QKV; g.ldc = 3 * C; RUN(gemm_tc(c.st, g));
+    }
     RUN(temporal_attention(c.st, h->QKV, h->ATT, c.B, c.F, hw, C, h->cfg.motion_num_heads));
     RUN(linear(c, h->ATT, M, m.out[i], h->T, h->T));
   }
-  RUN(layernorm(c.st, h->T, M, C, m.ff_norm.g, m.ff_norm.b, nullptr, 1, 1, h->TN));
-  RUN(geglu_ff(c, h->TN, M, C, m.ff1w, m.ff1b, m.ff2, h->T));
+  if (use_fold(m.f_ff)) {
+    RUN(ln_linear(c, h->T, M, C, m.f_ff, 8 * C, EPI_GEGLU, hw, 0, h->HH, 4 * C));
+    RUN(linear(c, h->HH, M, m.ff2, h->T, h->T));
+  } else {
+    RUN(layernorm(c.st, h->T, M, C, m.ff_norm.g, m.ff_norm.b, nullptr, 1, 1, h->TN));
+    RUN(geglu_ff(c, h->TN, M, C, m.ff1w, m.ff1b, m.ff2, h->T));
+  }
   RUN(linear(c, h->T, M, m.proj_out, x, x));
   return 0;
 }
@@ -487,7 +551,8 @@ int ensure_workspace(vs_unet* h, int B, int F, int H, int W) {
   for (auto& r : req) total += align_up(r.second * 2);
   const int temb = boc[0] * 4;
   const size_t fl = align_up(4 * 64) + align_up((size_t)B * boc[0] * 4) + 2 * align_up((size_t)B * temb * 4) +
-                    align_up((size_t)B * h->tproj_n * 4) + align_up((size_t)kMaxGroupNorms * NI * 64 * 4);
+                    align_up((size_t)B * h->tproj_n * 4) + align_up((size_t)kMaxGroupNorms * NI * 64 * 4) +
+                    align_up(NI * hw[0] * 2 * 4);
   total += fl;
   VS_CHECK_CUDA(cudaMalloc(&h->ws, total));
   h->ws_bytes = total;
@@ -498,7 +563,8 @@ int ensure_workspace(vs_unet* h, int B, int F, int H, int W) {
   h->F_TE1 = (float*)p; p += align_up((size_t)B * temb * 4);
   h->F_EMB = (float*)p; p += align_up((size_t)B * temb * 4);
   h->F_TPROJ = (float*)p; p += align_up((size_t)B * h->tproj_n * 4);
-  h->F_SUMS = (float*)p;
+  h->F_SUMS = (float*)p; p += align_up((size_t)kMaxGroupNorms * NI * 64 * 4);
+  h->F_LNS = (float*)p;
   h->wsB = B; h->wsF = F; h->wsH = H; h->wsW = W;
   return 0;
 }

@@ -117,6 +117,24 @@ def layernorm(x, gamma, beta, pe=None, hw=1, F=1):
     return out
 
 
+def ln_linear(x, W, gamma, beta, bias=None, pe=None, hw=1, frames=1, mode=EPI_LINEAR):
+    """LayerNorm(x)(+pe[(row // hw) % frames]) @ W^T + bias with the norm folded into the GEMM (C in 320/640/1280)."""
+    _chk16(x, W)
+    _chk32(gamma, beta, bias, pe)
+    M, Cc = x.shape
+    N = W.shape[0]
+    dev = x.device
+    wf = torch.empty_like(W)
+    u = torch.empty((N,), dtype=torch.float32, device=dev)
+    c = torch.empty((N,), dtype=torch.float32, device=dev)
+    cpe = torch.empty((pe.shape[0], N), dtype=torch.float32, device=dev) if pe is not None else None
+    stats = torch.empty((M, 2), dtype=torch.float32, device=dev)
+    out = torch.empty((M, N // 2 if mode == EPI_GEGLU else N), dtype=torch.float16, device=dev)
+    _lib.call("vs_ln_linear", _stream(), _p(x), M, Cc, _p(W), _p(bias), N, _p(gamma), _p(beta), _p(pe),
+              0 if pe is None else pe.shape[0], hw, frames, mode, _p(wf), _p(u), _p(c), _p(cpe), _p(stats), _p(out))
+    return out
+
+
 def attention(q, k, v, heads, kv_div=1):
     """q [B, Nq, h*d], k/v [Bk, Nk, h*d] (may be strided views with contiguous last dim) -> [B, Nq, h*d]."""
     B, nq, Cc = q.shape
