@@ -100,7 +100,9 @@ def cpu_oracle_sample(frames=2, latent=LATENT, reps_budget_s=15.0, warmup=1, max
     import torch
     from oracle import unet3d_oracle as O
     from videoswap_b200 import UNetConfig, seeded_state_dict, unet_param_shapes
-    torch.set_num_threads(os.cpu_count() or 1)
+    # measured on the 128-core GPU box (tools/cpu_thread_sweep.py): 16 threads 5.8 s, 32: 6.0 s, 64: 8.9 s, 128: 138 s per
+    # sample -- the sample's tensors are too small for more threads, so the baseline uses the fastest setting
+    torch.set_num_threads(min(os.cpu_count() or 1, 16))
     sd = seeded_state_dict(unet_param_shapes(UNetConfig()), seed=0)
     x = torch.randn(1, 4, frames, latent, latent)
     ehs = torch.randn(1, 16, 77, 768)
@@ -125,7 +127,8 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     import torch
-    times, frac = cpu_oracle_sample(frames=2, reps_budget_s=1e9, warmup=min(args.warmup, 1), max_reps=max(args.steps, 1))
+    # bounded: at most `steps` samples and ~90 s of CPU time in total, so the arm always ends within a few minutes
+    times, frac = cpu_oracle_sample(frames=2, reps_budget_s=90.0, warmup=min(args.warmup, 1), max_reps=max(args.steps, 1))
     t = sorted(times)[len(times) // 2]
     v = frac / t
     sample = "oracle UNet forward fp32 on [1,4,2,64,64] + ED-LoRA embeds = 1/16 of a CFG step; value = (1/16)/median time"
