@@ -93,3 +93,26 @@ def test_registry_names():
     assert V.build_model("AnimateDiffUNet3DModel") is V.AnimateDiffUNet3DModel
     assert V.build_model("UNet3DConditionModel") is V.AnimateDiffUNet3DModel
     assert V.build_pipeline("TuneAVideoPipeline") is V.VideoSwapPipeline
+
+
+def test_layernorm_folding_algebra():
+    """LN(x)(+pe) W^T + b == rstd (x W'^T) - rstd mean u + c (+ cpe): the identity behind ln_fold / EPI_F_LN (gemm.cu)."""
+    import torch
+    g = torch.Generator().manual_seed(5)
+    rows, C, N, F, hw = 60, 320, 96, 3, 4
+    x = torch.randn(rows, C, generator=g, dtype=torch.float64) * 2 + 0.7
+    gamma = 1 + 0.1 * torch.randn(C, generator=g, dtype=torch.float64)
+    beta = 0.1 * torch.randn(C, generator=g, dtype=torch.float64)
+    W = torch.randn(N, C, generator=g, dtype=torch.float64) / C ** 0.5
+    b = torch.randn(N, generator=g, dtype=torch.float64)
+    pe = torch.randn(F, C, generator=g, dtype=torch.float64)
+    frame = (torch.arange(rows) // hw) % F
+    ref = (torch.nn.functional.layer_norm(x, (C,), gamma, beta, 1e-5) + pe[frame]) @ W.t() + b
+    mean = x.mean(1, keepdim=True)
+    rstd = (x.var(1, unbiased=False, keepdim=True) + 1e-5).rsqrt()
+    Wf = W * gamma                       # folded weights
+    u = Wf.sum(1)                        # row sums
+    c = W @ beta + b                     # constant offset
+    cpe = pe @ W.t()                     # per-frame positional offsets
+    out = rstd * (x @ Wf.t()) + (-mean * rstd) * u + c + cpe[frame]
+    assert torch.allclose(out, ref, atol=1e-9)

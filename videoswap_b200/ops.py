@@ -62,7 +62,7 @@ def pack_conv3x3(w):
 
 
 def pack_geglu(w, b):
-    """FeedForward.net.0.proj [8C, C] / [8C] -> value/gate interleaved in 80-row granules (+ fp32 bias)."""
+    """FeedForward.net.0.proj [8C, C] / [8C] -> value/gate interleaved in GEGLU_GRANULE-row (128) granules (+ fp32 bias)."""
     _chk16(w, b)
     hidden, K = w.shape[0] // 2, w.shape[1]
     wout = torch.empty_like(w)
