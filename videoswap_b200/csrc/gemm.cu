@@ -9,14 +9,16 @@
 //
 // What bounds it (ncu):
 //  * main loop: the L2 -> SM operand feed.  A 128 x 160 tile needs 36 KB per k-block (320 tensor cycles); every shape
-//    measured -- GEMM, conv, any K -- plateaus where that feed is ~55-60 B/clk/SM, i.e. ~55% of the tensor pipe.  Wider
+//    measured -- GEMM, conv, any K -- plateaus where that feed is ~45-60 B/clk/SM, i.e. ~55% of the tensor pipe.  Wider
 //    tiles need fewer bytes per flop, so BN is picked per shape by a wave-quantisation x bytes-per-k-block model
-//    (BN = 256: 48 KB per 512 tensor cycles).
+//    (BN = 256: 48 KB per 512 tensor cycles) and, for K >= 768, two CTAs of a cluster share one 256-row tile with
+//    cta_group::2 MMAs (PAIR: each CTA loads half of the weight tile, 32 KB per 512 tensor cycles).
 //  * K <= 640: the epilogue.  With two epilogue warps per scheduler it is bound by the serial instruction stream of each
 //    warp, so the epilogue is specialised at compile time (GEGLU / residual / row vector), epilogue group g owns
 //    accumulator stage g (whole tiles: the per-tile set-up is paid once), and its body is kept small.
 //
-// Epilogue: TMEM -> registers (thread = output row) -> fused bias / time-embedding row vector / GEGLU -> fp16 -> warp-
+// Epilogue: TMEM -> registers (thread = output row) -> [folded LayerNorm: rstd * acc - rstd * mean * u] + bias (+ warp-
+// uniform time-embedding / positional row vector; both come from a per-warp shared-memory slice) / GEGLU -> fp16 -> warp-
 // private swizzled shared-memory transpose -> (+ fp16 residual, loaded coalesced one sub-tile ahead) -> coalesced 16-byte
 // global stores.  Tiny-N outputs (conv_out, N = 4) keep a direct-store path.
 //
