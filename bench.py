@@ -152,6 +152,9 @@ def main():
     ap.add_argument("--frames", type=int, default=FRAMES)
     ap.add_argument("--latent-h", type=int, default=LATENT, help="latent height (extra configs, e.g. 56 for 448x768 video)")
     ap.add_argument("--latent-w", type=int, default=LATENT, help="latent width (e.g. 96)")
+    ap.add_argument("--mode", default="replicas", choices=["replicas", "cfg-split"],
+                    help="multi-GPU scheme: independent videos per rank (weak scaling, default) or ONE video with the "
+                         "unconditional / conditional halves of the CFG batch on two ranks (strong scaling, --gpus 2)")
     ap.add_argument("--option", action="append", default=[], help="kernel A/B switch name=value (vs_set_option)")
     ap.add_argument("--tag", default="", help="suffix of the per-shape profile CSV")
     args = ap.parse_args()
@@ -172,6 +175,12 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     W = max(args.warmup, 3)
     K = args.steps
+    cfg_split = args.mode == "cfg-split"
+    if cfg_split:
+        assert world == 2, "--mode cfg-split needs exactly two ranks"
+        args.no_graph = True                        # the all-gather of the two noise predictions is not captured
+    cfg_group = dist.group.WORLD if cfg_split else None
+    seed_rank = 0 if cfg_split else rank           # both ranks work on the SAME video
     Fr = args.frames
 
     model = AnimateDiffUNet3DModel(init="empty")
@@ -179,7 +188,7 @@ def main():
     pipe = VideoSwapPipeline(model, DDIMScheduler())
     pipe.scheduler.set_timesteps(50)
     ts = pipe.scheduler.timesteps
-    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    g = torch.Generator(device=dev).manual_seed(100 + seed_rank)
     LH, LW = args.latent_h, args.latent_w
     lat0 = torch.randn((1, 4, Fr, LH, LW), device=dev, generator=g).half()
     embeds = torch.randn((2, 16, 77, 768), device=dev, generator=g).half()
@@ -187,7 +196,7 @@ def main():
     residuals = [(0.1 * torch.randn((2 * Fr, c, LH >> l, LW >> l), device=dev, generator=g)).half() for l, c in enumerate(boc)]
 
     def step(lat, i):
-        return pipe.step(lat, ts[i % len(ts)], embeds, 7.5, list(residuals))
+        return pipe.step(lat, ts[i % len(ts)], embeds, 7.5, list(residuals), cfg_group=cfg_group)
 
     lib = _lib.lib()
     for opt in args.option:
@@ -274,7 +283,7 @@ def main():
         if gstep is not None:
             out = gstep(d_lat, ts[i % len(ts)])
         else:
-            out = pipe.step(d_lat, ts[i % len(ts)], d_emb, 7.5, list(residuals))
+            out = pipe.step(d_lat, ts[i % len(ts)], d_emb, 7.5, list(residuals), cfg_group=cfg_group)
         h_out.copy_(out, non_blocking=True)
         torch.cuda.current_stream().synchronize()      # the caller reads the result on the host every step
         h_lat.copy_(h_out)
@@ -298,8 +307,9 @@ def main():
 
     if rank == 0:
         pk = peaks()
-        value = world * K / (ms / 1e3)
-        e2e = world * K / (ms_e2e / 1e3)
+        jobs = 1 if cfg_split else world            # videos denoised concurrently
+        value = jobs * K / (ms / 1e3)
+        e2e = jobs * K / (ms_e2e / 1e3)
         tensor_cats = ["gemm", "conv3x3", "attention"]
         # dominant kernel: gemm_tc_kernel -- one template serves the GEMMs and the implicit-GEMM 3x3 convs, so its launches
         # of both categories are pooled: achieved = algorithmic FLOPs per launch / average launch duration
@@ -333,10 +343,11 @@ def main():
                               "frac_of_peak": round(rate / 1e9 / pk["gbs"], 3), "launches": p_["launches_per_step"]}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if cfg_split else "weak", "vs_baseline": None, "dtype": "f16",
             "data": "synthetic",
             "config": {"workload": f"{Fr}-frame {8 * LH}x{8 * LW} (latent [1,4,{Fr},{LH},{LW}]), CFG 7.5 (UNet batch 2), ED-LoRA embeds "
-                                   f"[2,16,77,768], adapter residuals active, DDIM step; one video per GPU",
+                                   f"[2,16,77,768], adapter residuals active, DDIM step; " + ("ONE video, CFG halves split over 2 GPUs, one all-gather of eps per step" if cfg_split else "one video per GPU"),
+                       "parallelism": "cfg2" if cfg_split else f"replicas x{world}",
                        "timing": "CUDA events; working set (2.55 GB weights + activations) >> 126 MB L2, no flush needed; "
                                  "`value`/`e2e` replay the step as a CUDA graph, the per-kernel profile comes from an eager pass "
                                  "of the same K steps with per-launch events",
