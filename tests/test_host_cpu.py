@@ -116,3 +116,35 @@ def test_layernorm_folding_algebra():
     cpe = pe @ W.t()                     # per-frame positional offsets
     out = rstd * (x @ Wf.t()) + (-mean * rstd) * u + c + cpe[frame]
     assert torch.allclose(out, ref, atol=1e-9)
+
+
+def test_from_pretrained_2d_contract(tmp_path):
+    """The reference builds the model with from_pretrained_2d(path, subfolder='unet', unet_additional_kwargs=...) from a
+    2-D SD checkpoint (unet.py:483-523, test.py:52-58): config.json keys it does not know are ignored, the 2-D weights
+    load with strict=False and the motion-module parameters are the missing keys."""
+    import json
+    import torch
+    cfg2d = {"_class_name": "UNet2DConditionModel", "_diffusers_version": "0.6.0", "act_fn": "silu", "attention_head_dim": 8,
+             "block_out_channels": [320, 640, 1280, 1280], "center_input_sample": False, "cross_attention_dim": 768,
+             "down_block_types": ["CrossAttnDownBlock2D"] * 3 + ["DownBlock2D"], "downsample_padding": 1,
+             "flip_sin_to_cos": True, "freq_shift": 0, "in_channels": 4, "layers_per_block": 2, "mid_block_scale_factor": 1,
+             "norm_eps": 1e-05, "norm_num_groups": 32, "out_channels": 4, "sample_size": 64,
+             "up_block_types": ["UpBlock2D"] + ["CrossAttnUpBlock2D"] * 3}
+    d = tmp_path / "sd" / "unet"
+    d.mkdir(parents=True)
+    (d / "config.json").write_text(json.dumps(cfg2d))
+    shapes = V.unet_param_shapes(V.UNetConfig())
+    # a PARTIAL 2-D checkpoint (biases / norm parameters only: no 3 GB file); strict=False must accept it
+    ckpt = {k: torch.zeros(v) for k, v in shapes.items() if "motion_modules" not in k and len(v) == 1}
+    ckpt["conv_in.bias"] = torch.full((320,), 0.25)
+    torch.save(ckpt, d / "diffusion_pytorch_model.bin")
+    kw = {"use_motion_module": True, "motion_module_type": "Vanilla",
+          "motion_module_kwargs": {"num_attention_heads": 8, "num_transformer_block": 1,
+                                   "attention_block_types": ["Temporal_Self", "Temporal_Self"],
+                                   "temporal_position_encoding": True, "temporal_position_encoding_max_len": 24}}
+    m = V.AnimateDiffUNet3DModel.from_pretrained_2d(str(tmp_path / "sd"), subfolder="unet", unet_additional_kwargs=kw)
+    assert isinstance(m, V.AnimateDiffUNet3DModel)
+    assert torch.allclose(m.conv_in.bias.float(), torch.full((320,), 0.25))            # loaded
+    assert sum(1 for k in m.state_dict() if "motion_modules" in k) == 560              # present, left at their init
+    with pytest.raises(RuntimeError):
+        V.AnimateDiffUNet3DModel.from_pretrained_2d(str(tmp_path / "nope"), subfolder="unet")
