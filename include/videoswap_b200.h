@@ -71,6 +71,12 @@ int vs_unet_forward(vs_unet* h, void* stream, const void* d_sample, int io_f32, 
                     const float* d_timesteps, const void* d_ehs, int ehs_tokens, int ehs_layers,
                     const void* const* d_residuals, int residuals_nhwc, float residual_scale, void* d_out);
 size_t vs_unet_workspace_bytes(const vs_unet* h);
+/* The activation workspace is one arena that only grows: a forward of a smaller shape re-uses it.  A captured CUDA graph
+ * holds raw pointers into it, so the owner of a graph pins the arena (pin != 0; unpin with 0 when the graph dies): while
+ * pinned, a forward that would need a LARGER arena fails instead of re-allocating.  vs_unet_reserve_workspace sizes the
+ * arena for a shape ahead of time (e.g. the CFG batch before the B = 1 inversion graph is captured). */
+int vs_unet_pin_workspace(vs_unet* h, int pin);
+int vs_unet_reserve_workspace(vs_unet* h, int B, int F, int H, int W);
 /* Debug taps: after the next forward, copies of named intermediate activations (NHWC fp16) can be fetched. */
 int vs_unet_enable_taps(vs_unet* h, int enable);
 int vs_unet_num_taps(const vs_unet* h);

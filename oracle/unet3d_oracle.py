@@ -49,6 +49,10 @@ class OracleConfig:
 Tensor = torch.Tensor
 SD = Dict[str, Tensor]
 
+# False: softmax(q k^T) v spelled out (the arithmetic the oracle is pinned with).  True: F.scaled_dot_product_attention,
+# used only when bench.py runs this same graph in fp16 on the GPU as the "library baseline" (cuDNN / cuBLASLt / SDPA).
+USE_SDPA = False
+
 
 # ----------------------------------------------------------------------------------------------------------------
 # small ops
@@ -87,6 +91,12 @@ def _mha(q: Tensor, k: Tensor, v: Tensor, heads: int) -> Tensor:
     qh = q.reshape(b, nq, heads, d).transpose(1, 2)
     kh = k.reshape(b, k.shape[1], heads, d).transpose(1, 2)
     vh = v.reshape(b, v.shape[1], heads, d).transpose(1, 2)
+    if USE_SDPA:
+        return F.scaled_dot_product_attention(qh, kh, vh).transpose(1, 2).reshape(b, nq, c)
+    if b * heads * nq * kh.shape[2] > (1 << 30):      # bound the score matrix (N = 4096, 16+ frames): batch chunks
+        o = torch.cat([torch.matmul((torch.matmul(qh[i:i + 2], kh[i:i + 2].transpose(-1, -2)) * (d ** -0.5)).softmax(dim=-1),
+                                    vh[i:i + 2]) for i in range(0, b, 2)])
+        return o.transpose(1, 2).reshape(b, nq, c)
     s = torch.matmul(qh, kh.transpose(-1, -2)) * (d ** -0.5)
     o = torch.matmul(s.softmax(dim=-1), vh)
     return o.transpose(1, 2).reshape(b, nq, c)
@@ -166,7 +176,7 @@ def motion_module(sd: SD, p: str, x: Tensor, cfg: OracleConfig) -> Tensor:
     t = t.permute(0, 2, 3, 1).reshape(b * f, h * w, c)
     t = _lin(sd, p + ".proj_in", t)
     q = p + ".transformer_blocks.0"
-    pe = temporal_pe(f, c)
+    pe = temporal_pe(f, c).to(x)
     for i in (0, 1):
         n = _ln(sd, f"{q}.norms.{i}", t)
         # '(b f) d c -> (b d) f c', add PE after the LayerNorm, to the tensor that feeds q, k and v (P5)
@@ -202,7 +212,7 @@ def unet_forward(sd: SD, cfg: OracleConfig, sample: Tensor, timestep, ehs: Tenso
     B = sample.shape[0]
     t = torch.as_tensor(timestep).reshape(-1).expand(B)
     boc = list(cfg.block_out_channels)
-    temb = timestep_embedding(t, boc[0])
+    temb = timestep_embedding(t, boc[0]).to(sample)          # fp32 sinusoid, cast to the model dtype (unet.py:396)
     temb = _lin(sd, "time_embedding.linear_2", F.silu(_lin(sd, "time_embedding.linear_1", temb)))
     tap("temb", temb)
     residuals = list(residuals) if residuals is not None else None
@@ -327,17 +337,24 @@ class DDIM:
         return a_p ** 0.5 * x0 + (1 - a_p) ** 0.5 * eps
 
     def inverse_timesteps(self, n: int) -> List[int]:
-        """DDIMInverseScheduler.set_timesteps (0.19.3): the forward 'leading' timesteps, ascending."""
+        """DDIMInverseScheduler.set_timesteps: arange(n) * ratio + steps_offset, ascending (both conventions)."""
         return self.timesteps(n)[::-1]
 
-    def inverse_step(self, eps: Tensor, t: int, x: Tensor, n: int) -> Tensor:
-        """DDIMInverseScheduler.step (0.19.3): x_t -> x_{t+ratio}; here `t` is the *target* of the previous
-        iteration: prev_timestep = t - ratio is the level the sample is currently at.  (unpinned: see header)"""
-        prev = t - self.num_train_timesteps // n
-        a_t = self.alphas_cumprod[t]
-        a_p = self.alphas_cumprod[prev] if prev >= 0 else self.final_alpha_cumprod
-        x0 = (x - (1 - a_p) ** 0.5 * eps) / a_p ** 0.5
-        return a_t ** 0.5 * x0 + (1 - a_t) ** 0.5 * eps
+    def inverse_step(self, eps: Tensor, t: int, x: Tensor, n: int, convention: str = "0.19.3") -> Tensor:
+        """DDIMInverseScheduler.step, x_t -> x_{t+ratio} (unpinned: no diffusers offline, see header).
+        "0.19.3" (the release the reference pins): prev_timestep = t + ratio; x0 from alpha[t]; target alpha[t + ratio],
+        beyond the table alphas_cumprod[-1] (set_alpha_to_zero False via the SD config's set_alpha_to_one False).
+        "0.21": the sample sits at t - ratio and moves to t."""
+        ratio = self.num_train_timesteps // n
+        if convention == "0.19.3":
+            a_cur = self.alphas_cumprod[t]
+            a_nxt = self.alphas_cumprod[t + ratio] if t + ratio < self.num_train_timesteps else self.alphas_cumprod[-1]
+        else:
+            prev = t - ratio
+            a_nxt = self.alphas_cumprod[t]
+            a_cur = self.alphas_cumprod[prev] if prev >= 0 else self.final_alpha_cumprod
+        x0 = (x - (1 - a_cur) ** 0.5 * eps) / a_cur ** 0.5
+        return a_nxt ** 0.5 * x0 + (1 - a_nxt) ** 0.5 * eps
 
 
 def cfg_combine(eps2: Tensor, guidance: float) -> Tensor:
@@ -353,3 +370,35 @@ def denoise_step(sd: SD, cfg: OracleConfig, sched: DDIM, latents: Tensor, t: int
     res2 = [torch.cat([r] * 2, dim=0) for r in residuals] if residuals is not None else None
     eps2 = unet_forward(sd, cfg, x2, t, ehs2, res2)
     return sched.step(cfg_combine(eps2, guidance), t, latents, n_steps)
+
+
+def denoise_loop(sd: SD, cfg: OracleConfig, latents: Tensor, pos: Tensor, neg: Tensor, n_steps: int, guidance: float,
+                 adapter_state: Optional[List[Tensor]] = None, t2i_start: float = 0.0, t2i_end: float = 1.0,
+                 max_iters: Optional[int] = None) -> Tensor:
+    """pipeline_videoswap.py:552-610: the loop with the adapter window (`i <= len * t2i_end and i >= len * t2i_start`,
+    :561) and the final 'b c f h w -> (b f) c h w' (:603).  adapter_state: 4 x [(F),C,h,w] already scaled by
+    t2i_guidance_scale (:544-545); `max_iters` truncates the loop (tests run a few iterations of the 50-step schedule)."""
+    sched = DDIM()
+    ts = sched.timesteps(n_steps)
+    ehs2 = torch.cat([neg, pos]) if guidance > 1.0 else pos
+    for i, t in enumerate(ts):
+        if max_iters is not None and i >= max_iters:
+            break
+        res = adapter_state if (adapter_state is not None and len(ts) * t2i_start <= i <= len(ts) * t2i_end) else None
+        if guidance > 1.0:
+            latents = denoise_step(sd, cfg, sched, latents, t, n_steps, ehs2, guidance, res)
+        else:
+            latents = sched.step(unet_forward(sd, cfg, latents, t, ehs2, res), t, latents, n_steps)
+    b, c, f, h, w = latents.shape
+    return latents.permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w)
+
+
+def invert_loop(sd: SD, cfg: OracleConfig, latents: Tensor, ehs: Tensor, n_steps: int, convention: str = "0.19.3",
+                max_iters: Optional[int] = None) -> Tensor:
+    """pipeline_videoswap.py:677-703 with guidance_scale = 1: UNet at the scheduler's timestep, inverse DDIM step."""
+    sched = DDIM()
+    for i, t in enumerate(sched.inverse_timesteps(n_steps)):
+        if max_iters is not None and i >= max_iters:
+            break
+        latents = sched.inverse_step(unet_forward(sd, cfg, latents, t, ehs), t, latents, n_steps, convention)
+    return latents

@@ -144,9 +144,9 @@ def check_upsample(n=2, H=5, W=6, c=640, seed=90):
 
 
 # ---------------------------------------------------------------------------------------------------- norms
-def check_groupnorm(B=2, Fr=3, H=8, W=8, c1=320, c2=0, per_frame=False, silu=True, eps=1e-5, seed=100):
+def check_groupnorm(B=2, Fr=3, H=8, W=8, c1=320, c2=0, per_frame=False, silu=True, eps=1e-5, seed=100, mean=0.3):
     n = B * Fr
-    x1 = (_rand((n, H, W, c1), seed) * 1.5 + 0.3).half()
+    x1 = (_rand((n, H, W, c1), seed) * 1.5 + mean).half()
     x2 = (_rand((n, H, W, c2), seed + 1) * 0.7 - 0.2).half() if c2 else None
     C = c1 + c2
     gamma = (1 + 0.1 * _rand((C,), seed + 2)).float()
@@ -326,6 +326,10 @@ CHECKS = {
     "gn5d_concat": lambda: check_groupnorm(c1=640, c2=320),
     "gn_frame": lambda: check_groupnorm(per_frame=True, silu=False, eps=1e-6),
     "gn5d_1280": lambda: check_groupnorm(B=1, Fr=2, H=4, W=4, c1=1280, c2=1280),
+    # headline sizes: one statistics set = 16 frames x 64 x 64 x 10 channels = 655 360 elements with a mean 2-4x the spread
+    "gn5d_c2_l0_mean3": lambda: check_groupnorm(B=2, Fr=16, H=64, W=64, c1=320, mean=3.0, seed=101),
+    "gn5d_c2_l0_concat": lambda: check_groupnorm(B=1, Fr=16, H=64, W=64, c1=320, c2=320, mean=-6.0, seed=102),
+    "gn_frame_l0": lambda: check_groupnorm(B=2, Fr=4, H=64, W=64, c1=320, per_frame=True, silu=False, eps=1e-6, mean=2.0, seed=103),
     "ln_fold_qkv_320": lambda: check_ln_linear(),
     "ln_fold_qkv_pe_640": lambda: check_ln_linear(rows=1280, C=640, N=1920, pe=True, seed=116, hw=64),   # one frame per warp
     "ln_fold_q_1280": lambda: check_ln_linear(rows=700, C=1280, N=1280, seed=117),
@@ -340,6 +344,11 @@ CHECKS = {
     "self_attn_d40_n600": lambda: check_self_attention(B=2, N=600, C=320, seed=121),
     "self_attn_d40_n1024": lambda: check_self_attention(B=1, N=1024, C=320, seed=122),
     "self_attn_d80_n300": lambda: check_self_attention(B=2, N=300, C=640, seed=123),
+    # the launch that is 88 % of the attention FLOPs of the benchmark: N = 4096 keys (64 key tiles), d = 40
+    "self_attn_d40_n4096": lambda: check_self_attention(B=2, N=4096, C=320, seed=124),
+    "self_attn_d40_n5376": lambda: check_self_attention(B=1, N=5376, C=320, seed=125),     # 448x768 video: 56x96 latent
+    "self_attn_d80_n1024": lambda: check_self_attention(B=2, N=1024, C=640, seed=126),
+    "cross_attn_d40_n4096": lambda: check_cross_attention(B=1, Fr=2, N=4096, C=320, seed=132),
     "self_attn_d40_mma": lambda: check_self_attention_mma(C=320),
     "self_attn_d80_mma": lambda: check_self_attention_mma(B=2, N=64, C=640),
     "cross_attn_d40": lambda: check_cross_attention(B=2, Fr=2, N=300, C=320, seed=131),

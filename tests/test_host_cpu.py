@@ -146,5 +146,39 @@ def test_from_pretrained_2d_contract(tmp_path):
     assert isinstance(m, V.AnimateDiffUNet3DModel)
     assert torch.allclose(m.conv_in.bias.float(), torch.full((320,), 0.25))            # loaded
     assert sum(1 for k in m.state_dict() if "motion_modules" in k) == 560              # present, left at their init
+    # ... and that init is the reference's: every temporal_transformer.proj_out is ZERO (motion_module.py:76-77), so a
+    # motion module is an exact identity until a motion checkpoint arrives; other motion weights are not zero
+    po = [v for k, v in m.state_dict().items() if ".temporal_transformer.proj_out." in k]
+    assert len(po) == 40 and all(float(v.abs().max()) == 0.0 for v in po)
+    assert float(m.state_dict()["down_blocks.0.motion_modules.0.temporal_transformer.proj_in.weight"].abs().max()) > 0
     with pytest.raises(RuntimeError):
         V.AnimateDiffUNet3DModel.from_pretrained_2d(str(tmp_path / "nope"), subfolder="unet")
+
+
+def test_inverse_scheduler_conventions_and_alpha_table():
+    """DDIM / inverse-DDIM index arithmetic against an independent float64 restatement of the SD-1.5 schedule
+    (scaled_linear 0.00085 -> 0.012, 1000 steps), for all 50 steps of both DDIMInverseScheduler conventions."""
+    import numpy as np
+    betas = np.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, dtype=np.float64) ** 2
+    ac = np.cumprod(1.0 - betas)
+    fwd = V.DDIMScheduler()
+    fwd.set_timesteps(50)
+    assert fwd.timesteps == [981 - 20 * i for i in range(50)]
+    for t in fwd.timesteps:
+        a_t, a_p = fwd.alphas(t)
+        assert abs(a_t - ac[t]) < 2e-6 and abs(a_p - (ac[t - 20] if t >= 20 else ac[0])) < 2e-6
+    old = V.DDIMInverseScheduler(convention="0.19.3")
+    new = V.DDIMInverseScheduler(convention="0.21")
+    assert V.DDIMInverseScheduler().convention == "0.19.3"        # the release the reference pins (requirements.txt:2)
+    for s_ in (old, new):
+        s_.set_timesteps(50)
+        assert s_.timesteps == [1 + 20 * i for i in range(50)]
+    for t in old.timesteps:      # UNet at t, x0 from alpha[t], moves to alpha[t + 20] (alphas_cumprod[-1] beyond the table)
+        a_cur, a_nxt = old.alphas(t)
+        assert abs(a_cur - ac[t]) < 2e-6 and abs(a_nxt - (ac[t + 20] if t + 20 < 1000 else ac[999])) < 2e-6
+        assert a_nxt < a_cur                                         # noise level increases
+    for t in new.timesteps:      # UNet at the target t, sample at t - 20 (alphas_cumprod[0] before the table)
+        a_cur, a_nxt = new.alphas(t)
+        assert abs(a_nxt - ac[t]) < 2e-6 and abs(a_cur - (ac[t - 20] if t >= 20 else ac[0])) < 2e-6
+    with pytest.raises(ValueError):
+        V.DDIMInverseScheduler(convention="0.20")

@@ -10,8 +10,10 @@ pytestmark = pytest.mark.gpu
 PSNR_MIN = 40.0
 
 
-def test_unet_matches_reference_golden():
-    r = U.unet_vs_reference_golden()
+@pytest.mark.parametrize("name", ["full_arch_small", "full_arch_c1"])
+def test_unet_matches_reference_golden(name):
+    """full_arch_c1 = BASELINE configs[0] at its real size ([1,4,1,64,64], N = 4096 attention) from the reference's files."""
+    r = U.unet_vs_reference_golden(name)
     assert r["psnr"] >= PSNR_MIN, r
 
 
@@ -19,10 +21,15 @@ def test_unet_matches_reference_golden():
                                 dict(B=1, Fr=16, hw=8, edlora=False, t=1),
                                 dict(B=1, Fr=2, hw=8, w=24, edlora=True, residuals=True),    # non-square (56x96-like aspect)
                                 dict(B=1, Fr=1, hw=8, edlora=True),                          # C1: single frame
-                                dict(B=1, Fr=24, hw=8, edlora=False)])                       # longest clip of the PE table
+                                dict(B=1, Fr=24, hw=8, edlora=False),                        # longest clip of the PE table
+                                dict(B=1, Fr=1, hw=64, edlora=True),                         # C1 at its real 64x64 latent
+                                dict(B=1, Fr=4, hw=64, edlora=True, residuals=True, taps=True),   # headline resolution, 4 frames
+                                dict(B=2, Fr=2, hw=64, w=32, edlora=True, residuals=True)])  # CFG batch, 512x256
 def test_unet_matches_oracle(kw):
     r = U.unet_vs_oracle(**kw)
     assert r["finite"] and r["psnr"] >= PSNR_MIN, r
+    for name, tp in r.get("taps", {}).items():          # every block output, not only the final 4-channel epsilon
+        assert tp["psnr"] >= PSNR_MIN, (name, tp)
 
 
 def test_fp32_latents_take_the_same_path():
@@ -57,6 +64,45 @@ def test_denoise_loop_matches_oracle():
     assert r["psnr"] >= PSNR_MIN, r
 
 
+def test_pipeline_call_with_conditions_matches_oracle():
+    """VideoSwapPipeline.__call__: adapter from `conditions`, t2i window (closed after iteration 1), CFG, DDIM, and the
+    reference's final 'b c f h w -> (b f) c h w' (pipeline_videoswap.py:525-610)."""
+    r = U.pipeline_call_vs_oracle(iters=3)
+    assert r["shape"] == r["ref_shape"] == (2, 4, 16, 16), r
+    assert r["psnr"] >= PSNR_MIN, r
+    assert r["psnr_if_window_ignored"] < r["psnr"] - 6.0, r      # the window really closed (residuals matter)
+
+
+@pytest.mark.parametrize("convention", ["0.19.3", "0.21"])
+def test_invert_matches_oracle(convention):
+    r = U.invert_vs_oracle(iters=3, convention=convention)
+    assert r["psnr"] >= PSNR_MIN, r
+
+
+def test_workspace_survives_other_shapes_under_a_captured_graph():
+    """a captured graph holds raw pointers into the workspace.  Smaller shapes re-use the arena (the replay stays
+    correct); a LARGER shape must fail loudly instead of re-allocating under the graph."""
+    from videoswap_b200 import DDIMScheduler, VideoSwapPipeline
+    from videoswap_b200.pipeline import GraphedStep
+    m = U.fresh_model()                        # own handle: its arena has only ever seen the shapes of this test
+    pipe = VideoSwapPipeline(m, DDIMScheduler())
+    pipe.scheduler.set_timesteps(50)
+    lat = U.randn((1, 4, 2, 16, 16), 33).half().cuda()
+    emb = U.randn((2, 16, 77, 768), 34).half().cuda()
+    g = GraphedStep(pipe, lat, emb, 7.5)
+    ref = g(lat, 981).clone()
+    small = m(torch.zeros(1, 4, 1, 8, 8, dtype=torch.float16, device="cuda"), 1, emb[:1], return_dict=False)[0]   # B=1 inversion-like
+    assert torch.isfinite(small).all()
+    again = g(lat, 981).clone()
+    torch.cuda.synchronize()
+    assert U.psnr(again, ref) >= 60.0
+    with pytest.raises(Exception, match="pinned"):
+        m(torch.zeros(2, 4, 4, 32, 32, dtype=torch.float16, device="cuda"), 1, emb, return_dict=False)
+    del g
+    big = m(torch.zeros(2, 4, 4, 32, 32, dtype=torch.float16, device="cuda"), 1, emb, return_dict=False)[0]       # unpinned: grows
+    assert torch.isfinite(big).all()
+
+
 def test_cuda_graph_step_equals_eager_step():
     from videoswap_b200 import DDIMScheduler, VideoSwapPipeline
     from videoswap_b200.pipeline import GraphedStep
@@ -73,6 +119,14 @@ def test_cuda_graph_step_equals_eager_step():
         assert torch.isfinite(out).all()
         # same kernels, same inputs: only fp32-atomic summation order in the GroupNorm statistics may differ
         assert U.psnr(out, ref) >= 60.0, (t, U.psnr(out, ref))
+
+
+def test_adapter_fp16_coordinates_match_reference_golden():
+    """Product default path: fp16 coordinate quantisation against the reference's half-precision adapter."""
+    r = U.adapter_fp16_vs_golden()
+    assert all(r["same_support"]), r
+    for e, ref in zip(r["errs"], r["refs"]):
+        assert e <= 2 ** -7 * ref + 4e-3, r       # fp16 accumulation order differs (gather vs the reference's += sequence)
 
 
 def test_adapter_matches_reference_golden():

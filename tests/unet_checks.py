@@ -38,6 +38,24 @@ def get_model():
     return _CACHE["m"]
 
 
+def fresh_model():
+    """A second, independent model instance (own native handle and workspace) with random weights made on the GPU."""
+    m = AnimateDiffUNet3DModel(init="empty")
+    g = torch.Generator(device="cuda").manual_seed(0)
+    sd = {}
+    for name, shape in unet_param_shapes(m.cfg).items():
+        if name.endswith(".pe"):
+            continue
+        if len(shape) >= 2:
+            sd[name] = ((torch.rand(shape, device="cuda", generator=g) * 2 - 1) / math.sqrt(math.prod(shape[1:]))).half()
+        elif name.endswith(".weight"):
+            sd[name] = (1 + 0.1 * torch.randn(shape, device="cuda", generator=g)).half()
+        else:
+            sd[name] = (0.02 * torch.randn(shape, device="cuda", generator=g)).half()
+    m.load_state_dict(sd, strict=False, assign=True)
+    return m.half().cuda()
+
+
 def nhwc_tap_to_ncfhw(t, B):
     n, h, w, c = t.shape
     return t.float().cpu().reshape(B, n // B, h, w, c).permute(0, 4, 1, 2, 3)
@@ -73,14 +91,15 @@ def unet_vs_oracle(B=1, Fr=2, hw=8, edlora=True, residuals=False, t=981, taps=Fa
     return r
 
 
-def unet_vs_reference_golden():
-    """tests/golden/unet_full_arch_small.pt was produced by the REFERENCE's own model files (oracle/make_golden.py)."""
+def unet_vs_reference_golden(name="full_arch_small"):
+    """tests/golden/unet_<name>.pt was produced by the REFERENCE's own model files (oracle/make_golden.py)."""
     from oracle.make_golden import make_inputs
-    g = torch.load(os.path.join(GOLD, "unet_full_arch_small.pt"))
+    g = torch.load(os.path.join(GOLD, f"unet_{name}.pt"))
     case = g["case"]
     m, _ = get_model()
-    x, ehs, _ = make_inputs(case)
-    out = m(x.half().cuda(), case["t"], ehs.half().cuda(), return_dict=False)[0]
+    x, ehs, res = make_inputs(case)
+    res16 = [r.half().cuda() for r in res] if res else None
+    out = m(x.half().cuda(), case["t"], ehs.half().cuda(), down_block_additional_residuals=res16, return_dict=False)[0]
     torch.cuda.synchronize()
     return {"psnr": psnr(out, g["out"]), "max_err": (out.float().cpu() - g["out"]).abs().max().item()}
 
@@ -107,6 +126,77 @@ def pipeline_vs_oracle(steps=3, Fr=2, hw=8, guidance=7.5):
         nat = ops.cfg_ddim_step(eps, nat, guidance, a_t, a_p)
     torch.cuda.synchronize()
     return {"psnr": psnr(nat, ref), "max_err": (nat.float().cpu() - ref).abs().max().item()}
+
+
+def _conditions(Fr, img, P=6, seed=51):
+    """Synthetic TAP conditions: tracks U[0, img) with some invisible, point embeddings N(0,1)."""
+    g = torch.Generator().manual_seed(seed)
+    tracks = torch.rand((Fr, P, 2), generator=g) * img
+    tracks[0, 0] = -1.0
+    tracks[Fr - 1, P - 1, 1] = -1.0
+    emb = torch.randn((P, 1280), generator=g)
+    return {"pred_tracks": tracks[None], "img_size": (img, img), "point_embedding": emb[None], "index_list": list(range(P - 1))}
+
+
+def pipeline_call_vs_oracle(iters=3, Fr=2, hw=16, guidance=7.5, t2i_scale=0.5, t2i_end=1.0 / 50):
+    """VideoSwapPipeline.__call__ (conditions -> adapter, residual window, CFG, DDIM, final rearrange) vs the oracle's
+    restatement of pipeline_videoswap.py:525-610.  `t2i_end` = 1/50 closes the adapter window after iteration 1."""
+    m, sd = get_model()
+    ad = SparsePointAdapter(init="empty")
+    asd = seeded_state_dict(adapter_param_shapes(), seed=5)
+    ad.load_state_dict(asd)
+    ad = ad.half().cuda()
+    pipe = VideoSwapPipeline(m, DDIMScheduler(), adapter=ad)
+    cond = _conditions(Fr, hw * 8)
+    lat = randn((1, 4, Fr, hw, hw), 21).half()
+    pos, neg = randn((1, 16, 77, 768), 22).half(), randn((1, 16, 77, 768), 23).half()
+    out = pipe(pos.cuda(), lat.cuda(), negative_prompt_embeds=neg.cuda(), conditions=cond, num_inference_steps=50,
+               guidance_scale=guidance, t2i_guidance_scale=t2i_scale, t2i_start=0.0, t2i_end=t2i_end, max_iters=iters).videos
+    torch.cuda.synchronize()
+    # oracle: the reference's fp16 adapter arithmetic, then the fp32 loop on the fp16-rounded maps
+    asd16 = {k: v.half() for k, v in asd.items()}
+    maps = O.adapter_forward(asd16, cond["pred_tracks"][0].half(), cond["img_size"], cond["point_embedding"][0].half(),
+                             index_list=cond["index_list"])
+    state = [(mm * t2i_scale).float() for mm in maps]
+    with torch.no_grad():
+        ref = O.denoise_loop(sd, O.OracleConfig(), lat.float(), pos.float(), neg.float(), 50, guidance, state, 0.0, t2i_end,
+                             max_iters=iters)
+        ref_no_window = O.denoise_loop(sd, O.OracleConfig(), lat.float(), pos.float(), neg.float(), 50, guidance, state, 0.0, 1.0,
+                                       max_iters=iters)
+    return {"psnr": psnr(out, ref), "shape": tuple(out.shape), "ref_shape": tuple(ref.shape),
+            "psnr_if_window_ignored": psnr(out, ref_no_window)}
+
+
+def invert_vs_oracle(iters=3, Fr=2, hw=8, convention="0.19.3"):
+    from videoswap_b200 import DDIMInverseScheduler
+    m, sd = get_model()
+    pipe = VideoSwapPipeline(m, DDIMScheduler(), inverse_scheduler=DDIMInverseScheduler(convention=convention))
+    lat = randn((1, 4, Fr, hw, hw), 61).half()
+    emb = randn((1, 77, 768), 62).half()
+    out = pipe.invert(emb.cuda(), lat.cuda(), num_inference_steps=50, max_iters=iters).latents
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = O.invert_loop(sd, O.OracleConfig(), lat.float(), emb.float(), 50, convention, max_iters=iters)
+    return {"psnr": psnr(out, ref), "max_err": (out.float().cpu() - ref).abs().max().item()}
+
+
+def adapter_fp16_vs_golden():
+    """Product default (coord_fp16=True, the reference's fp16 inference arithmetic) vs the fixture the reference's own
+    SparsePointAdapter produced in half precision."""
+    from oracle.make_golden import adapter_fp16_inputs, densify
+    g = torch.load(os.path.join(GOLD, "adapter_fp16.pt"))
+    ref = densify(g["maps_sparse"])
+    ad = SparsePointAdapter(init="empty")
+    ad.load_state_dict(seeded_state_dict(adapter_param_shapes(), seed=5))
+    ad = ad.half().cuda()
+    tracks, emb, size, index_list = adapter_fp16_inputs()
+    maps = ad(tracks.cuda(), size, emb.half().cuda(), index_list=index_list, coord_fp16=True, as_nchw=True)
+    torch.cuda.synchronize()
+    errs = [(m.float().cpu() - r.float()).abs().max().item() for m, r in zip(maps, ref)]
+    refs = [r.float().abs().max().item() for r in ref]
+    # the support (which cells a point touches) must be identical: that is what the fp16 coordinate quantisation decides
+    same_support = [bool(((m.float().cpu() != 0).any(1) == (r != 0).any(1)).all()) for m, r in zip(maps, ref)]
+    return {"errs": errs, "refs": refs, "same_support": same_support}
 
 
 def adapter_vs_golden():

@@ -60,7 +60,8 @@ struct vs_unet {
   std::vector<void*> allocs;
   std::unordered_map<std::string, Loader> loaders;
   std::vector<std::string> names;
-  std::vector<FoldJob> folds;           // re-run after every weight load
+  std::vector<FoldJob> folds;           // re-derived lazily (next forward) after weight loads
+  bool folds_dirty = true;
 
   // parameters
   __half* conv_in_w = nullptr; float* conv_in_b = nullptr;
@@ -72,8 +73,10 @@ struct vs_unet {
   float* pe[4] = {nullptr, nullptr, nullptr, nullptr};   // [pe_max_len, C_l] fp32 per level
 
   // workspace
-  size_t ws_bytes = 0; void* ws = nullptr;
-  int wsB = 0, wsF = 0, wsH = 0, wsW = 0;
+  size_t ws_bytes = 0; void* ws = nullptr;   // arena: grows monotonically, never shrinks (captured CUDA graphs hold raw
+  int wsB = 0, wsF = 0, wsH = 0, wsW = 0;     // pointers into it); `ws_pinned` > 0 forbids the re-allocation altogether
+  int ws_pinned = 0;
+  int n_groupnorms = 0;                        // GroupNorm calls of one forward (sizes the statistics slices)
   __half *XIN, *XN, *T, *TN, *QKV, *ATT, *HH, *SC, *P0, *P1, *SCR, *KV, *RES, *OUT;
   std::vector<__half*> skip;            // 12 skip buffers
   float *F_T, *F_TE0, *F_TE1, *F_EMB, *F_TPROJ, *F_SUMS, *F_LNS;
@@ -229,6 +232,7 @@ extern "C" int vs_unet_create(const vs_unet_config* cfg, vs_unet** out) {
                "block_out_channels[%d]=%d unsupported (need C %% 64 == 0 and head dim in {40,80,160})", i,
                cfg->block_out_channels[i]);
   VS_REQUIRE(cfg->cross_attention_dim % 64 == 0, "cross_attention_dim must be a multiple of 64");
+  VS_REQUIRE(cfg->norm_num_groups >= 1 && cfg->norm_num_groups <= 32, "norm_num_groups must be in [1, 32] (statistics slices hold 32 groups)");
   vs_unet* h = new vs_unet();
   h->cfg = *cfg;
   const int* boc = cfg->block_out_channels;
@@ -301,6 +305,13 @@ extern "C" int vs_unet_create(const vs_unet_config* cfg, vs_unet** out) {
   h->norm_out = h->norm("conv_norm_out", boc[0]);
   h->conv_out = h->conv3("conv_out", cfg->out_channels, boc[0]);
   VS_REQUIRE(toff == tn, "internal: time_emb_proj stacking mismatch (%d vs %d)", toff, tn);
+  {   // GroupNorm calls per forward: 2 per resnet, 1 per transformer, 1 per motion module, conv_norm_out
+    int n = 1 + 2 /*mid1*/;
+    auto count = [&](const Layer& L) { n += 2 + (L.has_tr ? 1 : 0) + (L.has_mo ? 1 : 0); };
+    for (int i = 0; i < 4; ++i) { for (const Layer& L : h->down[i].layers) count(L); for (const Layer& L : h->up[i].layers) count(L); }
+    count(h->mid0);
+    h->n_groupnorms = n;
+  }
   for (void* p : h->allocs) if (!p) { delete h; return 1; }
   VS_CHECK_CUDA(cudaGetLastError());
   *out = h;
@@ -336,8 +347,7 @@ extern "C" int vs_unet_load_weights(vs_unet* h, void* stream, int n, const char*
     }
     if (e) return e;
   }
-  for (const FoldJob& f : h->folds)
-    if (int e = ln_fold(st, f.w, f.N, f.K, f.gamma, f.beta, f.bias, f.pe, f.pe_len, f.dst.wf, f.dst.u, f.dst.c, f.dst.cpe)) return e;
+  h->folds_dirty = true;                // the LayerNorm-folded copies are re-derived once, at the next forward
   return 0;
 }
 
@@ -351,8 +361,12 @@ struct Ctx {
   int gn_idx = 0;          // GroupNorm call counter: every call owns a slice of F_SUMS, all zeroed by ONE memset per forward
 };
 
-constexpr int kMaxGroupNorms = 128;
-inline float* next_sums(Ctx& c) { return c.h->F_SUMS + (size_t)(c.gn_idx++ % kMaxGroupNorms) * ((size_t)c.NI * 64); }
+// every GroupNorm call of a forward owns one slice [NI, 32 groups, 2] of F_SUMS (h->n_groupnorms of them, counted at create)
+inline float* next_sums(Ctx& c) {
+  if (c.gn_idx >= c.h->n_groupnorms) { set_error("internal: more GroupNorm calls (%d) than statistics slices (%d)", c.gn_idx + 1, c.h->n_groupnorms); return nullptr; }
+  return c.h->F_SUMS + (size_t)(c.gn_idx++) * ((size_t)c.NI * 64);
+}
+#define NEXT_SUMS(var) float* var = next_sums(c); if (!var) return 2
 
 #define RUN(expr) do { if (int _e = (expr)) return _e; } while (0)
 
@@ -387,11 +401,12 @@ int resnet(Ctx& c, const Resnet& r, const __half* in1, int C1, const __half* in2
   const int hw = c.H * c.W, G = h->cfg.norm_num_groups;
   const float eps = h->cfg.norm_eps;
   VS_REQUIRE(C1 + C2 == r.cin, "internal: resnet input channels %d+%d != %d", C1, C2, r.cin);
-  float* sums = next_sums(c);
+  NEXT_SUMS(sums);
   RUN(groupnorm_stats(c.st, in1, C1, in2, C2, c.NI, hw, c.F, G, sums, false));
   RUN(groupnorm_apply(c.st, in1, C1, in2, C2, c.NI, hw, c.F, G, sums, eps, r.n1.g, r.n1.b, true, h->XN));
   RUN(conv(c, h->XN, r.cin, r.c1, h->F_TPROJ + r.temb_off, nullptr, h->T));
   sums = next_sums(c);
+  if (!sums) return 2;
   RUN(groupnorm_stats(c.st, h->T, r.cout, nullptr, 0, c.NI, hw, c.F, G, sums, false));
   RUN(groupnorm_apply(c.st, h->T, r.cout, nullptr, 0, c.NI, hw, c.F, G, sums, eps, r.n2.g, r.n2.b, true, h->XN));
   const __half* residual = in1;
@@ -432,7 +447,7 @@ int geglu_ff(Ctx& c, const __half* tn, int M, int C, const __half* w1, const flo
 int transformer(Ctx& c, const Transformer& t, __half* x) {
   vs_unet* h = c.h;
   const int hw = c.H * c.W, C = t.C, M = c.NI * hw, heads = h->cfg.num_heads, d = C / heads;
-  float* sums = next_sums(c);
+  NEXT_SUMS(sums);
   RUN(groupnorm_stats(c.st, x, C, nullptr, 0, c.NI, hw, 1, h->cfg.norm_num_groups, sums, false));
   RUN(groupnorm_apply(c.st, x, C, nullptr, 0, c.NI, hw, 1, h->cfg.norm_num_groups, sums, 1e-6f, t.norm.g, t.norm.b, false, h->XN));
   RUN(linear(c, h->XN, M, t.proj_in, nullptr, h->T));
@@ -485,7 +500,7 @@ int motion(Ctx& c, const Motion& m, int level, __half* x) {
   vs_unet* h = c.h;
   const int hw = c.H * c.W, C = m.C, M = c.NI * hw;
   VS_REQUIRE(c.F <= h->cfg.pe_max_len, "video_length %d exceeds temporal_position_encoding_max_len %d", c.F, h->cfg.pe_max_len);
-  float* sums = next_sums(c);
+  NEXT_SUMS(sums);
   RUN(groupnorm_stats(c.st, x, C, nullptr, 0, c.NI, hw, 1, 32, sums, false));
   RUN(groupnorm_apply(c.st, x, C, nullptr, 0, c.NI, hw, 1, 32, sums, 1e-6f, m.norm.g, m.norm.b, false, h->XN));
   RUN(linear(c, h->XN, M, m.proj_in, nullptr, h->T));
@@ -512,9 +527,11 @@ int motion(Ctx& c, const Motion& m, int level, __half* x) {
 
 size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
+// Lays the activation arena out for (B, F, H, W).  The arena only ever GROWS (a smaller shape re-uses it with a new
+// layout), and never while it is pinned: a captured CUDA graph holds raw pointers into it, so a re-allocation would leave
+// the graph reading and writing freed memory (vs_unet_pin_workspace; GraphedStep pins).
 int ensure_workspace(vs_unet* h, int B, int F, int H, int W) {
   if (h->ws && h->wsB == B && h->wsF == F && h->wsH == H && h->wsW == W) return 0;
-  if (h->ws) { cudaFree(h->ws); h->ws = nullptr; }
   const int* boc = h->cfg.block_out_channels;
   const size_t NI = (size_t)B * F;
   // per-level pixel counts
@@ -551,11 +568,17 @@ int ensure_workspace(vs_unet* h, int B, int F, int H, int W) {
   for (auto& r : req) total += align_up(r.second * 2);
   const int temb = boc[0] * 4;
   const size_t fl = align_up(4 * 64) + align_up((size_t)B * boc[0] * 4) + 2 * align_up((size_t)B * temb * 4) +
-                    align_up((size_t)B * h->tproj_n * 4) + align_up((size_t)kMaxGroupNorms * NI * 64 * 4) +
+                    align_up((size_t)B * h->tproj_n * 4) + align_up((size_t)h->n_groupnorms * NI * 64 * 4) +
                     align_up(NI * hw[0] * 2 * 4);
   total += fl;
-  VS_CHECK_CUDA(cudaMalloc(&h->ws, total));
-  h->ws_bytes = total;
+  if (total > h->ws_bytes) {
+    VS_REQUIRE(h->ws_pinned == 0, "vs_unet_forward: shape [%d,%d,%d,%d] needs a %zu-byte workspace but the current one "
+               "(%zu bytes) is pinned by a captured CUDA graph; run the largest shape first or call "
+               "vs_unet_reserve_workspace before capturing", B, F, H, W, total, h->ws_bytes);
+    if (h->ws) { VS_CHECK_CUDA(cudaDeviceSynchronize()); cudaFree(h->ws); h->ws = nullptr; h->ws_bytes = 0; }
+    VS_CHECK_CUDA(cudaMalloc(&h->ws, total));
+    h->ws_bytes = total;
+  }
   char* p = (char*)h->ws;
   for (auto& r : req) { *r.first = (__half*)p; p += align_up(r.second * 2); }
   h->F_T = (float*)p; p += align_up(4 * 64);
@@ -563,13 +586,24 @@ int ensure_workspace(vs_unet* h, int B, int F, int H, int W) {
   h->F_TE1 = (float*)p; p += align_up((size_t)B * temb * 4);
   h->F_EMB = (float*)p; p += align_up((size_t)B * temb * 4);
   h->F_TPROJ = (float*)p; p += align_up((size_t)B * h->tproj_n * 4);
-  h->F_SUMS = (float*)p; p += align_up((size_t)kMaxGroupNorms * NI * 64 * 4);
+  h->F_SUMS = (float*)p; p += align_up((size_t)h->n_groupnorms * NI * 64 * 4);
   h->F_LNS = (float*)p;
   h->wsB = B; h->wsF = F; h->wsH = H; h->wsW = W;
   return 0;
 }
 
 }  // namespace
+
+extern "C" int vs_unet_pin_workspace(vs_unet* h, int pin) {
+  VS_REQUIRE(h != nullptr, "vs_unet_pin_workspace: null handle");
+  h->ws_pinned += pin ? 1 : -1;
+  if (h->ws_pinned < 0) h->ws_pinned = 0;
+  return 0;
+}
+extern "C" int vs_unet_reserve_workspace(vs_unet* h, int B, int F, int H, int W) {
+  VS_REQUIRE(h && B >= 1 && F >= 1 && H >= 1 && W >= 1, "vs_unet_reserve_workspace: bad arguments");
+  return ensure_workspace(h, B, F, H, W);
+}
 
 extern "C" int vs_unet_enable_taps(vs_unet* h, int enable) {
   for (auto& t : h->taps) cudaFree(t.p);
@@ -601,13 +635,18 @@ extern "C" int vs_unet_forward(vs_unet* h, void* stream, const void* d_sample, i
   VS_REQUIRE(h->cfg.in_channels <= 8 && h->cfg.out_channels <= 8, "in/out channels > 8 unsupported");
   cudaStream_t st = (cudaStream_t)stream;
   RUN(ensure_workspace(h, B, F, H, W));
+  if (h->folds_dirty) {
+    for (const FoldJob& f : h->folds)
+      RUN(ln_fold(st, f.w, f.N, f.K, f.gamma, f.beta, f.bias, f.pe, f.pe_len, f.dst.wf, f.dst.u, f.dst.c, f.dst.cpe));
+    h->folds_dirty = false;
+  }
   if (h->taps_on) { for (auto& t : h->taps) cudaFree(t.p); h->taps.clear(); }
   const vs_unet_config& cf = h->cfg;
   const int* boc = cf.block_out_channels;
   const int temb = boc[0] * 4, lpb = cf.layers_per_block;
   Ctx c{h, st, B, F, B * F, H, W, (const __half*)d_ehs, ehs_tokens, ehs_layers};
 
-  VS_CHECK_CUDA(cudaMemsetAsync(h->F_SUMS, 0, (size_t)kMaxGroupNorms * c.NI * 64 * sizeof(float), st));
+  VS_CHECK_CUDA(cudaMemsetAsync(h->F_SUMS, 0, (size_t)h->n_groupnorms * c.NI * 64 * sizeof(float), st));
   // ---- time embedding (unet.py:376-397): Timesteps -> Linear -> SiLU -> Linear; then every resnet's projection of
   //      SiLU(emb) in one stacked tiny-M linear (resnet.py:171-172)
   RUN(timestep_embedding(st, d_timesteps, B, boc[0], h->F_TE0));
@@ -713,7 +752,7 @@ extern "C" int vs_unet_forward(vs_unet* h, void* stream, const void* d_sample, i
   }
   VS_REQUIRE(c.H == H && c.W == W, "input H/W (%d,%d) must be multiples of 8 (the reference's forward_upsample_size path is not implemented)", H, W);
   // ---- out: GroupNorm(5-D) + SiLU + conv_out
-  float* osums = next_sums(c);
+  NEXT_SUMS(osums);
   RUN(groupnorm_stats(st, cur, curC, nullptr, 0, c.NI, H * W, F, cf.norm_num_groups, osums, false));
   RUN(groupnorm_apply(st, cur, curC, nullptr, 0, c.NI, H * W, F, cf.norm_num_groups, osums, cf.norm_eps, h->norm_out.g, h->norm_out.b, true, h->XN));
   {

@@ -145,7 +145,8 @@ class VideoSwapPipeline:
     def __call__(self, prompt_embeds: torch.Tensor, latents: torch.Tensor, negative_prompt_embeds: Optional[torch.Tensor] = None,
                  conditions: Optional[Dict] = None, num_inference_steps: int = 50, guidance_scale: float = 7.5,
                  t2i_guidance_scale: float = 1.0, t2i_start: float = 0.0, t2i_end: float = 1.0, controller=None,
-                 output_type: str = "latent", return_dict: bool = True, callback=None, callback_steps: int = 1):
+                 output_type: str = "latent", return_dict: bool = True, callback=None, callback_steps: int = 1,
+                 max_iters: Optional[int] = None):
         """prompt_embeds: [1,77,D] / ED-LoRA [1,16,77,D] (conditional); negative_prompt_embeds same shape (uncond).
         latents [1,4,F,h,w] (e.g. DDIM-inverted).  Mirrors pipeline_videoswap.py:552-601."""
         if controller is not None:
@@ -166,31 +167,43 @@ class VideoSwapPipeline:
         if conditions is not None:
             if self.adapter is None:
                 raise ValueError("conditions given but the pipeline has no adapter")
-            adapter_state = self.adapter(conditions["pred_tracks"].to(dev), conditions["img_size"],
-                                         conditions["point_embedding"].to(dev), index_list=conditions.get("index_list"),
-                                         scale=t2i_guidance_scale)
+            # the reference casts tracks AND the point embedding to the latents dtype first (pipeline_videoswap.py:528-533)
+            emb = conditions["point_embedding"].to(dev)
+            if latents.dtype == torch.float16:
+                emb = emb.half()
+            adapter_state = self.adapter(conditions["pred_tracks"].to(dev), conditions["img_size"], emb,
+                                         index_list=conditions["index_list"], scale=t2i_guidance_scale,
+                                         coord_fp16=latents.dtype == torch.float16)
             adapter_state = self._residuals_for_cfg(adapter_state, cfg)
         latents = latents.contiguous()
         for i, t in enumerate(timesteps):
+            if max_iters is not None and i >= max_iters:      # truncated schedules (tests / benchmarks)
+                break
             res = None
             if adapter_state is not None and len(timesteps) * t2i_start <= i <= len(timesteps) * t2i_end:
                 res = list(adapter_state)        # the UNet pops from this list (no clone needed: it never writes to them)
             latents = self.step(latents, t, embeds, guidance_scale, res)
             if callback is not None and i % callback_steps == 0:
                 callback(i, t, latents)
+        # the reference always rearranges 'b c f h w -> (b f) c h w' before returning (pipeline_videoswap.py:603-610)
+        b, c, f, h, w = latents.shape
+        video = latents.permute(0, 2, 1, 3, 4).reshape(b * f, c, h, w)
         if not return_dict:
-            return latents
-        return TuneAVideoPipelineOutput(videos=latents)
+            return video
+        return TuneAVideoPipelineOutput(videos=video)
 
     @torch.no_grad()
     def invert(self, prompt_embeds: torch.Tensor, latents: torch.Tensor, num_inference_steps: int = 50,
-               return_dict: bool = True, controller=None):
-        """DDIM inversion loop (pipeline_videoswap.py:677-703), guidance_scale = 1 (no CFG)."""
+               return_dict: bool = True, controller=None, max_iters: Optional[int] = None):
+        """DDIM inversion loop (pipeline_videoswap.py:677-703), guidance_scale = 1 (no CFG).  The UNet is evaluated at
+        the inverse scheduler's timestep; which noise levels the step connects is the scheduler's `convention`."""
         if controller is not None:
             raise NotImplementedError("attention controllers (SURVEY 8f-2) are not on the native path yet")
         self.inverse_scheduler.set_timesteps(num_inference_steps)
         latents = latents.contiguous()
-        for t in self.inverse_scheduler.timesteps:
+        for i, t in enumerate(self.inverse_scheduler.timesteps):
+            if max_iters is not None and i >= max_iters:
+                break
             eps = self.unet(latents, t, encoder_hidden_states=prompt_embeds, return_dict=False)[0]
             a_cur, a_next = self.inverse_scheduler.alphas(t)
             latents = ops.cfg_ddim_step(eps, latents, 1.0, a_cur, a_next, cfg=False)
@@ -206,8 +219,14 @@ class GraphedStep:
     static.  Removes ~750 kernel-launch gaps per step."""
 
     def __init__(self, pipe: VideoSwapPipeline, latents: torch.Tensor, embeds: torch.Tensor, guidance_scale: float = 7.5,
-                 residuals: Optional[List[torch.Tensor]] = None):
-        self.pipe, self.guidance, self.residuals = pipe, guidance_scale, residuals
+                 residuals: Optional[List[torch.Tensor]] = None, inverse: bool = False):
+        """inverse=True: the DDIM-inversion loop body (pipeline_videoswap.py:677-696, no CFG) -- `__call__` then takes the
+        inverse scheduler's timesteps and coefficients."""
+        self.pipe, self.guidance, self.residuals, self.inverse = pipe, guidance_scale, residuals, inverse
+        if inverse:
+            assert guidance_scale <= 1.0 and residuals is None, "the inversion loop runs without CFG and without adapter residuals"
+            if pipe.inverse_scheduler.num_inference_steps is None:
+                pipe.inverse_scheduler.set_timesteps(pipe.scheduler.num_inference_steps or 50)
         dev = latents.device
         self.lat = latents.clone().contiguous()
         self.embeds = embeds.contiguous()
@@ -225,6 +244,18 @@ class GraphedStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.out = self._body()
+        # the graph holds raw pointers into the UNet's workspace arena: forbid its re-allocation while this object lives
+        from . import _lib
+        self._pinned = pipe.unet._handle
+        _lib.call("vs_unet_pin_workspace", self._pinned, 1)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_pinned", None) is not None:
+                from . import _lib
+                _lib.lib().vs_unet_pin_workspace(self._pinned, 0)
+        except Exception:  # noqa: BLE001
+            pass
 
     def _body(self):
         cfg = self.guidance > 1.0
@@ -236,8 +267,8 @@ class GraphedStep:
 
     def __call__(self, latents: torch.Tensor, t: int) -> torch.Tensor:
         """Runs the step at timestep t.  The returned tensor is overwritten by the next call."""
-        a_t, a_p = self.pipe.scheduler.alphas(t)
-        c_x, c_e = ops.ddim_coefficients(a_t, a_p)
+        a_t, a_p = (self.pipe.inverse_scheduler if self.inverse else self.pipe.scheduler).alphas(t)
+        c_x, c_e = ops.ddim_coefficients(a_t, a_p)      # the same update serves both directions: x' = c_x x + c_e eps
         # a fresh pinned staging tensor per call: torch's caching host allocator keeps it alive until the async copy ran
         h = torch.tensor([float(t), c_x, c_e], dtype=torch.float32).pin_memory()
         self._d.copy_(h, non_blocking=True)

@@ -46,16 +46,35 @@ class DDIMScheduler:
 
 
 class DDIMInverseScheduler(DDIMScheduler):
-    """x_t -> x_{t+ratio} (DDIM inversion, pipeline_videoswap.py:667,696).  NOTE: diffusers changed the index
-    convention of DDIMInverseScheduler.step between 0.17 and 0.21 and no diffusers install is available offline, so
-    this follows the later (documented) convention and is flagged 'parity unpinned' in DESIGN.md."""
+    """x_t -> x_{t+ratio} (DDIM inversion, pipeline_videoswap.py:163,667,696: built with
+    `DDIMInverseScheduler.from_config(scheduler.config)`).
+
+    diffusers changed this scheduler's index convention after the release the reference pins (requirements.txt:2,
+    diffusers==0.19.3), so it is a constructor switch:
+      * "0.19.3" (default = the pinned release): timesteps ascend 1, 21, ..., 981; the step taken at `t` evaluates the UNet
+        at t (the level the sample is AT), uses alpha[t] for x0 and moves to alpha[t + ratio]; past the table the final
+        alpha is alphas_cumprod[-1] because `set_alpha_to_one=False` of the SD config maps onto `set_alpha_to_zero=False`.
+      * "0.21": the later convention -- the UNet is evaluated at the TARGET timestep t, the sample sits at t - ratio.
+    No diffusers install exists offline, so both are restated from the published sources ('parity unpinned')."""
+
+    def __init__(self, *a, convention: str = "0.19.3", **k):
+        super().__init__(*a, **k)
+        if convention not in ("0.19.3", "0.21"):
+            raise ValueError("convention must be '0.19.3' or '0.21'")
+        self.convention = convention
+        self.last_alpha_cumprod = self.alphas_cumprod[-1]
 
     def set_timesteps(self, num_inference_steps: int, device=None):
         super().set_timesteps(num_inference_steps, device)
         self.timesteps = self.timesteps[::-1]
 
     def alphas(self, timestep: int):
-        """(alpha at the level the sample is currently at, alpha at the target level `timestep`)."""
-        prev = int(timestep) - self.num_train_timesteps // self.num_inference_steps
+        """(alpha of the level the sample is at, alpha of the level it moves to) for the step taken at `timestep`."""
+        ratio = self.num_train_timesteps // self.num_inference_steps
+        if self.convention == "0.19.3":
+            nxt = int(timestep) + ratio
+            a_next = float(self.alphas_cumprod[nxt]) if nxt < self.num_train_timesteps else float(self.last_alpha_cumprod)
+            return float(self.alphas_cumprod[int(timestep)]), a_next
+        prev = int(timestep) - ratio
         a_cur = float(self.alphas_cumprod[prev]) if prev >= 0 else float(self.final_alpha_cumprod)
         return a_cur, float(self.alphas_cumprod[int(timestep)])

@@ -315,10 +315,18 @@ class AnimateDiffUNet3DModel(nn.Module):
         expected = unet_param_shapes(cfg)
         mine = {k: tuple(v.shape) for k, v in super().state_dict().items()}
         assert mine == dict(expected), "internal: module tree does not match the architecture spec"
-        if init == "seeded":
-            self.load_state_dict(seeded_state_dict(expected, seed=0))
+        if init in ("seeded", "reference"):
+            sd0 = seeded_state_dict(expected, seed=0)
+            if init == "reference":
+                # the reference zero-initialises every temporal_transformer.proj_out (motion_module.py:76-77), so a motion
+                # module is an exact identity until a motion checkpoint is loaded; keys a checkpoint does not cover must
+                # keep THAT behaviour (from_pretrained_2d loads with strict=False; test.py makes the motion ckpt optional)
+                for k in sd0:
+                    if ".temporal_transformer.proj_out." in k:
+                        sd0[k] = torch.zeros_like(sd0[k])
+            self.load_state_dict(sd0)
         elif init != "empty":
-            raise ValueError("init must be 'seeded' or 'empty'")
+            raise ValueError("init must be 'seeded' (tests: non-zero motion proj_out), 'reference' or 'empty'")
         self.eval()
 
     # ------------------------------------------------------------------------------------------ reference surface
@@ -328,6 +336,7 @@ class AnimateDiffUNet3DModel(nn.Module):
         sig = inspect.signature(cls.__init__).parameters
         init = {k: v for k, v in dict(config).items() if k in sig}
         init.update({k: v for k, v in kwargs.items() if k in sig})
+        init.setdefault("init", "reference")      # zero motion proj_out like the reference's constructor
         return cls(**init)
 
     @classmethod
