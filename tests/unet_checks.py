@@ -128,7 +128,7 @@ def pipeline_vs_oracle(steps=3, Fr=2, hw=8, guidance=7.5):
     return {"psnr": psnr(nat, ref), "max_err": (nat.float().cpu() - ref).abs().max().item()}
 
 
-def _conditions(Fr, img, P=6, seed=51):
+def _conditions(Fr, img, P=24, seed=51):
     """Synthetic TAP conditions: tracks U[0, img) with some invisible, point embeddings N(0,1)."""
     g = torch.Generator().manual_seed(seed)
     tracks = torch.rand((Fr, P, 2), generator=g) * img
@@ -138,9 +138,10 @@ def _conditions(Fr, img, P=6, seed=51):
     return {"pred_tracks": tracks[None], "img_size": (img, img), "point_embedding": emb[None], "index_list": list(range(P - 1))}
 
 
-def pipeline_call_vs_oracle(iters=3, Fr=2, hw=16, guidance=7.5, t2i_scale=0.5, t2i_end=1.0 / 50):
+def pipeline_call_vs_oracle(iters=3, Fr=2, hw=16, guidance=7.5, t2i_scale=4.0, t2i_end=0.0):
     """VideoSwapPipeline.__call__ (conditions -> adapter, residual window, CFG, DDIM, final rearrange) vs the oracle's
-    restatement of pipeline_videoswap.py:525-610.  `t2i_end` = 1/50 closes the adapter window after iteration 1."""
+    restatement of pipeline_videoswap.py:525-610.  `t2i_end` = 0 closes the adapter window after iteration 0; the strong
+    t2i scale makes a wrongly open (or never opened) window cost > 15 dB against the oracle."""
     m, sd = get_model()
     ad = SparsePointAdapter(init="empty")
     asd = seeded_state_dict(adapter_param_shapes(), seed=5)
@@ -163,8 +164,10 @@ def pipeline_call_vs_oracle(iters=3, Fr=2, hw=16, guidance=7.5, t2i_scale=0.5, t
                              max_iters=iters)
         ref_no_window = O.denoise_loop(sd, O.OracleConfig(), lat.float(), pos.float(), neg.float(), 50, guidance, state, 0.0, 1.0,
                                        max_iters=iters)
+        ref_never = O.denoise_loop(sd, O.OracleConfig(), lat.float(), pos.float(), neg.float(), 50, guidance, None, 0.0, 1.0,
+                                   max_iters=iters)
     return {"psnr": psnr(out, ref), "shape": tuple(out.shape), "ref_shape": tuple(ref.shape),
-            "psnr_if_window_ignored": psnr(out, ref_no_window)}
+            "psnr_if_window_ignored": psnr(out, ref_no_window), "psnr_if_never_applied": psnr(out, ref_never)}
 
 
 def invert_vs_oracle(iters=3, Fr=2, hw=8, convention="0.19.3"):

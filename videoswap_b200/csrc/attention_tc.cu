@@ -56,6 +56,7 @@ struct TAttnArgs {
   long long o_bs;
   int nq, nk, kv_div;
   float scale_log2;
+  int heads, n_qblk, n_items;   // persistent kernel: work item = (batch, head, 256-query block), q block fastest
 };
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
@@ -363,13 +364,315 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const __grid_co
   }
 }
 
-template <int D, int HO>
+// exp2 on the FMA pipe (Cody-Waite split + cubic minimax of 2^f on [-0.5, 0.5], |rel err| <= 7.5e-5 -- below the fp16
+// rounding of P): the softmax of d = 40 attention needs 16 384 exponentials per 128 x 128 score tile against ~200 tensor
+// cycles, so the 16/clk/SM MUFU pipe is the bound; a share of the exponentials is moved onto the (idle) FMA pipe.
+__device__ __forceinline__ float exp2_fma(float x) {
+  x = fmaxf(x, -126.f);
+  const float t = x + 12582912.f;                  // 1.5 * 2^23: round(x) lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);
+  float pl = fmaf(f, 0.05517166f, 0.24261112f);
+  pl = fmaf(pl, f, 0.69326099f);
+  pl = fmaf(pl, f, 0.99992807f);
+  return __int_as_float(__float_as_int(pl) + (__float_as_int(t) << 23));   // * 2^round(x) through the exponent field
+}
+
+// PERSISTENT variant (default): one CTA per SM walks work items (batch, head, 256-query block) round-robin.  Every role
+// keeps running counters across items, so the K/V ring, the S / P double buffers and the MUFU ping-pong never drain at
+// an item boundary: the producer prefetches the next item's Q (double-buffered for d <= 64) and first K/V tiles while
+// the current item finishes, Q K^T of the next item is issued two key tiles ahead as inside an item, and a softmax
+// warpgroup writes its O tile out while the other one keeps the MUFU pipe busy.  This removes the per-CTA prologue
+// (barrier init, TMEM allocation, Q + first K/V round trip: 15 % of the softmax warps' time at N = 4096 and nearly all
+// of it for the 2-tile cross-attention CTAs) and the wave tail.  O needs no double buffering: P V of item n+1 / tile i
+// is only issued after p_full(i), which warpgroup i signals after its epilogue of item n.
+// NPOLY of the 8 sixteen-byte P chunks per key tile take their exponentials from exp2_fma instead of MUFU.EX2.
+template <int D, int HO, int NPOLY>
+__global__ void __launch_bounds__(ATT_THREADS, 1) attn_tcp_kernel(const __grid_constant__ TAttnArgs p) {
+  using C = TCfg<D>;
+  constexpr int QB = (D <= 64) ? 2 : 1;                        // Q buffers
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t q_s = base;                                   // [QB][2 tiles][NCB][128 rows x 128 B]
+  const uint32_t kv_s = q_s + QB * C::Q_BYTES;                 // [ST][K: NCB blocks | V: NCB blocks]
+  const uint32_t p_s = kv_s + C::ST * C::KV_STAGE_BYTES;       // [2 tiles][2 buffers][128 rows x 128 B]
+  const uint32_t bars = p_s + 4 * C::P_TILE_BYTES;
+  auto q_full = [&](int b) { return bars + 8u * b; };
+  auto q_empty = [&](int b) { return bars + 8u * (2 + b); };
+  auto kv_full = [&](int s) { return bars + 8u * (4 + s); };
+  auto kv_empty = [&](int s) { return bars + 8u * (4 + C::ST + s); };
+  auto v_ready = [&](int s) { return bars + 8u * (4 + 2 * C::ST + s); };
+  auto s_full = [&](int i, int b) { return bars + 8u * (4 + 3 * C::ST + 2 * i + b); };
+  auto p_full = [&](int i, int b) { return bars + 8u * (8 + 3 * C::ST + 2 * i + b); };
+  auto p_empty = [&](int i, int b) { return bars + 8u * (12 + 3 * C::ST + 2 * i + b); };
+  auto o_full = [&](int i) { return bars + 8u * (16 + 3 * C::ST + i); };
+  const uint32_t tmem_slot = bars + 8u * (18 + 3 * C::ST);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkt = (p.nk + BKV - 1) / BKV;
+  const int item0 = blockIdx.x, istep = gridDim.x;
+
+  if (warp == 0 && lane == 0) { prefetch_tmap(&p.tmQ); prefetch_tmap(&p.tmK); prefetch_tmap(&p.tmV); }
+  if (warp == 1 && lane == 0) {
+    for (int b = 0; b < 2; ++b) { mbar_init(q_full(b), 1); mbar_init(q_empty(b), 1); }
+    for (int s = 0; s < C::ST; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); mbar_init(v_ready(s), 1); }
+    for (int i = 0; i < 2; ++i) {
+      for (int bb = 0; bb < 2; ++bb) {
+        mbar_init(s_full(i, bb), 1);
+        mbar_init(p_full(i, bb), 128);
+        mbar_init(p_empty(i, bb), 1);
+      }
+      mbar_init(o_full(i), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  pdl_trigger();
+  pdl_wait();                                    // set-up above overlaps the previous kernel's tail
+
+  if (warp == 0) {
+    // ================================================================ TMA producer
+    uint32_t g = 0, n = 0;                       // running key-tile / item counters
+    for (int item = item0; item < p.n_items; item += istep, ++n) {
+      const int qblk = item % p.n_qblk, bh = item / p.n_qblk, head = bh % p.heads, b = bh / p.heads;
+      const int q0 = qblk * 2 * TQ, bk = b / p.kv_div;
+      const uint32_t qb = n % QB;
+      if (n >= (uint32_t)QB) mbar_wait(q_empty(qb), ((n / QB) - 1) & 1);    // the item that used this Q buffer issued its last Q K^T
+      if (elect_one()) {
+        mbar_expect_tx(q_full(qb), C::Q_BYTES);
+        for (int i = 0; i < 2; ++i)
+          for (int cb = 0; cb < C::NCB; ++cb)
+            tma_load_4d(q_s + qb * C::Q_BYTES + (i * C::NCB + cb) * TQ * 128, &p.tmQ, q_full(qb), cb * 64, head, q0 + i * TQ, b);
+      }
+      __syncwarp();
+      for (int j = 0; j < nkt; ++j, ++g) {
+        const uint32_t s = g % C::ST;
+        mbar_wait(kv_empty(s), ((g / C::ST) & 1) ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(kv_full(s), C::KV_STAGE_BYTES);
+          const uint32_t k_dst = kv_s + s * C::KV_STAGE_BYTES;
+          const uint32_t v_dst = k_dst + C::NCB * C::KV_BLOCK_BYTES;
+#pragma unroll
+          for (int cb = 0; cb < C::NCB; ++cb) {
+            tma_load_4d(k_dst + cb * C::KV_BLOCK_BYTES, &p.tmK, kv_full(s), cb * 64, head, j * BKV, bk);
+            tma_load_4d(v_dst + cb * C::KV_BLOCK_BYTES, &p.tmV, kv_full(s), cb * 64, head, j * BKV, bk);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================ MMA issuer
+    constexpr uint32_t idesc_qk = umma_idesc_f16(TQ, BKV);
+    constexpr uint32_t idesc_pv = umma_idesc_f16(TQ, C::DPO) | (1u << 16);   // B operand MN-major
+    const int my_items = (p.n_items - item0 + istep - 1) / istep;
+    const uint32_t total = (uint32_t)my_items * (uint32_t)nkt;               // key tiles this CTA walks
+    // Q K^T cursor: runs two key tiles ahead of the P V cursor, across item boundaries
+    uint32_t gq = 0, nq_item = 0; int jq = 0;
+    auto issue_qk = [&](int i) {
+      const uint32_t s = gq % C::ST, qb = nq_item % QB;
+      if (i == 0) {
+        if (jq == 0) mbar_wait(q_full(qb), (nq_item / QB) & 1);
+        mbar_wait(kv_full(s), (gq / C::ST) & 1);
+        tc_fence_after();
+      }
+      if (elect_one()) {
+        const uint32_t qa = q_s + qb * C::Q_BYTES + i * C::NCB * TQ * 128;
+        const uint32_t ka = kv_s + s * C::KV_STAGE_BYTES;
+#pragma unroll
+        for (int k = 0; k < C::DPK / 16; ++k) {
+          const int cb = (k * 16) / 64, off = ((k * 16) % 64) * 2;
+          tc_mma_f16(tmem + C::S_COL + (2 * i + (gq & 1)) * BKV, umma_desc_sw128_kmajor(qa + cb * TQ * 128 + off),
+                     umma_desc_sw128_kmajor(ka + cb * C::KV_BLOCK_BYTES + off), idesc_qk, k != 0 ? 1u : 0u);
+        }
+        tc_commit(s_full(i, gq & 1));
+        if (i == 1 && jq == nkt - 1) tc_commit(q_empty(qb));     // last Q K^T of this item: its Q buffer may be refilled
+      }
+      __syncwarp();
+      if (i == 1) { ++gq; if (++jq == nkt) { jq = 0; ++nq_item; } }
+    };
+    for (int a = 0; a < 2 && gq < total; ++a) { issue_qk(0); issue_qk(1); }
+    int j = 0;
+    for (uint32_t g = 0; g < total; ++g) {
+      const uint32_t s = g % C::ST, sph = (g / C::ST) & 1;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        mbar_wait(p_full(i, g & 1), (g >> 1) & 1);
+        if (i == 0) mbar_wait(v_ready(s), sph);      // ones column of this V tile is in place
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t pa = p_s + (2 * i + (g & 1)) * C::P_TILE_BYTES;
+          const uint32_t va = kv_s + s * C::KV_STAGE_BYTES + C::NCB * C::KV_BLOCK_BYTES;
+#pragma unroll
+          for (int k = 0; k < BKV / 16; ++k)
+            tc_mma_f16(tmem + C::O_COL + i * C::O_STRIDE, umma_desc_sw128_kmajor(pa + k * 32),
+                       umma_desc_sw128_mnmajor(va + k * 16 * 128, C::KV_BLOCK_BYTES), idesc_pv, (j > 0 || k != 0) ? 1u : 0u);
+          tc_commit(p_empty(i, g & 1));              // this P buffer consumed, O_i quiescent once this retires
+          if (i == 1) tc_commit(kv_empty(s));        // K_j / V_j fully consumed once these MMAs retire
+          if (j == nkt - 1) tc_commit(o_full(i));    // O_i of this item complete
+        }
+        __syncwarp();
+        if (gq < total) issue_qk(i);                 // S_{i, g&1} was drained by the softmax before it signalled p_full
+      }
+      if (++j == nkt) j = 0;
+    }
+  } else if (warp == 3) {
+    // ================================================================ ones column: V[:, D] = 1 for every landed V tile
+    constexpr int blk = D / 64, chunk = ((D % 64) * 2) / 16, within = ((D % 64) * 2) % 16;
+    const int my_items = (p.n_items - item0 + istep - 1) / istep;
+    const uint32_t total = (uint32_t)my_items * (uint32_t)nkt;
+    for (uint32_t g = 0; g < total; ++g) {
+      const uint32_t s = g % C::ST;
+      mbar_wait(kv_full(s), (g / C::ST) & 1);
+      const uint32_t v_blk = kv_s + s * C::KV_STAGE_BYTES + (C::NCB + blk) * C::KV_BLOCK_BYTES;
+#pragma unroll
+      for (int r = lane; r < BKV; r += 32) {
+        const uint32_t dst = v_blk + r * 128 + ((chunk ^ (r & 7)) << 4) + within;
+        asm volatile("st.shared.b16 [%0], %1;" ::"r"(dst), "h"((unsigned short)0x3C00) : "memory");   // fp16 1.0
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(v_ready(s));
+    }
+  } else if (warp >= 4) {
+    // ================================================================ softmax warpgroups + epilogue
+    const int i = (warp - 4) >> 2;               // query tile handled by this warpgroup
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;         // query row inside the tile == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    const uint32_t o_addr = tmem + lane_addr + C::O_COL + i * C::O_STRIDE;
+    const uint32_t p_row0 = p_s + 2 * i * C::P_TILE_BYTES + row * 128;
+    const float sc = p.scale_log2;
+    if (i == 1) named_bar_arrive(9 + 0, 256);    // warpgroup 0 goes first on the MUFU pipe
+    uint32_t g = 0, n = 0;
+    for (int item = item0; item < p.n_items; item += istep, ++n) {
+      const int qblk = item % p.n_qblk, bh = item / p.n_qblk, head = bh % p.heads, b = bh / p.heads;
+      float m_used = -INFINITY;
+      for (int j = 0; j < nkt; ++j, ++g) {
+        mbar_wait(s_full(i, g & 1), (g >> 1) & 1);
+        tc_fence_after();
+        const int kbase = j * BKV;
+        uint32_t sv[BKV];
+        const uint32_t s_addr = tmem + lane_addr + C::S_COL + (2 * i + (g & 1)) * BKV;
+        tmem_ld32(s_addr, sv);
+        tmem_ld32(s_addr + 32, sv + 32);
+        tmem_ld_wait();
+        if (kbase + BKV > p.nk) {   // keys beyond nk were zero-filled by TMA: mask them (last tile only)
+#pragma unroll
+          for (int t = 0; t < BKV; ++t)
+            if (kbase + t >= p.nk) sv[t] = 0xff800000u;   // -inf
+        }
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int t = 0; t < BKV; t += 8) {
+          mx0 = fmax3(mx0, __uint_as_float(sv[t]), __uint_as_float(sv[t + 1]));
+          mx1 = fmax3(mx1, __uint_as_float(sv[t + 2]), __uint_as_float(sv[t + 3]));
+          mx2 = fmax3(mx2, __uint_as_float(sv[t + 4]), __uint_as_float(sv[t + 5]));
+          mx3 = fmax3(mx3, __uint_as_float(sv[t + 6]), __uint_as_float(sv[t + 7]));
+        }
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        // lazy rescale: only when the maximum moved by more than 2^8 (always "needed" on the first tile: m_used = -inf,
+        // but there O is overwritten by the non-accumulating P V, so nothing is rescaled)
+        const bool need = (mx - m_used) * sc > 8.f;
+        if (j > 0 && __any_sync(0xffffffffu, need)) {
+          mbar_wait(p_empty(i, (g - 1) & 1), ((g - 1) >> 1) & 1);       // O_i quiescent: the previous P V has retired
+          tc_fence_after();
+          const float alpha = need ? exp2f((m_used - mx) * sc) : 1.f;   // also rescales the row-sum column O[:, D]
+#pragma unroll 1
+          for (int c0 = 0; c0 < C::DPO; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(o_addr + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int t = 0; t < 16; ++t) v[t] = __float_as_uint(__uint_as_float(v[t]) * alpha);
+            tmem_st16(o_addr + c0, v);
+          }
+          tmem_st_wait();
+        }
+        if (need) m_used = mx;
+        const float ms = m_used * sc;
+        if (g >= 2) mbar_wait(p_empty(i, g & 1), ((g - 2) >> 1) & 1);   // this P buffer was consumed two key tiles ago
+        const uint32_t p_row = p_row0 + (g & 1) * C::P_TILE_BYTES;
+        named_bar_sync(9 + i, 256);                                       // my turn on the MUFU pipe
+#pragma unroll
+        for (int c8 = 0; c8 < BKV / 8; ++c8) {       // one 16-byte chunk (8 keys) at a time
+          // chunks spread evenly over the tile take the FMA-pipe exponential (NPOLY of 8)
+          const bool poly = ((c8 + 1) * NPOLY) / 8 > (c8 * NPOLY) / 8;      // compile-time after unrolling
+          uint32_t pk[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float x0 = __uint_as_float(sv[c8 * 8 + 2 * u]) * sc - ms, x1 = __uint_as_float(sv[c8 * 8 + 2 * u + 1]) * sc - ms;
+            const float e0 = poly ? exp2_fma(x0) : fast_exp2(x0);
+            const float e1 = poly ? exp2_fma(x1) : fast_exp2(x1);
+            const __half2 h = __floats2half2_rn(e0, e1);   // the row sum is formed by the MMA from these rounded values
+            pk[u] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          const uint32_t dst = p_row + ((c8 ^ (row & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
+                       : "memory");
+          if (c8 == HO) named_bar_arrive(9 + (i ^ 1), 256);   // hand the MUFU pipe over a little early (wake-up latency)
+        }
+        fence_proxy_async();                     // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+        tc_fence_before();
+        mbar_arrive(p_full(i, g & 1));
+      }
+      // ---- epilogue of this item: O / l -> fp16 -> HBM (the other warpgroup keeps the MUFU pipe busy meanwhile)
+      mbar_wait(o_full(i), n & 1);
+      tc_fence_after();
+      const int qrow = qblk * 2 * TQ + i * TQ + row;
+      float inv;
+      {   // softmax denominator = the ones column of the accumulator
+        uint32_t v[16];
+        tmem_ld16(o_addr + (D / 16) * 16, v);
+        tmem_ld_wait();
+        inv = 1.f / __uint_as_float(v[D % 16]);
+      }
+      __half* orow = p.o + b * p.o_bs + (long long)qrow * p.ldo + head * D;
+#pragma unroll 1
+      for (int c0 = 0; c0 < C::DPO; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(o_addr + c0, v);
+        tmem_ld_wait();
+        if (qrow < p.nq) {
+#pragma unroll
+          for (int t = 0; t < 16; t += 8) {
+            if (c0 + t < D) {
+              uint4 o4;
+              __half2* h = reinterpret_cast<__half2*>(&o4);
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                h[u] = __floats2half2_rn(__uint_as_float(v[t + 2 * u]) * inv, __uint_as_float(v[t + 2 * u + 1]) * inv);
+              *reinterpret_cast<uint4*>(orow + c0 + t) = o4;
+            }
+          }
+        }
+      }
+      tc_fence_before();                         // the O reads above are ordered before this warpgroup's next p_full arrive
+    }
+    if (i == 0) named_bar_sync(9 + 0, 256);      // absorb the other warpgroup's last hand-over
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem, C::TMEM_COLS);
+  }
+}
+
+template <int D, int HO, int NPOLY, bool PERSIST>
 int launch(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv, __half* o, int ldo,
            int batch, int nq, int nk, int heads, long long q_bs, long long kv_bs, long long o_bs, int kv_div) {
   using C = TCfg<D>;
+  constexpr int SMEM_P = C::SMEM + ((D <= 64) ? C::Q_BYTES : 0) + 64;      // persistent: second Q buffer, more barriers
+  static_assert(SMEM_P <= 227 * 1024, "shared memory budget (persistent)");
   static bool configured = false;
   if (!configured) {
-    VS_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D, HO>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+    if constexpr (PERSIST) VS_CHECK_CUDA(cudaFuncSetAttribute(attn_tcp_kernel<D, HO, NPOLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_P));
+    else VS_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D, HO>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     configured = true;
   }
   TAttnArgs a;
@@ -391,9 +694,18 @@ int launch(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, 
   }
   a.o = o; a.ldo = ldo; a.o_bs = o_bs; a.nq = nq; a.nk = nk; a.kv_div = kv_div;
   a.scale_log2 = 1.4426950408889634f / sqrtf((float)D);
-  dim3 grid((nq + 2 * TQ - 1) / (2 * TQ), heads, batch);
+  a.heads = heads;
+  a.n_qblk = (nq + 2 * TQ - 1) / (2 * TQ);
+  a.n_items = a.n_qblk * heads * batch;
   ProfScope prof(st, PC_ATTN, 4.0 * batch * heads * (double)nq * nk * D, 1, nq, nk, D);
-  return launch_pdl(attn_tc_kernel<D, HO>, grid, dim3(ATT_THREADS), C::SMEM, st, 1, a);
+  if constexpr (PERSIST) {
+    const int ctas = a.n_items < num_sms() ? a.n_items : num_sms();
+    return launch_pdl(attn_tcp_kernel<D, HO, NPOLY>, dim3(ctas), dim3(ATT_THREADS), SMEM_P, st, 1, a);
+  }
+  else {
+    dim3 grid(a.n_qblk, heads, batch);
+    return launch_pdl(attn_tc_kernel<D, HO>, grid, dim3(ATT_THREADS), C::SMEM, st, 1, a);
+  }
 }
 
 }  // namespace
@@ -408,8 +720,23 @@ int attention_tc(cudaStream_t st, const __half* q, int ldq, const __half* k, int
   // "attn_handoff" (A/B switch): 1 = the softmax ping-pong hands the MUFU pipe over after key chunk 6 of 8 (L0 self-
   // attention 1549 us), 0 = after the last exponential (1607 us; interleaved repetitions on one box).
   const bool early = get_option("attn_handoff") != 0;
-  if (d == 40) return early ? launch<40, 6>(VS_ATT_ARGS) : launch<40, 7>(VS_ATT_ARGS);
-  if (d == 80) return early ? launch<80, 6>(VS_ATT_ARGS) : launch<80, 7>(VS_ATT_ARGS);
+  // "attn_persist" (default 1): persistent CTAs; 0 = one CTA per (batch, head, 256 queries) as in round 1 (A/B switch).
+  // "attn_poly": how many of the 8 P chunks per key tile take exp2 from the FMA pipe (0, 1, 2, 3; persistent kernel only).
+  if (get_option("attn_persist") != 0) {
+    const int np = get_option("attn_poly");
+    if (d == 40) {
+      switch (np) {
+        case 0: return launch<40, 6, 0, true>(VS_ATT_ARGS);
+        case 1: return launch<40, 6, 1, true>(VS_ATT_ARGS);
+        case 3: return launch<40, 6, 3, true>(VS_ATT_ARGS);
+        default: return launch<40, 6, 2, true>(VS_ATT_ARGS);
+      }
+    }
+    if (d == 80) return np > 0 ? launch<80, 6, 2, true>(VS_ATT_ARGS) : launch<80, 6, 0, true>(VS_ATT_ARGS);
+    return -1;
+  }
+  if (d == 40) return early ? launch<40, 6, 0, false>(VS_ATT_ARGS) : launch<40, 7, 0, false>(VS_ATT_ARGS);
+  if (d == 80) return early ? launch<80, 6, 0, false>(VS_ATT_ARGS) : launch<80, 7, 0, false>(VS_ATT_ARGS);
 #undef VS_ATT_ARGS
   return -1;
 }

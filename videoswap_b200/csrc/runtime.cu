@@ -116,6 +116,8 @@ ProfScope::~ProfScope() {
 struct Option { const char* name; int value; };
 static Option g_options[] = {
     {"attn_tc", 1},        // tcgen05 attention for d = 40 / 80 (0 = mma.sync kernel)
+    {"attn_persist", 1},   // persistent tcgen05 attention (work items walked by one CTA per SM); 0 = one CTA per item
+    {"attn_poly", 0},      // P chunks (of 8 per key tile) whose exp2 runs on the FMA pipe instead of MUFU (0..3)
     {"attn_handoff", 1},   // 1: the softmax ping-pong hands the MUFU pipe over after 7 of 8 key chunks, 0: after the last
     {"gemm_pair", 1},      // CTA pairs (cta_group::2, 256-row tiles): 1 = for K >= 768, 0 = never, 2 = whenever possible
     {"gemm_stages", 0},    // smem ring depth limit (0 = all)
