@@ -77,6 +77,23 @@ size_t vs_unet_workspace_bytes(const vs_unet* h);
  * arena for a shape ahead of time (e.g. the CFG batch before the B = 1 inversion graph is captured). */
 int vs_unet_pin_workspace(vs_unet* h, int pin);
 int vs_unet_reserve_workspace(vs_unet* h, int B, int F, int H, int W);
+/* ---- multi-GPU (the reference has no inference-time parallelism) --------------------------------------
+ * One process per GPU.  A vs_comm wraps one NCCL communicator (bound at run time with dlopen); the caller distributes
+ * the 128-byte unique id (e.g. torch.distributed broadcast) and calls vs_comm_create on every rank of the group.
+ * Frame sharding: rank `shard` of `nshards` holds frames [shard F/k, (shard+1) F/k) of ONE batch element and passes that
+ * LOCAL frame count to vs_unet_forward.  Per forward the library exchanges (i) the (sum, sum of squares) of the 45
+ * cross-frame GroupNorms (all-reduce of 64 floats each) and (ii) a frames <-> pixels all-to-all around each of the 20
+ * motion modules; everything else is per frame.  The two CFG halves live on two such groups and swap their noise
+ * predictions with vs_comm_all_gather before vs_cfg_ddim_step.  All exchanges are asynchronous on `stream` and CUDA-
+ * graph capturable. */
+typedef struct vs_comm vs_comm;
+int vs_comm_unique_id(void* out128);
+int vs_comm_create(const void* id128, int rank, int nranks, vs_comm** out);
+void vs_comm_destroy(vs_comm* c);
+int vs_comm_all_gather(vs_comm* c, void* stream, const void* d_send, void* d_recv, size_t bytes_per_rank);
+int vs_comm_all_reduce_sum_f32(vs_comm* c, void* stream, float* d_buf, size_t n);
+int vs_unet_set_frame_shard(vs_unet* h, vs_comm* frame_comm, int shard, int nshards);
+
 /* Debug taps: after the next forward, copies of named intermediate activations (NHWC fp16) can be fetched. */
 int vs_unet_enable_taps(vs_unet* h, int enable);
 int vs_unet_num_taps(const vs_unet* h);
@@ -123,6 +140,14 @@ int vs_layernorm(void* stream, const void* d_x, int rows, int C, const float* d_
 int vs_ln_linear(void* stream, const void* d_x, int M, int C, const void* d_w, const float* d_bias, int N,
                  const float* d_gamma, const float* d_beta, const float* d_pe, int pe_len, int hw, int frames, int mode,
                  void* d_wf, float* d_u, float* d_c, float* d_cpe, float* d_stats, void* d_out);
+/* The form the UNet forward uses: the linear layer that PRODUCES the LayerNorm's input (x = x0 W0^T + b0 (+ residual),
+ * fp16, written to d_x) also emits the per-row (sum, sum of squares) of what it stores, one slice per column tile of its
+ * epilogue (d_parts: [parts_capacity][M][2] fp32), and the consuming GEMM derives mean / rstd from those slices -- no
+ * statistics pass over x (attention.py:229-256 / motion_module.py:224-234: proj_in -> norm1 -> to_q/k/v, ...). */
+int vs_linear_ln_linear(void* stream, const void* d_x0, int M, int K0, const void* d_w0, const float* d_b0,
+                        const void* d_residual, int C, void* d_x, const void* d_w, const float* d_bias, int N,
+                        const float* d_gamma, const float* d_beta, int mode, void* d_wf, float* d_u, float* d_c,
+                        float* d_parts, int parts_capacity, void* d_out);
 int vs_attention(void* stream, const void* d_q, int ldq, const void* d_k, int ldk, const void* d_v, int ldv, void* d_o,
                  int ldo, int batch, int nq, int nk, int heads, int d, long long q_bstride, long long kv_bstride,
                  long long o_bstride, int kv_div);
@@ -146,7 +171,10 @@ int vs_profile_dump(const char* path);   /* CSV: category, shape (m,n,k), work p
  *   "attn_handoff" 1  softmax warpgroups hand the MUFU pipe over after 7 of 8 key chunks; 0 = after the last one
  *   "gemm_pair"    1  CTA pairs (cta_group::2, 256-row tiles) for K >= 768; 0 = never; 2 = whenever >= 2 row tiles
  *   "gemm_stages"  0  limit of the shared-memory ring depth of the GEMM (0 = as many as fit)
+ *   "attn_persist" 1  persistent tcgen05 attention (one CTA per SM walks the work items); 0 = one CTA per work item
+ *   "attn_poly"    0  P chunks (of 8 per key tile) whose exp2 runs on the FMA pipe instead of MUFU.EX2 (0..3)
  *   "ln_fold"      1  LayerNorms folded into the consuming GEMM; 0 = stand-alone LayerNorm kernel
+ *   "ln_fuse"      1  row statistics of folded LayerNorms written by the producing GEMM's epilogue; 0 = ln_stats pass
  *   "pdl"          1  programmatic dependent launch between the hot kernels; 0 = plain stream order */
 int vs_set_option(const char* name, int value);
 

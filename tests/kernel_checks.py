@@ -207,6 +207,38 @@ def check_ln_linear(rows=2000, C=320, N=960, pe=False, geglu=False, seed=115, hw
     return _res(out, ref)
 
 
+def check_linear_ln_linear(rows=2000, K0=320, C=320, N=960, residual=False, geglu=False, seed=160, mean=0.7):
+    """Producer GEMM (row statistics from its epilogue) -> LayerNorm folded into the consumer GEMM, vs fp32 torch on the
+    fp16 intermediate the producer actually stored."""
+    x0 = (_rand((rows, K0), seed) * 2).half()
+    W0 = _rand((C, K0), seed + 1, 1 / math.sqrt(K0)).half()
+    b0 = (_rand((C,), seed + 2) + mean).float()
+    R = (_rand((rows, C), seed + 3) * 1.5 - 0.4).half() if residual else None
+    gamma = (1 + 0.1 * _rand((C,), seed + 4)).float()
+    beta = (0.1 * _rand((C,), seed + 5)).float()
+    W = _rand((N, C), seed + 6, 1 / math.sqrt(C)).half()
+    b = _rand((N,), seed + 7).float() if geglu else None
+    if geglu:
+        Wp, bp = ops.pack_geglu(W, b.half())
+        x, out = ops.linear_ln_linear(x0, W0, b0, Wp, gamma, beta, residual=R, bias=bp, mode=ops.EPI_GEGLU)
+    else:
+        x, out = ops.linear_ln_linear(x0, W0, b0, W, gamma, beta, residual=R)
+    xr = x0.float() @ W0.float().t() + b0
+    if residual:
+        xr = xr.half().float() + R.float()
+    r1 = _res(x, xr)
+    y = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
+    ref = y @ W.float().t()
+    if geglu:
+        ref = ref + b.half().float()
+        h = N // 2
+        ref = ref[:, :h] * F.gelu(ref[:, h:])
+    r2 = _res(out, ref)
+    r2["ok"] = r2["ok"] and r1["ok"]
+    r2["producer_err"] = r1["err"]
+    return r2
+
+
 # ---------------------------------------------------------------------------------------------------- attention
 def _mha_ref(q, k, v, heads):
     B, nq, C = q.shape
@@ -298,6 +330,16 @@ CHECKS = {
     "gemm_149_tiles": lambda: check_gemm(128 * 149, 128, 128, residual=True, seed=11),
     # tcgen05 attention variants kept for A/B measurements: late hand-over of the MUFU pipe
     "self_attn_d40_late_handoff": with_option("attn_handoff", 0, lambda: check_self_attention(B=2, N=600, C=320, seed=121), 1),
+    # round-1 kernel (one CTA per work item) kept behind "attn_persist" = 0; FMA-pipe exponentials ("attn_poly") on the
+    # persistent kernel; more work items than SMs so that every CTA walks several items (148 SMs: 2*8*24 = 384 items)
+    "self_attn_d40_nonpersistent": with_option("attn_persist", 0, lambda: check_self_attention(B=2, N=600, C=320, seed=121), 1),
+    "self_attn_d80_nonpersistent": with_option("attn_persist", 0, lambda: check_self_attention(B=2, N=300, C=640, seed=123), 1),
+    "self_attn_d40_poly2": with_option("attn_poly", 2, lambda: check_self_attention(B=2, N=4096, C=320, seed=124), 0),
+    "self_attn_d40_poly3": with_option("attn_poly", 3, lambda: check_self_attention(B=3, N=700, C=320, seed=127), 0),
+    "self_attn_d80_poly2": with_option("attn_poly", 2, lambda: check_self_attention(B=2, N=1024, C=640, seed=126), 0),
+    "self_attn_d40_many_items": lambda: check_self_attention(B=2, N=6144, C=320, seed=128),
+    "self_attn_d80_many_items_odd_tiles": lambda: check_self_attention(B=6, N=1100, C=640, seed=129),     # nkt = 18, 5 q blocks
+    "cross_attn_d80_many_items": lambda: check_cross_attention(B=2, Fr=8, N=1024, C=640, seed=133),
     "gemm_bn160": lambda: check_gemm(512, 320, 320),
     "gemm_bn128_tail": lambda: check_gemm(300, 768, 320, bn=128),
     "gemm_bn64": lambda: check_gemm(130, 64, 128, bn=64),
@@ -335,6 +377,12 @@ CHECKS = {
     "ln_fold_q_1280": lambda: check_ln_linear(rows=700, C=1280, N=1280, seed=117),
     "ln_fold_geglu_320": lambda: check_ln_linear(rows=1500, C=320, N=2560, geglu=True, seed=118),
     "ln_fold_pe_mixed_warps": lambda: check_ln_linear(rows=40 * 7, C=320, N=960, pe=True, seed=119),
+    # LayerNorm statistics emitted by the producing GEMM's epilogue (2 / 3 / 5 column tiles, residual, ragged rows, GEGLU)
+    "ln_fuse_320_proj_in": lambda: check_linear_ln_linear(),
+    "ln_fuse_320_res": lambda: check_linear_ln_linear(rows=128 * 150 + 37, residual=True, N=320, seed=161, mean=2.0),
+    "ln_fuse_640_res_geglu": lambda: check_linear_ln_linear(rows=3000, K0=640, C=640, N=5120, residual=True, geglu=True, seed=162),
+    "ln_fuse_1280_res": lambda: check_linear_ln_linear(rows=700, K0=1280, C=1280, N=3840, residual=True, seed=163, mean=-1.5),
+    "ln_fuse_1280_pair": lambda: check_linear_ln_linear(rows=8192, K0=1280, C=1280, N=1280, residual=True, seed=164),
     "ln_320": lambda: check_layernorm(C=320),
     "ln_1280_pe": lambda: check_layernorm(rows=640, C=1280, pe=True),
     "self_attn_d40": lambda: check_self_attention(C=320),

@@ -1,4 +1,7 @@
-"""A/B of attention kernel options on one box: interleaved repetitions, medians.  usage: gpu_attn_ab.py name=v1,v2,... [reps]"""
+"""A/B of attention kernel options on one box: interleaved repetitions, medians.
+usage: gpu_attn_ab.py [--reps N] cfg [cfg ...]   with cfg = name=v[:name=v...], e.g.  attn_persist=0  attn_persist=1:attn_poly=2
+Shapes: the C2 launches (BF = 32): L0 self (88 % of the attention FLOPs), L0 cross (77 keys), L1 self, L1 cross."""
+import json
 import os
 import sys
 
@@ -8,26 +11,49 @@ import torch  # noqa: E402
 
 from videoswap_b200 import ops  # noqa: E402
 
-name, vals = sys.argv[1].split("=")
-vals = [int(v) for v in vals.split(",")]
-reps = int(sys.argv[2]) if len(sys.argv) > 2 else 15
+args = sys.argv[1:]
+reps = 11
+if args and args[0] == "--reps":
+    reps = int(args[1])
+    args = args[2:]
+cfgs = [dict((kv.split("=")[0], int(kv.split("=")[1])) for kv in a.split(":")) for a in args]
+names = sorted({k for c in cfgs for k in c})
 dev = "cuda"
-shapes = {"L0 self 4096x4096 d40": (32, 4096, 320), "L1 self 1024x1024 d80": (32, 1024, 640)}
-for label, (B, N, C) in shapes.items():
-    qkv = torch.randn(B, N, 3 * C, device=dev).half()
-    q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
-    times = {x: [] for x in vals}
+shapes = {"L0 self 4096x4096 d40": (32, 4096, 4096, 320, 1), "L0 cross 4096x77 d40": (32, 4096, 77, 320, 16),
+          "L1 self 1024x1024 d80": (32, 1024, 1024, 640, 1), "L1 cross 1024x77 d80": (32, 1024, 77, 640, 16)}
+out = {}
+for label, (B, N, NK, C, kvdiv) in shapes.items():
+    if NK == N:
+        qkv = torch.randn(B, N, 3 * C, device=dev).half()
+        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    else:
+        q = torch.randn(B, N, C, device=dev).half()
+        kv = torch.randn(B // kvdiv, NK, 2 * C, device=dev).half()
+        k, v = kv[..., :C], kv[..., C:]
+    times = [[] for _ in cfgs]
+    ref = None
     for r in range(reps + 2):
-        for x in vals:
-            ops.set_option(name, x)
+        for ci, c in enumerate(cfgs):
+            for n in names:
+                ops.set_option(n, c.get(n, {"attn_persist": 1, "attn_poly": 0, "attn_handoff": 1, "attn_tc": 1}.get(n, 0)))
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            ops.attention(q, k, v, 8)
+            o = ops.attention(q, k, v, 8, kv_div=kvdiv)
             b.record()
             torch.cuda.synchronize()
+            if r == 0:
+                if ref is None:
+                    ref = o.float()
+                else:
+                    d = (o.float() - ref).abs().max().item()
+                    assert d < 2e-2, (label, c, d)          # variants agree with each other (parity proper: kernel checks)
             if r >= 2:
-                times[x].append(a.elapsed_time(b) * 1e3)
-    flops = 4.0 * B * 8 * N * N * (C // 8)
-    for x in vals:
-        t = sorted(times[x])[len(times[x]) // 2]
-        print(f"{label}: {name}={x}: median {t:8.1f} us  ({flops / t / 1e6:6.1f} TFLOP/s)  min {min(times[x]):8.1f}", flush=True)
+                times[ci].append(a.elapsed_time(b) * 1e3)
+    flops = 4.0 * B * 8 * N * NK * (C // 8)
+    for ci, c in enumerate(cfgs):
+        t = sorted(times[ci])[len(times[ci]) // 2]
+        out[f"{label} | {args[ci]}"] = {"median_us": t, "min_us": min(times[ci]), "tflops": flops / t / 1e6}
+        print(f"{label}: {args[ci]}: median {t:8.1f} us  ({flops / t / 1e6:6.1f} TFLOP/s)  min {min(times[ci]):8.1f}", flush=True)
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+with open(os.path.join(ROOT, "gpurun_out", "attn_ab.json"), "w") as f:
+    json.dump(out, f, indent=1)

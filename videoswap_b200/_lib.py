@@ -46,6 +46,12 @@ _SIGNATURES = {
     "vs_unet_workspace_bytes": (_SZ, [_P]),
     "vs_unet_pin_workspace": (_I, [_P, _I]),
     "vs_unet_reserve_workspace": (_I, [_P, _I, _I, _I, _I]),
+    "vs_comm_unique_id": (_I, [_P]),
+    "vs_comm_create": (_I, [_P, _I, _I, C.POINTER(_P)]),
+    "vs_comm_destroy": (None, [_P]),
+    "vs_comm_all_gather": (_I, [_P, _P, _P, _P, _SZ]),
+    "vs_comm_all_reduce_sum_f32": (_I, [_P, _P, _P, _SZ]),
+    "vs_unet_set_frame_shard": (_I, [_P, _P, _I, _I]),
     "vs_unet_enable_taps": (_I, [_P, _I]),
     "vs_unet_num_taps": (_I, [_P]),
     "vs_unet_get_tap": (_I, [_P, _I, C.POINTER(C.c_char_p), C.POINTER(_P), C.POINTER(_I), C.POINTER(_I), C.POINTER(_I),
@@ -67,6 +73,7 @@ _SIGNATURES = {
     "vs_groupnorm": (_I, [_P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _P, _P, _I, _P, _P]),
     "vs_layernorm": (_I, [_P, _P, _I, _I, _P, _P, _P, _I, _I, _P]),
     "vs_ln_linear": (_I, [_P, _P, _I, _I, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "vs_linear_ln_linear": (_I, [_P, _P, _I, _I, _P, _P, _P, _I, _P, _P, _P, _I, _P, _P, _I, _P, _P, _P, _P, _I, _P]),
     "vs_attention": (_I, [_P, _P, _I, _P, _I, _P, _I, _P, _I, _I, _I, _I, _I, _I, _LL, _LL, _LL, _I]),
     "vs_temporal_attention": (_I, [_P, _P, _P, _I, _I, _I, _I, _I]),
     "vs_conv_in": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _P]),

@@ -93,6 +93,23 @@ extern "C" int vs_ln_linear(void* stream, const void* d_x, int M, int C, const v
   if (d_pe) { g.rowvec = d_cpe; g.ldrv = N; g.pix_per_batch = hw; g.rv_mod = frames; }
   return gemm_tc(st, g);
 }
+extern "C" int vs_linear_ln_linear(void* stream, const void* d_x0, int M, int K0, const void* d_w0, const float* d_b0,
+                                   const void* d_residual, int C, void* d_x, const void* d_w, const float* d_bias, int N,
+                                   const float* d_gamma, const float* d_beta, int mode, void* d_wf, float* d_u, float* d_c,
+                                   float* d_parts, int parts_capacity, void* d_out) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int e = ln_fold(st, (const __half*)d_w, N, C, d_gamma, d_beta, d_bias, nullptr, 0, (__half*)d_wf, d_u, d_c, nullptr)) return e;
+  GemmArgs g0;                                  // producer: x = x0 W0^T + b0 (+ residual), row statistics from its epilogue
+  g0.A = (const __half*)d_x0; g0.K1 = K0; g0.lda1 = K0; g0.Bw = (const __half*)d_w0; g0.M = M; g0.N = C; g0.bias = d_b0;
+  g0.residual = (const __half*)d_residual; g0.ldr = C; g0.out = (__half*)d_x; g0.ldc = C; g0.ln_sums_out = d_parts;
+  const int parts = gemm_n_tiles(g0);
+  VS_REQUIRE(parts >= 1 && parts <= parts_capacity, "vs_linear_ln_linear: %d partial-sum slices do not fit the buffer (%d)", parts, parts_capacity);
+  if (int e = gemm_tc(st, g0)) return e;
+  GemmArgs g;                                   // consumer: LayerNorm(x) folded into this GEMM, statistics from the slices
+  g.A = (const __half*)d_x; g.K1 = C; g.lda1 = C; g.Bw = (const __half*)d_wf; g.M = M; g.N = N; g.bias = d_c;
+  g.ln_parts = d_parts; g.ln_nparts = parts; g.ln_u = d_u; g.out = (__half*)d_out; g.ldc = mode == EPI_GEGLU ? N / 2 : N; g.mode = mode;
+  return gemm_tc(st, g);
+}
 extern "C" int vs_attention(void* stream, const void* d_q, int ldq, const void* d_k, int ldk, const void* d_v, int ldv,
                             void* d_o, int ldo, int batch, int nq, int nk, int heads, int d, long long q_bstride,
                             long long kv_bstride, long long o_bstride, int kv_div) {

@@ -40,7 +40,7 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int EPI_COLS = 32;                        // output columns per epilogue sub-tile (64 B of fp16: SWIZZLE_64B)
 constexpr int EPI_WARP_BYTES = 4096;                // per epilogue warp: 2 KB transpose staging + 1 KB bias + 1 KB LN-fold slice
 constexpr int EPI_BYTES = 8 * EPI_WARP_BYTES;
-enum { EPI_F_GEGLU = 1, EPI_F_RES = 2, EPI_F_RV = 4, EPI_F_LN = 8 };   // compile-time epilogue features
+enum { EPI_F_GEGLU = 1, EPI_F_RES = 2, EPI_F_RV = 4, EPI_F_LN = 8, EPI_F_LNOUT = 16 };   // compile-time epilogue features
 
 struct GemmParams {
   CUtensorMap tmA, tmA2, tmB;
@@ -60,6 +60,10 @@ struct GemmParams {
   int rv_mod;        // row-vector index = (pix / pix_per_batch) % rv_mod when > 0 (per-frame vectors)
   const float2* ln_stats;   // folded LayerNorm: per-row (rstd, -mean * rstd)
   const float* ln_u;        // ... and per-column sum of the gamma-scaled weight row
+  const float2* ln_parts;   // alternative to ln_stats: [ln_nparts][M] per-row partial (sum, sum of squares) written by the
+  int ln_nparts;            // epilogue of the GEMM that PRODUCED this GEMM's A operand (ln_sums_out below)
+  float ln_inv_c;           // 1 / (LayerNorm width)
+  float2* ln_sums_out;      // EPI_F_LNOUT: [n_tiles][M] per-row (sum, sum of squares) of this tile's stored fp16 outputs
   const __half* residual;
   int ldr;
   __half* out;
@@ -100,6 +104,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   // LN: the A operand is the RAW input of a LayerNorm whose affine map is folded into the weights:
   //   LN(x) W^T = rstd (x W'^T) - rstd mean u + c,  W' = W * gamma, u[n] = sum_k W'[n,k], c = beta W^T + bias (the `bias`)
   constexpr bool LN = (EPI & EPI_F_LN) != 0;
+  // LNOUT: this GEMM's output feeds a LayerNorm (folded into the NEXT GEMM): the row statistics of what is stored -- the
+  // fp16-rounded values, after the residual add -- are accumulated here, in the shadow of the store path, and written as
+  // one (sum, sum of squares) pair per (column tile, row).  Deterministic (no atomics); replaces the stand-alone
+  // ln_stats_kernel pass, which re-read every such tensor from HBM (4.5 GB per step).
+  constexpr bool LNOUT = (EPI & EPI_F_LNOUT) != 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t epi_base = smem_base + C::STAGES * C::STAGE_BYTES;
@@ -298,9 +307,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         }
         float la = 1.f, lb = 0.f;           // folded LayerNorm: row scale and row shift factor
         if (LN && pix >= 0) {
-          const float2 st2 = __ldg(p.ln_stats + pix);
-          la = st2.x; lb = st2.y;
+          if (p.ln_nparts > 0) {            // statistics from the producer GEMM's per-column-tile partial sums
+            float S = 0.f, Q = 0.f;
+            for (int k = 0; k < p.ln_nparts; ++k) {
+              const float2 v = __ldg(p.ln_parts + (long long)k * p.M + pix);
+              S += v.x; Q += v.y;
+            }
+            const float mean = S * p.ln_inv_c;
+            la = rsqrtf(fmaxf(fmaf(-mean, mean, Q * p.ln_inv_c), 0.f) + 1e-5f);
+            lb = -mean * la;
+          } else {
+            const float2 st2 = __ldg(p.ln_stats + pix);
+            la = st2.x; lb = st2.y;
+          }
         }
+        float rs[4] = {0.f, 0.f, 0.f, 0.f}, rq[4] = {0.f, 0.f, 0.f, 0.f};   // LNOUT: sums of the 4 rows this lane stores
         int tpix[4];                        // pixels of the rows this lane stores after the transpose
 #pragma unroll
         for (int i = 0; i < 4; ++i) tpix[i] = __shfl_sync(0xffffffffu, pix, i * 8 + tr);
@@ -437,6 +458,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
               for (int u = 0; u < 4; ++u) oh[u] = __hadd2(oh[u], rh[u]);
             }
             if (tpix[i] >= 0) *reinterpret_cast<uint4*>(p.out + (long long)tpix[i] * p.ldc + col) = o;
+            if (LNOUT) {                      // off the store's critical path: 8 values of row i*8+tr
+              const __half2* oh = reinterpret_cast<const __half2*>(&o);
+              const float2 a = __half22float2(oh[0]), b = __half22float2(oh[1]), c = __half22float2(oh[2]), d = __half22float2(oh[3]);
+              rs[i] += ((a.x + a.y) + (b.x + b.y)) + ((c.x + c.y) + (d.x + d.y));
+              float q0 = fmaf(a.x, a.x, a.y * a.y), q1 = fmaf(b.x, b.x, b.y * b.y);
+              float q2 = fmaf(c.x, c.x, c.y * c.y), q3 = fmaf(d.x, d.x, d.y * d.y);
+              rq[i] += (q0 + q1) + (q2 + q3);
+            }
+          }
+        }
+        if (LNOUT) {                          // the 4 column chunks of a row sit in 4 adjacent lanes
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], 1); rq[i] += __shfl_xor_sync(0xffffffffu, rq[i], 1);
+            rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], 2); rq[i] += __shfl_xor_sync(0xffffffffu, rq[i], 2);
+            if (tch == 0 && tpix[i] >= 0) p.ln_sums_out[(long long)n_tile * p.M + tpix[i]] = make_float2(rs[i], rq[i]);
           }
         }
       } else {
@@ -522,14 +559,18 @@ int launch(cudaStream_t st, const GemmParams& p) {
 
 template <int BN, bool PAIR>
 int launch_linear(cudaStream_t st, const GemmParams& p) {
-  const int epi = (p.residual ? EPI_F_RES : 0) | (p.rowvec ? EPI_F_RV : 0) | (p.ln_stats ? EPI_F_LN : 0);
+  const int epi = (p.residual ? EPI_F_RES : 0) | (p.rowvec ? EPI_F_RV : 0) | ((p.ln_stats || p.ln_parts) ? EPI_F_LN : 0) |
+                  (p.ln_sums_out ? EPI_F_LNOUT : 0);
   switch (epi) {
+    case EPI_F_LNOUT: return launch<BN, EPI_F_LNOUT, PAIR>(st, p);
+    case EPI_F_LNOUT | EPI_F_RES: return launch<BN, EPI_F_LNOUT | EPI_F_RES, PAIR>(st, p);
     case EPI_F_LN: return launch<BN, EPI_F_LN, PAIR>(st, p);
     case EPI_F_LN | EPI_F_RV: return launch<BN, EPI_F_LN | EPI_F_RV, PAIR>(st, p);
     case 0: return launch<BN, 0, PAIR>(st, p);
     case EPI_F_RES: return launch<BN, EPI_F_RES, PAIR>(st, p);
     case EPI_F_RV: return launch<BN, EPI_F_RV, PAIR>(st, p);
-    default: return launch<BN, EPI_F_RES | EPI_F_RV, PAIR>(st, p);
+    case EPI_F_RES | EPI_F_RV: return launch<BN, EPI_F_RES | EPI_F_RV, PAIR>(st, p);
+    default: set_error("gemm_tc: unsupported epilogue combination 0x%x", epi); return 2;
   }
 }
 
@@ -559,6 +600,15 @@ int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
 }  // namespace
 
+// Column tiles the kernel will use for this problem (= number of LayerNorm partial-sum slices a producer writes).
+int gemm_n_tiles(const GemmArgs& a) {
+  if (a.taps != 1) return 0;
+  int bn = a.force_bn;
+  if (a.mode == EPI_GEGLU) bn = 2 * kGegluGranule;
+  else if (bn == 0) bn = pick_bn((a.M + BM - 1) / BM, a.N, (a.K1 + BK - 1) / BK + a.K2 / BK);
+  return (a.N + bn - 1) / bn;
+}
+
 int gemm_tc(cudaStream_t st, const GemmArgs& a) {
   VS_REQUIRE(a.A && a.Bw && a.out, "gemm_tc: null pointer");
   VS_REQUIRE(a.taps == 1 || a.taps == 9, "gemm_tc: taps must be 1 or 9");
@@ -583,7 +633,14 @@ int gemm_tc(cudaStream_t st, const GemmArgs& a) {
   p.rv_mod = a.rv_mod;
   p.ln_stats = reinterpret_cast<const float2*>(a.ln_stats);
   p.ln_u = a.ln_u;
-  if (a.ln_stats) VS_REQUIRE(a.ln_u != nullptr && a.bias != nullptr && a.residual == nullptr, "gemm_tc: folded LayerNorm needs u and c vectors and no residual");
+  p.ln_parts = reinterpret_cast<const float2*>(a.ln_parts);
+  p.ln_nparts = a.ln_parts ? a.ln_nparts : 0;
+  p.ln_inv_c = 1.f / (float)(a.K1 + a.K2);
+  p.ln_sums_out = reinterpret_cast<float2*>(a.ln_sums_out);
+  if (a.ln_parts) VS_REQUIRE(a.ln_stats == nullptr && a.ln_nparts >= 1 && a.ln_nparts <= 16 && a.taps == 1, "gemm_tc: bad LayerNorm partial-sum input");
+  if (a.ln_stats || a.ln_parts) VS_REQUIRE(a.ln_u != nullptr && a.bias != nullptr && a.residual == nullptr, "gemm_tc: folded LayerNorm needs u and c vectors and no residual");
+  if (a.ln_sums_out) VS_REQUIRE(a.taps == 1 && a.mode == EPI_LINEAR && a.rowvec == nullptr && !a.ln_stats && !a.ln_parts,
+                                "gemm_tc: row statistics output is implemented for plain linear layers (+ bias / residual)");
   p.residual = a.residual;
   p.ldr = a.ldr;
   p.out = a.out;
@@ -656,10 +713,11 @@ int gemm_tc(cudaStream_t st, const GemmArgs& a) {
              (!a.bias || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0) &&
              (!a.rowvec || ((reinterpret_cast<uintptr_t>(a.rowvec) & 15) == 0 && p.ldrv % 4 == 0));
   if (!p.staged) VS_REQUIRE(a.mode == EPI_LINEAR, "gemm_tc: GEGLU output needs 32-column aligned, 16-byte strided rows");
-  if (a.ln_stats) VS_REQUIRE(p.staged && (reinterpret_cast<uintptr_t>(a.ln_u) & 15) == 0, "gemm_tc: folded LayerNorm needs the staged epilogue");
+  if (a.ln_stats || a.ln_parts) VS_REQUIRE(p.staged && (reinterpret_cast<uintptr_t>(a.ln_u) & 15) == 0, "gemm_tc: folded LayerNorm needs the staged epilogue");
+  if (a.ln_sums_out) VS_REQUIRE(p.staged, "gemm_tc: row statistics output needs the staged epilogue (N %% 32 == 0, aligned rows)");
   ProfScope prof(st, a.taps == 9 ? PC_CONV : PC_GEMM, 2.0 * a.M * (double)a.N * Ktot, 1, a.M, a.N, Ktot);
   if (a.mode == EPI_GEGLU) {
-    if (p.ln_stats) return pair ? launch<256, EPI_F_GEGLU | EPI_F_LN, true>(st, p) : launch<256, EPI_F_GEGLU | EPI_F_LN, false>(st, p);
+    if (p.ln_stats || p.ln_parts) return pair ? launch<256, EPI_F_GEGLU | EPI_F_LN, true>(st, p) : launch<256, EPI_F_GEGLU | EPI_F_LN, false>(st, p);
     return pair ? launch<256, EPI_F_GEGLU, true>(st, p) : launch<256, EPI_F_GEGLU, false>(st, p);
   }
   if (pair) {

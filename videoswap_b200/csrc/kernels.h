@@ -30,12 +30,19 @@ struct GemmArgs {
   // LayerNorm folded into this GEMM (A = the LayerNorm's RAW input, Bw = W * gamma, bias = beta W^T + b; see ln_fold):
   const float* ln_stats = nullptr;            // [M, 2] fp32 per-row (rstd, -mean * rstd) from ln_rowstats
   const float* ln_u = nullptr;                // [N] fp32 row sums of Bw
+  // ... or, instead of ln_stats, the partial sums the PRODUCER of A wrote from its epilogue (ln_sums_out of that GEMM):
+  const float* ln_parts = nullptr;            // [ln_nparts][M][2] fp32 (sum, sum of squares) over column tiles of A's producer
+  int ln_nparts = 0;                          // = gemm_n_tiles(producer args)
+  // This GEMM's output feeds a LayerNorm: write per-row (sum, sum of squares) of the stored fp16 values, one slice per
+  // column tile: [gemm_n_tiles(*this)][M][2] fp32.  Plain linear layers only (+ bias / residual).
+  float* ln_sums_out = nullptr;
   const __half* residual = nullptr; int ldr = 0;
   __half* out = nullptr; int ldc = 0;
   int mode = EPI_LINEAR;
   int force_bn = 0;                           // 0 = auto
 };
 int gemm_tc(cudaStream_t st, const GemmArgs& a);
+int gemm_n_tiles(const GemmArgs& a);         // column tiles gemm_tc will use (taps == 1)
 constexpr int kGegluGranule = 128;           // value/gate column interleave granule (= BLOCK_N/2 of the GEGLU GEMM)
 
 // ---- normalisation -------------------------------------------------------------------------------------------
@@ -46,7 +53,8 @@ int groupnorm_stats(cudaStream_t st, const __half* x1, int c1, const __half* x2,
                     int imgs_per_set, int groups, float* sums, bool zero_first = true);
 int groupnorm_apply(cudaStream_t st, const __half* x1, int c1, const __half* x2, int c2, int nimg, int hw,
                     int imgs_per_set, int groups, const float* sums, float eps, const float* gamma,
-                    const float* beta, bool silu, __half* out);
+                    const float* beta, bool silu, __half* out, int count_scale = 1);   // count_scale: `sums` cover that many
+                    // times the local elements (frame-sharded 5-D GroupNorm after the all-reduce of the sums)
 // LayerNorm over the last dim of [rows, C]; optional temporal positional encoding pe[(row / hw) % F, :] added after.
 int layernorm(cudaStream_t st, const __half* x, int rows, int C, const float* gamma, const float* beta,
               const float* pe, int hw, int F, __half* out);
@@ -96,6 +104,17 @@ int cfg_ddim_step_dev(cudaStream_t st, const void* eps2, const void* latents, in
 // SparsePointAdapter splat: feat [P, C] fp32, tracks [F, P, 2] fp32 -> maps NHWC [F, h, w, C] fp16 (zeroed inside)
 int adapter_splat(cudaStream_t st, const float* feat, const float* tracks, const int* point_mask, int F, int P, int C,
                   int h, int w, float rate, int coord_fp16, float scale, __half* maps);
+
+// ---- multi-GPU exchanges (comm.cu; NCCL bound at run time) -----------------------------------------------------------
+}  // namespace vs
+struct vs_comm;
+namespace vs {
+int comm_rank(const vs_comm* c);
+int comm_size(const vs_comm* c);
+int comm_all_reduce_sum_f32(vs_comm* c, cudaStream_t st, float* buf, size_t n);             // in place
+int comm_all_gather(vs_comm* c, cudaStream_t st, const void* send, void* recv, size_t bytes);
+// frames <-> pixels re-sharding: src [n_outer][k][chunk] -> dst [k][n_outer][chunk] (gather = 0) or the inverse (gather = 1)
+int comm_all_to_all_rows(vs_comm* c, cudaStream_t st, const __half* src, __half* dst, int n_outer, size_t chunk, int gather);
 
 // ---- weight packing --------------------------------------------------------------------------------------------
 int pack_conv3x3(cudaStream_t st, const __half* w, int cout, int cin, __half* out);   // [co,ci,3,3] -> [co,tap,ci]

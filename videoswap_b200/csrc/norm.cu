@@ -22,6 +22,7 @@ struct GnParams {
   long long pix_per_set;     // imgs_per_set * hw
   float* sums;               // [nstat, groups, 2]
   const float* gamma; const float* beta; float eps; int silu;
+  int count_scale;           // the sums cover count_scale x the local elements (frame shards, after the all-reduce)
   __half* out;
   int rows_per_block;        // pixel rows in flight per block (blockDim.x = CV * rows_per_block)
   int pix_per_block;
@@ -80,7 +81,7 @@ __global__ void gn_apply_kernel(const GnParams p) {
   const int set = blockIdx.y;
   const int cv = threadIdx.x % p.CV, r = threadIdx.x / p.CV;
   float a[8], b[8];
-  const float inv_n = 1.f / ((float)p.pix_per_set * p.cpg);
+  const float inv_n = 1.f / ((float)p.pix_per_set * p.cpg * (float)p.count_scale);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = cv * 8 + j;
@@ -380,13 +381,14 @@ int groupnorm_stats(cudaStream_t st, const __half* x1, int c1, const __half* x2,
 
 int groupnorm_apply(cudaStream_t st, const __half* x1, int c1, const __half* x2, int c2, int nimg, int hw,
                     int imgs_per_set, int groups, const float* sums, float eps, const float* gamma, const float* beta,
-                    bool silu, __half* out) {
+                    bool silu, __half* out, int count_scale) {
   GnParams p{};
   dim3 grid;
   int threads;
   if (int e = gn_fill(p, grid, threads, x1, c1, x2, c2, nimg, hw, imgs_per_set, groups)) return e;
   p.sums = const_cast<float*>(sums);
   p.gamma = gamma; p.beta = beta; p.eps = eps; p.silu = silu ? 1 : 0; p.out = out;
+  p.count_scale = count_scale > 0 ? count_scale : 1;
   ProfScope prof(st, PC_GROUPNORM, 4.0 * nimg * (double)hw * (c1 + c2), 1, (long long)nimg * hw, c1 + c2, imgs_per_set);
   return launch_pdl(gn_apply_kernel, grid, dim3(threads), 0, st, 1, p);
 }

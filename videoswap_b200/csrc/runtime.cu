@@ -122,6 +122,7 @@ static Option g_options[] = {
     {"gemm_pair", 1},      // CTA pairs (cta_group::2, 256-row tiles): 1 = for K >= 768, 0 = never, 2 = whenever possible
     {"gemm_stages", 0},    // smem ring depth limit (0 = all)
     {"ln_fold", 1},        // LayerNorms folded into the GEMM that consumes them (0 = stand-alone LayerNorm kernel)
+    {"ln_fuse", 1},        // row statistics of folded LayerNorms come from the producing GEMM's epilogue (0 = ln_stats_kernel pass)
     {"pdl", 1},            // programmatic dependent launch between the hot kernels (0 = plain stream order)
 };
 int set_option(const char* name, int value) {

@@ -79,7 +79,11 @@ struct vs_unet {
   int n_groupnorms = 0;                        // GroupNorm calls of one forward (sizes the statistics slices)
   __half *XIN, *XN, *T, *TN, *QKV, *ATT, *HH, *SC, *P0, *P1, *SCR, *KV, *RES, *OUT;
   std::vector<__half*> skip;            // 12 skip buffers
-  float *F_T, *F_TE0, *F_TE1, *F_EMB, *F_TPROJ, *F_SUMS, *F_LNS;
+  float *F_T, *F_TE0, *F_TE1, *F_EMB, *F_TPROJ, *F_SUMS, *F_LNS, *F_LNP;
+
+  // frame sharding: this rank holds F/k frames of ONE batch element; exchanges over `fcomm` (comm.cu)
+  vs_comm* fcomm = nullptr;
+  int fshard = 0, fnshards = 1;
 
   // debug taps
   bool taps_on = false;
@@ -359,6 +363,7 @@ struct Ctx {
   int B, F, NI, H, W;      // W/H are the CURRENT resolution during the walk
   const __half* ehs; int ehs_tokens, ehs_layers;
   int gn_idx = 0;          // GroupNorm call counter: every call owns a slice of F_SUMS, all zeroed by ONE memset per forward
+  int ln_parts = 0;        // > 0: F_LNP holds that many per-row partial-sum slices of the tensor the last `linear` wrote
 };
 
 // every GroupNorm call of a forward owns one slice [NI, 32 groups, 2] of F_SUMS (h->n_groupnorms of them, counted at create)
@@ -381,10 +386,20 @@ int tap(Ctx& c, const std::string& name, const __half* p, int C) {
   return 0;
 }
 
-int linear(Ctx& c, const __half* A, int M, const Lin& l, const __half* residual, __half* out) {
+// ln_out: the output feeds a LayerNorm that is folded into the next GEMM -> the epilogue also writes the row statistics
+// (per column tile) into F_LNP and c.ln_parts says how many slices (0 when the fused statistics are switched off).
+int linear(Ctx& c, const __half* A, int M, const Lin& l, const __half* residual, __half* out, bool ln_out = false) {
   GemmArgs g;
   g.A = A; g.K1 = l.K; g.lda1 = l.K; g.Bw = l.w; g.M = M; g.N = l.N; g.bias = l.b;
   g.residual = residual; g.ldr = l.N; g.out = out; g.ldc = l.N;
+  c.ln_parts = 0;
+  if (ln_out && get_option("ln_fuse") != 0 && get_option("ln_fold") != 0 && ln_fold_supported(l.N) && l.N % 32 == 0) {
+    const int parts = gemm_n_tiles(g);
+    if (parts >= 1 && (long long)M * parts <= 4LL * c.NI * c.h->wsH * c.h->wsW) {   // capacity of F_LNP (float2 slots)
+      g.ln_sums_out = c.h->F_LNP;
+      c.ln_parts = parts;
+    }
+  }
   return gemm_tc(c.st, g);
 }
 
@@ -401,14 +416,17 @@ int resnet(Ctx& c, const Resnet& r, const __half* in1, int C1, const __half* in2
   const int hw = c.H * c.W, G = h->cfg.norm_num_groups;
   const float eps = h->cfg.norm_eps;
   VS_REQUIRE(C1 + C2 == r.cin, "internal: resnet input channels %d+%d != %d", C1, C2, r.cin);
+  const int k = h->fnshards;          // frame shards: the 5-D GroupNorm statistics span all of them (resnet.py:166,177)
   NEXT_SUMS(sums);
   RUN(groupnorm_stats(c.st, in1, C1, in2, C2, c.NI, hw, c.F, G, sums, false));
-  RUN(groupnorm_apply(c.st, in1, C1, in2, C2, c.NI, hw, c.F, G, sums, eps, r.n1.g, r.n1.b, true, h->XN));
+  if (k > 1) RUN(comm_all_reduce_sum_f32(h->fcomm, c.st, sums, (size_t)c.B * G * 2));
+  RUN(groupnorm_apply(c.st, in1, C1, in2, C2, c.NI, hw, c.F, G, sums, eps, r.n1.g, r.n1.b, true, h->XN, k));
   RUN(conv(c, h->XN, r.cin, r.c1, h->F_TPROJ + r.temb_off, nullptr, h->T));
   sums = next_sums(c);
   if (!sums) return 2;
   RUN(groupnorm_stats(c.st, h->T, r.cout, nullptr, 0, c.NI, hw, c.F, G, sums, false));
-  RUN(groupnorm_apply(c.st, h->T, r.cout, nullptr, 0, c.NI, hw, c.F, G, sums, eps, r.n2.g, r.n2.b, true, h->XN));
+  if (k > 1) RUN(comm_all_reduce_sum_f32(h->fcomm, c.st, sums, (size_t)c.B * G * 2));
+  RUN(groupnorm_apply(c.st, h->T, r.cout, nullptr, 0, c.NI, hw, c.F, G, sums, eps, r.n2.g, r.n2.b, true, h->XN, k));
   const __half* residual = in1;
   if (r.has_sc) {
     GemmArgs g;
@@ -428,9 +446,15 @@ int resnet(Ctx& c, const Resnet& r, const __half* in1, int C1, const __half* in2
 bool use_fold(const LnLin& f) { return f.wf != nullptr && get_option("ln_fold") != 0; }
 int ln_linear(Ctx& c, const __half* x, int M, int C, const LnLin& f, int N, int mode, int hw, int pe_frames, __half* out, int ldc) {
   vs_unet* h = c.h;
-  RUN(ln_rowstats(c.st, x, M, C, h->F_LNS));
   GemmArgs g;
-  g.A = x; g.K1 = C; g.lda1 = C; g.Bw = f.wf; g.M = M; g.N = N; g.bias = f.c; g.ln_stats = h->F_LNS; g.ln_u = f.u;
+  g.A = x; g.K1 = C; g.lda1 = C; g.Bw = f.wf; g.M = M; g.N = N; g.bias = f.c; g.ln_u = f.u;
+  if (c.ln_parts > 0) {            // the GEMM that wrote x left its row statistics in F_LNP
+    g.ln_parts = h->F_LNP; g.ln_nparts = c.ln_parts;
+    c.ln_parts = 0;
+  } else {
+    RUN(ln_rowstats(c.st, x, M, C, h->F_LNS));
+    g.ln_stats = h->F_LNS;
+  }
   g.out = out; g.ldc = ldc; g.mode = mode;
   if (pe_frames > 0) { g.rowvec = f.cpe; g.ldrv = N; g.pix_per_batch = hw; g.rv_mod = pe_frames; }
   return gemm_tc(c.st, g);
@@ -450,7 +474,7 @@ int transformer(Ctx& c, const Transformer& t, __half* x) {
   NEXT_SUMS(sums);
   RUN(groupnorm_stats(c.st, x, C, nullptr, 0, c.NI, hw, 1, h->cfg.norm_num_groups, sums, false));
   RUN(groupnorm_apply(c.st, x, C, nullptr, 0, c.NI, hw, 1, h->cfg.norm_num_groups, sums, 1e-6f, t.norm.g, t.norm.b, false, h->XN));
-  RUN(linear(c, h->XN, M, t.proj_in, nullptr, h->T));
+  RUN(linear(c, h->XN, M, t.proj_in, nullptr, h->T, use_fold(t.f_qkv)));
   // self-attention
   if (use_fold(t.f_qkv)) {
     RUN(ln_linear(c, h->T, M, C, t.f_qkv, 3 * C, EPI_LINEAR, hw, 0, h->QKV, 3 * C));
@@ -460,7 +484,7 @@ int transformer(Ctx& c, const Transformer& t, __half* x) {
   }
   RUN(attention(c.st, h->QKV, 3 * C, h->QKV + C, 3 * C, h->QKV + 2 * C, 3 * C, h->ATT, C, c.NI, hw, hw, heads, d,
                 (long long)hw * 3 * C, (long long)hw * 3 * C, (long long)hw * C, 1));
-  RUN(linear(c, h->ATT, M, t.out1, h->T, h->T));
+  RUN(linear(c, h->ATT, M, t.out1, h->T, h->T, use_fold(t.f_q)));
   // cross-attention to the (ED-LoRA layer-selected) text embeddings; K/V were projected once per (batch, layer)
   if (use_fold(t.f_q)) {
     RUN(ln_linear(c, h->T, M, C, t.f_q, C, EPI_LINEAR, hw, 0, h->QKV, C));
@@ -483,7 +507,7 @@ int transformer(Ctx& c, const Transformer& t, __half* x) {
     RUN(attention(c.st, h->QKV, C, h->KV, 2 * C, h->KV + C, 2 * C, h->ATT, C, c.NI, hw, nk, heads, d, (long long)hw * C,
                   (long long)nk * 2 * C, (long long)hw * C, c.F));
   }
-  RUN(linear(c, h->ATT, M, t.out2, h->T, h->T));
+  RUN(linear(c, h->ATT, M, t.out2, h->T, h->T, use_fold(t.f_ff)));
   // feed-forward
   if (use_fold(t.f_ff)) {
     RUN(ln_linear(c, h->T, M, C, t.f_ff, 8 * C, EPI_GEGLU, hw, 0, h->HH, 4 * C));
@@ -498,21 +522,33 @@ int transformer(Ctx& c, const Transformer& t, __half* x) {
 
 int motion(Ctx& c, const Motion& m, int level, __half* x) {
   vs_unet* h = c.h;
-  const int hw = c.H * c.W, C = m.C, M = c.NI * hw;
-  VS_REQUIRE(c.F <= h->cfg.pe_max_len, "video_length %d exceeds temporal_position_encoding_max_len %d", c.F, h->cfg.pe_max_len);
+  const int hw_all = c.H * c.W, C = m.C, M = c.NI * hw_all;
+  // Frame shards: the temporal attention couples the F frames of every pixel and everything else inside the module is per
+  // pixel, so the module runs on ALL frames x 1/k of the pixels: frames <-> pixels all-to-all of the GroupNorm output on
+  // the way in and of proj_out's result on the way back (2 C values per token instead of K and V per attention).
+  const int k = h->fnshards;
+  const int Ft = c.F * k;                     // frames the attention sees
+  const int hw = hw_all / k;                  // pixels per frame this rank owns inside the module
+  VS_REQUIRE(Ft <= h->cfg.pe_max_len, "video_length %d exceeds temporal_position_encoding_max_len %d", Ft, h->cfg.pe_max_len);
+  if (k > 1) VS_REQUIRE(c.B == 1 && hw_all % k == 0, "frame sharding needs batch 1 per rank and h*w (%d) divisible by the %d shards", hw_all, k);
   NEXT_SUMS(sums);
-  RUN(groupnorm_stats(c.st, x, C, nullptr, 0, c.NI, hw, 1, 32, sums, false));
-  RUN(groupnorm_apply(c.st, x, C, nullptr, 0, c.NI, hw, 1, 32, sums, 1e-6f, m.norm.g, m.norm.b, false, h->XN));
-  RUN(linear(c, h->XN, M, m.proj_in, nullptr, h->T));
+  RUN(groupnorm_stats(c.st, x, C, nullptr, 0, c.NI, hw_all, 1, 32, sums, false));
+  RUN(groupnorm_apply(c.st, x, C, nullptr, 0, c.NI, hw_all, 1, 32, sums, 1e-6f, m.norm.g, m.norm.b, false, h->XN));
+  const __half* xin = h->XN;
+  if (k > 1) {
+    RUN(comm_all_to_all_rows(h->fcomm, c.st, h->XN, h->SC, c.F, (size_t)hw * C, 0));    // [F/k, k, hw C] -> [k, F/k, hw C] = [F, hw, C]
+    xin = h->SC;
+  }
+  RUN(linear(c, xin, M, m.proj_in, nullptr, h->T, use_fold(m.f_qkv[0])));
   for (int i = 0; i < 2; ++i) {
     if (use_fold(m.f_qkv[i])) {
-      RUN(ln_linear(c, h->T, M, C, m.f_qkv[i], 3 * C, EPI_LINEAR, hw, c.F, h->QKV, 3 * C));
+      RUN(ln_linear(c, h->T, M, C, m.f_qkv[i], 3 * C, EPI_LINEAR, hw, Ft, h->QKV, 3 * C));
     } else {
-      RUN(layernorm(c.st, h->T, M, C, m.ln[i].g, m.ln[i].b, h->pe[level], hw, c.F, h->TN));
+      RUN(layernorm(c.st, h->T, M, C, m.ln[i].g, m.ln[i].b, h->pe[level], hw, Ft, h->TN));
       GemmArgs g; g.A = h->TN; g.K1 = C; g.lda1 = C; g.Bw = m.wqkv[i]; g.M = M; g.N = 3 * C; g.out = h->QKV; g.ldc = 3 * C; RUN(gemm_tc(c.st, g));
     }
-    RUN(temporal_attention(c.st, h->QKV, h->ATT, c.B, c.F, hw, C, h->cfg.motion_num_heads));
-    RUN(linear(c, h->ATT, M, m.out[i], h->T, h->T));
+    RUN(temporal_attention(c.st, h->QKV, h->ATT, c.B, Ft, hw, C, h->cfg.motion_num_heads));
+    RUN(linear(c, h->ATT, M, m.out[i], h->T, h->T, i == 0 ? use_fold(m.f_qkv[1]) : use_fold(m.f_ff)));
   }
   if (use_fold(m.f_ff)) {
     RUN(ln_linear(c, h->T, M, C, m.f_ff, 8 * C, EPI_GEGLU, hw, 0, h->HH, 4 * C));
@@ -520,6 +556,11 @@ int motion(Ctx& c, const Motion& m, int level, __half* x) {
   } else {
     RUN(layernorm(c.st, h->T, M, C, m.ff_norm.g, m.ff_norm.b, nullptr, 1, 1, h->TN));
     RUN(geglu_ff(c, h->TN, M, C, m.ff1w, m.ff1b, m.ff2, h->T));
+  }
+  if (k > 1) {
+    RUN(linear(c, h->T, M, m.proj_out, nullptr, h->XN));
+    RUN(comm_all_to_all_rows(h->fcomm, c.st, h->XN, h->SC, c.F, (size_t)hw * C, 1));    // back to [F/k, hw_all, C]
+    return add_inplace(c.st, x, h->SC, (size_t)M * C, 1.f);     // the module's residual: fp16 add, as in the fused epilogue
   }
   RUN(linear(c, h->T, M, m.proj_out, x, x));
   return 0;
@@ -569,7 +610,7 @@ int ensure_workspace(vs_unet* h, int B, int F, int H, int W) {
   const int temb = boc[0] * 4;
   const size_t fl = align_up(4 * 64) + align_up((size_t)B * boc[0] * 4) + 2 * align_up((size_t)B * temb * 4) +
                     align_up((size_t)B * h->tproj_n * 4) + align_up((size_t)h->n_groupnorms * NI * 64 * 4) +
-                    align_up(NI * hw[0] * 2 * 4);
+                    align_up(NI * hw[0] * 2 * 4) + align_up(NI * hw[0] * 4 * 2 * 4);
   total += fl;
   if (total > h->ws_bytes) {
     VS_REQUIRE(h->ws_pinned == 0, "vs_unet_forward: shape [%d,%d,%d,%d] needs a %zu-byte workspace but the current one "
@@ -587,12 +628,22 @@ int ensure_workspace(vs_unet* h, int B, int F, int H, int W) {
   h->F_EMB = (float*)p; p += align_up((size_t)B * temb * 4);
   h->F_TPROJ = (float*)p; p += align_up((size_t)B * h->tproj_n * 4);
   h->F_SUMS = (float*)p; p += align_up((size_t)h->n_groupnorms * NI * 64 * 4);
-  h->F_LNS = (float*)p;
+  h->F_LNS = (float*)p; p += align_up(NI * hw[0] * 2 * 4);
+  h->F_LNP = (float*)p;            // LayerNorm partial sums: up to 4 column-tile slices of [NI * hw0] float2
   h->wsB = B; h->wsF = F; h->wsH = H; h->wsW = W;
   return 0;
 }
 
 }  // namespace
+
+extern "C" int vs_unet_set_frame_shard(vs_unet* h, vs_comm* comm, int shard, int nshards) {
+  VS_REQUIRE(h != nullptr && nshards >= 1 && shard >= 0 && shard < nshards, "vs_unet_set_frame_shard: bad arguments");
+  VS_REQUIRE(nshards == 1 || (comm != nullptr && comm_size(comm) == nshards && comm_rank(comm) == shard),
+             "vs_unet_set_frame_shard: the communicator must have exactly one rank per shard, ranked by shard");
+  h->fcomm = nshards > 1 ? comm : nullptr;
+  h->fshard = shard; h->fnshards = nshards;
+  return 0;
+}
 
 extern "C" int vs_unet_pin_workspace(vs_unet* h, int pin) {
   VS_REQUIRE(h != nullptr, "vs_unet_pin_workspace: null handle");
@@ -633,6 +684,7 @@ extern "C" int vs_unet_forward(vs_unet* h, void* stream, const void* d_sample, i
   VS_REQUIRE(B >= 1 && F >= 1 && H >= 1 && W >= 1, "vs_unet_forward: bad shape");
   VS_REQUIRE(ehs_tokens >= 1 && ehs_tokens <= 128, "vs_unet_forward: ehs_tokens out of range");
   VS_REQUIRE(h->cfg.in_channels <= 8 && h->cfg.out_channels <= 8, "in/out channels > 8 unsupported");
+  VS_REQUIRE(h->fnshards == 1 || B == 1, "frame-sharded forward: one batch element per rank (got B = %d)", B);
   cudaStream_t st = (cudaStream_t)stream;
   RUN(ensure_workspace(h, B, F, H, W));
   if (h->folds_dirty) {
@@ -754,7 +806,9 @@ extern "C" int vs_unet_forward(vs_unet* h, void* stream, const void* d_sample, i
   // ---- out: GroupNorm(5-D) + SiLU + conv_out
   NEXT_SUMS(osums);
   RUN(groupnorm_stats(st, cur, curC, nullptr, 0, c.NI, H * W, F, cf.norm_num_groups, osums, false));
-  RUN(groupnorm_apply(st, cur, curC, nullptr, 0, c.NI, H * W, F, cf.norm_num_groups, osums, cf.norm_eps, h->norm_out.g, h->norm_out.b, true, h->XN));
+  if (h->fnshards > 1) RUN(comm_all_reduce_sum_f32(h->fcomm, st, osums, (size_t)B * cf.norm_num_groups * 2));
+  RUN(groupnorm_apply(st, cur, curC, nullptr, 0, c.NI, H * W, F, cf.norm_num_groups, osums, cf.norm_eps, h->norm_out.g, h->norm_out.b, true, h->XN,
+                      h->fnshards));
   {
     GemmArgs g;
     g.A = h->XN; g.K1 = curC; g.lda1 = curC; g.Bw = h->conv_out.w; g.taps = 9; g.nimg = c.NI; g.H = H; g.W = W;

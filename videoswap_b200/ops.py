@@ -135,6 +135,26 @@ def ln_linear(x, W, gamma, beta, bias=None, pe=None, hw=1, frames=1, mode=EPI_LI
     return out
 
 
+def linear_ln_linear(x0, W0, b0, W, gamma, beta, residual=None, bias=None, mode=EPI_LINEAR):
+    """x = x0 @ W0^T + b0 (+ residual) [fp16]; out = LayerNorm(x) @ W^T + bias (or GEGLU), the LayerNorm's row statistics
+    coming from the first GEMM's epilogue.  Returns (x, out)."""
+    _chk16(x0, W0, W, residual)
+    _chk32(b0, gamma, beta, bias)
+    M, K0 = x0.shape
+    Cc, N = W0.shape[0], W.shape[0]
+    dev = x0.device
+    x = torch.empty((M, Cc), dtype=torch.float16, device=dev)
+    wf = torch.empty_like(W)
+    u = torch.empty((N,), dtype=torch.float32, device=dev)
+    c = torch.empty((N,), dtype=torch.float32, device=dev)
+    cap = 16
+    parts = torch.empty((cap, M, 2), dtype=torch.float32, device=dev)
+    out = torch.empty((M, N // 2 if mode == EPI_GEGLU else N), dtype=torch.float16, device=dev)
+    _lib.call("vs_linear_ln_linear", _stream(), _p(x0), M, K0, _p(W0), _p(b0), _p(residual), Cc, _p(x), _p(W), _p(bias), N,
+              _p(gamma), _p(beta), mode, _p(wf), _p(u), _p(c), _p(parts), cap, _p(out))
+    return x, out
+
+
 def attention(q, k, v, heads, kv_div=1):
     """q [B, Nq, h*d], k/v [Bk, Nk, h*d] (may be strided views with contiguous last dim) -> [B, Nq, h*d]."""
     B, nq, Cc = q.shape
