@@ -6,8 +6,11 @@ One "step" = one loop body of the reference pipeline (pipelines/pipeline_videosw
 duplication, AnimateDiffUNet3DModel forward on [2,4,16,64,64], CFG combine, DDIM update.  Workload = BASELINE config
 "16-frame 512x512 ... 1xB200 fp16" with ED-LoRA per-layer embeddings and adapter residuals active (superset of
 configs[1] and configs[2]); synthetic inputs, seeded random weights of the real architecture (no checkpoints offline).
-N > 1: one process per GPU (torchrun), each rank denoises its own video (independent editing jobs -> weak scaling,
-no data-path collective); barrier + device timing, max over ranks.
+N > 1 (default --mode shard): one process per GPU (torchrun), ONE video split over the ranks -- strong scaling: N = 2 the two
+CFG halves (one all-gather of the noise predictions per step), N = 4 / 8 CFG x 2 / 4 frame shards (GroupNorm-statistics
+all-reduces + frames<->pixels all-to-all around the motion modules, NCCL over NVLink, captured in the CUDA graph);
+`value` = steps of that one video per second.  --mode replicas: one video per rank (weak scaling, no data-path
+collective).  Barrier + device timing, max over ranks.
 """
 from __future__ import annotations
 
@@ -199,9 +202,9 @@ def main():
     ap.add_argument("--frames", type=int, default=FRAMES)
     ap.add_argument("--latent-h", type=int, default=LATENT, help="latent height (extra configs, e.g. 56 for 448x768 video)")
     ap.add_argument("--latent-w", type=int, default=LATENT, help="latent width (e.g. 96)")
-    ap.add_argument("--mode", default="replicas", choices=["replicas", "cfg-split"],
-                    help="multi-GPU scheme: independent videos per rank (weak scaling, default) or ONE video with the "
-                         "unconditional / conditional halves of the CFG batch on two ranks (strong scaling, --gpus 2)")
+    ap.add_argument("--mode", default="shard", choices=["shard", "replicas"],
+                    help="multi-GPU scheme: ONE video split over the ranks (CFG halves x frame shards; strong scaling, "
+                         "default) or independent videos per rank (weak scaling)")
     ap.add_argument("--option", action="append", default=[], help="kernel A/B switch name=value (vs_set_option)")
     ap.add_argument("--tag", default="", help="suffix of the per-shape profile CSV")
     args = ap.parse_args()
@@ -214,7 +217,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from videoswap_b200 import AnimateDiffUNet3DModel, DDIMScheduler, VideoSwapPipeline, _lib, ops
+    from videoswap_b200 import AnimateDiffUNet3DModel, DDIMScheduler, VideoSwapPipeline, _lib, dist_util, ops
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -222,12 +225,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     W = max(args.warmup, 3)
     K = args.steps
-    cfg_split = args.mode == "cfg-split"
-    if cfg_split:
-        assert world == 2, "--mode cfg-split needs exactly two ranks"
-        args.no_graph = True                        # the all-gather of the two noise predictions is not captured
-    cfg_group = dist.group.WORLD if cfg_split else None
-    seed_rank = 0 if cfg_split else rank           # both ranks work on the SAME video
+    sharded = args.mode == "shard" and world > 1
+    cfg_split = sharded                             # (name kept for the JSON fields below)
+    plan = dist_util.make_plan(world, rank, cfg=True) if sharded else dist_util.ShardPlan()
+    seed_rank = 0 if sharded else rank              # all ranks work on the SAME video
     Fr = args.frames
 
     model = AnimateDiffUNet3DModel(init="empty")
@@ -242,9 +243,17 @@ def main():
     embeds = torch.randn((2, 16, 77, 768), device=dev, generator=g).half()
     boc = model.cfg.block_out_channels
     residuals = [(0.1 * torch.randn((2 * Fr, c, LH >> l, LW >> l), device=dev, generator=g)).half() for l, c in enumerate(boc)]
+    res_loc = None
+    if sharded:
+        plan = dist_util.create_comms(plan)
+        dist_util.attach(model, plan)
+        lat0 = plan.shard_frames(lat0, 2)                                       # this rank's frames of the one video
+        res_loc = [plan.shard_frame_major(r[:Fr], Fr) for r in residuals]       # per-frame maps (identical for both CFG halves)
 
     def step(lat, i):
-        return pipe.step(lat, ts[i % len(ts)], embeds, 7.5, list(residuals), cfg_group=cfg_group)
+        if sharded:
+            return pipe.step_sharded(lat, ts[i % len(ts)], embeds, 7.5, plan, res_loc)
+        return pipe.step(lat, ts[i % len(ts)], embeds, 7.5, list(residuals))
 
     lib = _lib.lib()
     for opt in args.option:
@@ -297,7 +306,7 @@ def main():
     gstep = None
     if not args.no_graph:
         from videoswap_b200.pipeline import GraphedStep
-        gstep = GraphedStep(pipe, lat0, embeds, 7.5, residuals)
+        gstep = GraphedStep(pipe, lat0, embeds, 7.5, res_loc if sharded else residuals, plan=plan if sharded else None)
         lat = lat0
         for i in range(W):
             lat = gstep(lat, ts[i % len(ts)])
@@ -331,7 +340,7 @@ def main():
         if gstep is not None:
             out = gstep(d_lat, ts[i % len(ts)])
         else:
-            out = pipe.step(d_lat, ts[i % len(ts)], d_emb, 7.5, list(residuals), cfg_group=cfg_group)
+            out = step(d_lat, i)
         h_out.copy_(out, non_blocking=True)
         torch.cuda.current_stream().synchronize()      # the caller reads the result on the host every step
         h_lat.copy_(h_out)
@@ -423,16 +432,19 @@ def main():
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if cfg_split else "weak", "vs_baseline": None, "dtype": "f16",
             "data": "synthetic",
             "config": {"workload": f"{Fr}-frame {8 * LH}x{8 * LW} (latent [1,4,{Fr},{LH},{LW}]), CFG 7.5 (UNet batch 2), ED-LoRA embeds "
-                                   f"[2,16,77,768], adapter residuals active, DDIM step; " + ("ONE video, CFG halves split over 2 GPUs, one all-gather of eps per step" if cfg_split else "one video per GPU"),
-                       "parallelism": "cfg2" if cfg_split else f"replicas x{world}",
+                                   f"[2,16,77,768], adapter residuals active, DDIM step; " +
+                                   (f"ONE video over {world} GPUs: CFG halves x {plan.frame_shards} frame shard(s); exchanges per step: 1 all-gather of eps"
+                                    + (", 45 GroupNorm-statistics all-reduces, 40 frames<->pixels all-to-alls (NCCL, inside the CUDA graph)" if plan.frame_shards > 1 else "")
+                                    if sharded else "one video per GPU"),
+                       "parallelism": (f"cfg2 x frames{plan.frame_shards}" if sharded else f"replicas x{world}"),
                        "timing": "CUDA events; working set (2.55 GB weights + activations) >> 126 MB L2, no flush needed; "
                                  "`value`/`e2e` replay the step as a CUDA graph, the per-kernel profile comes from an eager pass "
                                  "of the same K steps with per-launch events",
                        "eager_ms_per_step": round(ms_eager / K, 3), "cuda_graph": gstep is not None,
-                       "whole_step_tflops": (round(FLOP_PER_STEP * (Fr / FRAMES) * (K / (ms / 1e3)) / 1e12, 1)
+                       "whole_step_tflops": (round(FLOP_PER_STEP * (Fr / FRAMES) * value / 1e12, 1)
                                              if (LH, LW) == (LATENT, LATENT) else None)},
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h_lat.numel() * 2 + h_emb.numel() * 2,
-                    "d2h_bytes_per_step": h_out.numel() * 2},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": (h_lat.numel() * 2 + h_emb.numel() * 2) * world,
+                    "d2h_bytes_per_step": h_out.numel() * 2 * world},     # every rank moves its own latents (shard) + embeddings
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"kernel": dom_name, "bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s",

@@ -1,101 +1,126 @@
-"""world_size-2 gloo test of the multi-rank plumbing (job partition, max-over-ranks timing, result gather)."""
+"""CPU tests of the multi-rank path (gloo, world_size 2 and 4): the rank plan, and -- with the oracle standing in for the
+CUDA kernels -- that the exchanges the frame-sharded / CFG-split step performs (GroupNorm-statistics all-reduce, frames <->
+pixels re-sharding around the motion modules, all-gather of the two noise predictions) reproduce the single-process
+step.  The CUDA implementation of the same exchanges is checked on GPUs by tools/gpu_shard_check.py."""
 import os
 
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from videoswap_b200.dist_util import gather_latents, max_over_ranks, shard_jobs
+from videoswap_b200.dist_util import make_plan, max_over_ranks, shard_jobs
+
+TINY = dict(boc=(32, 64, 128, 128), ctx=64, groups=8)
 
 
-def _worker(rank, world, port, q):
+def _tiny_problem(frames=4, hw=16):      # 16x16 latents: 2x2 pixels at the deepest level, divisible by the 2 frame shards
+    from oracle import unet3d_oracle as O
+    from videoswap_b200.spec import UNetConfig, unet_param_shapes
+    from videoswap_b200.weights import seeded_state_dict
+    cfg = UNetConfig(block_out_channels=TINY["boc"], cross_attention_dim=TINY["ctx"], norm_num_groups=TINY["groups"])
+    sd = seeded_state_dict(unet_param_shapes(cfg), seed=0)
+    oc = O.OracleConfig(block_out_channels=TINY["boc"], cross_attention_dim=TINY["ctx"], norm_groups=TINY["groups"])
+    g = torch.Generator().manual_seed(3)
+    lat = torch.randn((1, 4, frames, hw, hw), generator=g)
+    ehs2 = torch.randn((2, 16, 77, TINY["ctx"]), generator=g)
+    res = [0.5 * torch.randn((frames, c, max(hw >> l, 1), max(hw >> l, 1)), generator=g) for l, c in enumerate(TINY["boc"])]
+    return sd, oc, lat, ehs2, res
+
+
+def _init(rank, world, port):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
+    torch.set_num_threads(2)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    jobs = shard_jobs(5, rank, world)
-    t = max_over_ranks(10.0 + rank)
-    lat = torch.full((1, 4, 2, 4, 4), float(rank))
-    allv = gather_latents(lat)
-    q.put((rank, jobs, t, [float(v.mean()) for v in allv]))
+
+
+def _shard_worker(rank, world, port, q, cfg_split):
+    try:
+        _shard_worker_body(rank, world, port, q, cfg_split)
+    except Exception as e:  # noqa: BLE001  (surface the failure in the parent instead of a queue timeout)
+        import traceback
+        q.put((rank, None, "".join(traceback.format_exception(e))[-2000:]))
+
+
+def _shard_worker_body(rank, world, port, q, cfg_split):
+    _init(rank, world, port)
+    from oracle import sharded
+    plan = make_plan(world, rank, cfg=cfg_split)
+    # every rank creates every group (torch.distributed requires it); keep the two this rank belongs to
+    groups = {}
+    for r in range(world):
+        pr = make_plan(world, r, cfg=cfg_split)
+        for key in (tuple(pr.frame_group), tuple(pr.cfg_group)):
+            if key not in groups:
+                groups[key] = dist.new_group(list(key))
+    sd, oc, lat, ehs2, res = _tiny_problem()
+    with torch.no_grad():
+        out = sharded.denoise_step_sharded(sd, oc, lat, 981, 50, ehs2, 7.5 if cfg_split else 1.0, res, plan,
+                                           groups[tuple(plan.frame_group)], groups[tuple(plan.cfg_group)]) if cfg_split else None
+        if not cfg_split:        # inversion-like: no CFG, every rank is a frame shard
+            from oracle import unet3d_oracle as O
+            r = plan.frame_range(lat.shape[2])
+            with sharded.frame_sharded(groups[tuple(plan.frame_group)], plan.frame_shard, plan.frame_shards):
+                out = O.unet_forward(sd, oc, lat[:, :, r.start:r.stop], 501, ehs2[1:2], [m[r.start:r.stop] for m in res])
+    q.put((rank, list(plan.frame_range(lat.shape[2])), out))
+    max_over_ranks(1.0)
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_two_rank_partition_and_timing():
+def _run(world, cfg_split, port_base):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = port_base + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_shard_worker, args=(r, world, port, q, cfg_split)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=120) for _ in procs)
+    res = [q.get(timeout=300) for _ in procs]
     for p in procs:
         p.join(timeout=60)
-    assert res[0][1] == [0, 1, 2] and res[1][1] == [3, 4]
-    assert res[0][2] == res[1][2] == 11.0
-    assert res[0][3] == res[1][3] == [0.0, 1.0]
+    for r in res:
+        assert r[1] is not None, f"rank {r[0]} failed:\n{r[2]}"
+    return res
 
 
-def _fake_unet(x, t, encoder_hidden_states=None, down_block_additional_residuals=None, return_dict=False):
-    """Stand-in for the native UNet (CUDA only): per-batch-element affine map, so halves are distinguishable."""
-    e = encoder_hidden_states.reshape(encoder_hidden_states.shape[0], -1).mean(dim=1).reshape(-1, 1, 1, 1, 1)
-    out = x * 0.5 + e
-    if down_block_additional_residuals is not None:
-        out = out + down_block_additional_residuals[0].mean()
-    return (out,)
+def test_frame_shards_reproduce_the_unsharded_unet_world2():
+    """2 frame shards, no CFG (the inversion loop's shape): GroupNorm all-reduce + motion-module re-sharding."""
+    from oracle import unet3d_oracle as O
+    sd, oc, lat, ehs2, res = _tiny_problem()
+    with torch.no_grad():
+        ref = O.unet_forward(sd, oc, lat, 501, ehs2[1:2], res)
+    for rank, frames, out in _run(2, False, 29500):
+        assert out.shape[2] == len(frames) == 2
+        assert torch.allclose(out, ref[:, :, frames[0]:frames[-1] + 1], atol=2e-5), (rank, (out - ref[:, :, frames[0]:frames[-1] + 1]).abs().max())
 
 
-def _test_combine(eps, latents, g, a_t, a_p, cfg):
-    from videoswap_b200 import ops
-    c_x, c_e = ops.ddim_coefficients(a_t, a_p)
-    e = eps[0:1] + g * (eps[1:2] - eps[0:1]) if cfg else eps
-    return c_x * latents + c_e * e
+def test_cfg_split_times_frame_shards_reproduce_the_step_world4():
+    """4 ranks = CFG pair x 2 frame shards: a full denoise step (UNet halves, eps all-gather, combine, DDIM)."""
+    from oracle import unet3d_oracle as O
+    sd, oc, lat, ehs2, res = _tiny_problem()
+    with torch.no_grad():
+        ref = O.denoise_step(sd, oc, O.DDIM(), lat, 981, 50, ehs2, 7.5, res)
+    got = _run(4, True, 33500)
+    assert sorted(r for r, _, _ in got) == [0, 1, 2, 3]
+    for rank, frames, out in got:
+        assert torch.allclose(out, ref[:, :, frames[0]:frames[-1] + 1], atol=2e-5), (rank, (out - ref[:, :, frames[0]:frames[-1] + 1]).abs().max())
+    # ranks 0 and 2 (the two CFG halves of frame shard 0) hold the same latents
+    by = {r: o for r, _, o in got}
+    assert torch.equal(by[0], by[2]) and torch.equal(by[1], by[3])
 
 
-def _cfg_worker(rank, world, port, q):
-    os.environ["MASTER_ADDR"] = "127.0.0.1"
-    os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    import videoswap_b200.pipeline as P
-    P._combine = _test_combine                      # the product's combine is CUDA-only; the exchange logic is what we test
-    pipe = P.VideoSwapPipeline.__new__(P.VideoSwapPipeline)
-    pipe.unet = _fake_unet
-    pipe.scheduler = P.DDIMScheduler()
-    pipe.scheduler.set_timesteps(50)
-    g = torch.Generator().manual_seed(7)
-    lat = torch.randn((1, 4, 2, 4, 4), generator=g)
-    emb = torch.randn((2, 77, 8), generator=g)
-    res = [torch.randn((4, 3, 4, 4), generator=g)]          # [(B F), C, h, w] with B = 2 (CFG), F = 2
-    split = pipe.step(lat, 981, emb, 7.5, [r.clone() for r in res], cfg_group=dist.group.WORLD)
-    q.put((rank, split))
-    dist.barrier()
-    dist.destroy_process_group()
-
-
-def test_cfg_split_two_ranks_equals_single_process():
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = 31500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_cfg_worker, args=(r, 2, port, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = dict(q.get(timeout=120) for _ in procs)
-    for p in procs:
-        p.join(timeout=60)
-    # single-process reference with the same fake UNet on the CFG batch of 2
-    import videoswap_b200.pipeline as P
-    g = torch.Generator().manual_seed(7)
-    lat = torch.randn((1, 4, 2, 4, 4), generator=g)
-    emb = torch.randn((2, 77, 8), generator=g)
-    r0 = torch.randn((4, 3, 4, 4), generator=g)
-    sched = P.DDIMScheduler()
-    sched.set_timesteps(50)
-    x2 = torch.cat([lat] * 2)
-    e = emb.reshape(2, -1).mean(dim=1).reshape(-1, 1, 1, 1, 1)
-    halves = r0.chunk(2, dim=0)
-    eps = torch.cat([x2[i:i + 1] * 0.5 + e[i:i + 1] + halves[i].mean() for i in range(2)])
-    ref = _test_combine(eps, lat, 7.5, *sched.alphas(981), True)
-    assert torch.allclose(res[0], ref, atol=1e-6) and torch.allclose(res[1], ref, atol=1e-6)
+def test_plan_layout():
+    p = [make_plan(8, r) for r in range(8)]
+    assert [x.cfg_index for x in p] == [0, 0, 0, 0, 1, 1, 1, 1] and [x.frame_shard for x in p] == [0, 1, 2, 3] * 2
+    assert p[5].frame_group == [4, 5, 6, 7] and p[5].cfg_group == [1, 5] and list(p[5].frame_range(16)) == [4, 5, 6, 7]
+    q = make_plan(2, 1)
+    assert (q.cfg_ranks, q.frame_shards, q.cfg_index, q.frame_group, q.cfg_group) == (2, 1, 1, [1], [0, 1])
+    inv = make_plan(4, 3, cfg=False)
+    assert (inv.cfg_ranks, inv.frame_shards, inv.frame_shard, inv.frame_group) == (1, 4, 3, [0, 1, 2, 3])
+    one = make_plan(1, 0)
+    assert one.world == 1 and one.frame_group == [0] and list(one.frame_range(16)) == list(range(16))
+    x = torch.arange(2 * 4 * 16).reshape(2, 4, 16)
+    assert torch.equal(p[2].shard_frames(x, 2), x[:, :, 8:12])
 
 
 def test_shard_jobs_covers_everything():

@@ -35,7 +35,7 @@ for label, (B, N, NK, C, kvdiv) in shapes.items():
     for r in range(reps + 2):
         for ci, c in enumerate(cfgs):
             for n in names:
-                ops.set_option(n, c.get(n, {"attn_persist": 1, "attn_poly": 0, "attn_handoff": 1, "attn_tc": 1}.get(n, 0)))
+                ops.set_option(n, c.get(n, {"attn_persist": 1, "attn_poly": 0, "attn_handoff": 1, "attn_tc": 1, "attn_epiwg": 1}.get(n, 0)))
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             o = ops.attention(q, k, v, 8, kv_div=kvdiv)
@@ -54,6 +54,29 @@ for label, (B, N, NK, C, kvdiv) in shapes.items():
         t = sorted(times[ci])[len(times[ci]) // 2]
         out[f"{label} | {args[ci]}"] = {"median_us": t, "min_us": min(times[ci]), "tflops": flops / t / 1e6}
         print(f"{label}: {args[ci]}: median {t:8.1f} us  ({flops / t / 1e6:6.1f} TFLOP/s)  min {min(times[ci]):8.1f}", flush=True)
+# ---- cycle breakdown of the instrumented persistent kernel at L0 self (softmax warp 4, lane 0; mean over the CTAs)
+import ctypes as C  # noqa: E402
+
+from videoswap_b200 import _lib  # noqa: E402
+qkv = torch.randn(32, 4096, 960, device=dev).half()
+q, k, v = qkv[..., :320], qkv[..., 320:640], qkv[..., 640:]
+for epiwg in (0, 1):
+    for n in ("attn_persist", "attn_debug", "attn_epiwg", "attn_poly"):
+        ops.set_option(n, {"attn_persist": 2, "attn_debug": 1, "attn_epiwg": epiwg, "attn_poly": 0}[n])
+    for _ in range(2):
+        ops.attention(q, k, v, 8)
+    torch.cuda.synchronize()
+    buf = (C.c_ulonglong * (148 * 16))()
+    _lib.call("vs_debug_read", buf, 148 * 16)
+    a = torch.tensor(list(buf), dtype=torch.float64).reshape(148, 16)
+    names = ["total", "wait_S", "wait_turn", "wait_Pbuf", "exp_phase", "epilogue", "wait_S_first_tile", "tiles",
+             "mma_total", "mma_wait_Q", "mma_wait_KV", "mma_wait_P0", "mma_wait_P1", "mma_wait_Vones", "mma_wait_Obuf", "items"]
+    mean, mx, mn = a.mean(0), a.max(0).values, a.min(0).values
+    out[f"debug_epiwg{epiwg}"] = {nm: {"mean": float(mean[i]), "min": float(mn[i]), "max": float(mx[i])} for i, nm in enumerate(names)}
+    print(f"debug epiwg={epiwg}: " + "  ".join(f"{nm}={mean[i]:.0f}[{mn[i]:.0f}..{mx[i]:.0f}]" for i, nm in enumerate(names)), flush=True)
+ops.set_option("attn_debug", 0)
+ops.set_option("attn_epiwg", 1)
+ops.set_option("attn_persist", 1)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 with open(os.path.join(ROOT, "gpurun_out", "attn_ab.json"), "w") as f:
     json.dump(out, f, indent=1)

@@ -93,6 +93,11 @@ extern "C" int vs_ln_linear(void* stream, const void* d_x, int M, int C, const v
   if (d_pe) { g.rowvec = d_cpe; g.ldrv = N; g.pix_per_batch = hw; g.rv_mod = frames; }
   return gemm_tc(st, g);
 }
+extern "C" int vs_debug_read(unsigned long long* host_out, int n) {
+  VS_REQUIRE(host_out && n > 0 && n <= 256 * 16, "vs_debug_read: bad arguments");
+  VS_REQUIRE(attention_debug_read(host_out, n) == 0, "vs_debug_read: no debug counters recorded (set option attn_debug)");
+  return 0;
+}
 extern "C" int vs_linear_ln_linear(void* stream, const void* d_x0, int M, int K0, const void* d_w0, const float* d_b0,
                                    const void* d_residual, int C, void* d_x, const void* d_w, const float* d_bias, int N,
                                    const float* d_gamma, const float* d_beta, int mode, void* d_wf, float* d_u, float* d_c,

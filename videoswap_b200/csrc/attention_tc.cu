@@ -57,6 +57,7 @@ struct TAttnArgs {
   int nq, nk, kv_div;
   float scale_log2;
   int heads, n_qblk, n_items;   // persistent kernel: work item = (batch, head, 256-query block), q block fastest
+  unsigned long long* dbg;      // DBG builds: per-CTA cycle breakdown (16 counters: softmax warp 4, MMA warp)
 };
 
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
@@ -386,9 +387,13 @@ __device__ __forceinline__ float exp2_fma(float x) {
 // of it for the 2-tile cross-attention CTAs) and the wave tail.  O needs no double buffering: P V of item n+1 / tile i
 // is only issued after p_full(i), which warpgroup i signals after its epilogue of item n.
 // NPOLY of the 8 sixteen-byte P chunks per key tile take their exponentials from exp2_fma instead of MUFU.EX2.
-template <int D, int HO, int NPOLY>
-__global__ void __launch_bounds__(ATT_THREADS, 1) attn_tcp_kernel(const __grid_constant__ TAttnArgs p) {
+// EPIWG (d <= 64, where TMEM has room for a second pair of O accumulators): a fourth warpgroup (warps 12-15) writes the
+// finished O tiles out, so the two softmax warpgroups run one uninterrupted stream of key tiles -- with the epilogue
+// inside the softmax warpgroups the strict MUFU ping-pong stalls both of them at every item boundary.
+template <int D, int HO, int NPOLY, bool EPIWG, bool DBG>
+__global__ void __launch_bounds__(EPIWG ? ATT_THREADS + 128 : ATT_THREADS, 1) attn_tcp_kernel(const __grid_constant__ TAttnArgs p) {
   using C = TCfg<D>;
+  static_assert(!EPIWG || C::O_COL + 4 * C::O_STRIDE <= 512, "no TMEM room for double-buffered O");
   constexpr int QB = (D <= 64) ? 2 : 1;                        // Q buffers
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -404,8 +409,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tcp_kernel(const __grid_c
   auto s_full = [&](int i, int b) { return bars + 8u * (4 + 3 * C::ST + 2 * i + b); };
   auto p_full = [&](int i, int b) { return bars + 8u * (8 + 3 * C::ST + 2 * i + b); };
   auto p_empty = [&](int i, int b) { return bars + 8u * (12 + 3 * C::ST + 2 * i + b); };
-  auto o_full = [&](int i) { return bars + 8u * (16 + 3 * C::ST + i); };
-  const uint32_t tmem_slot = bars + 8u * (18 + 3 * C::ST);
+  auto o_full = [&](int i, int ob) { return bars + 8u * (16 + 3 * C::ST + 2 * i + ob); };    // per (tile, O buffer)
+  auto o_empty = [&](int i, int ob) { return bars + 8u * (20 + 3 * C::ST + 2 * i + ob); };
+  const uint32_t tmem_slot = bars + 8u * (24 + 3 * C::ST);
+  auto o_col = [&](int i, uint32_t n) { return (uint32_t)(C::O_COL + (EPIWG ? ((n & 1) * 2 + i) : i) * C::O_STRIDE); };
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -421,8 +428,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tcp_kernel(const __grid_c
         mbar_init(s_full(i, bb), 1);
         mbar_init(p_full(i, bb), 128);
         mbar_init(p_empty(i, bb), 1);
+        mbar_init(o_full(i, bb), 1);
+        mbar_init(o_empty(i, bb), 128);
       }
-      mbar_init(o_full(i), 1);
     }
     fence_barrier_init();
   }
@@ -473,11 +481,19 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tcp_kernel(const __grid_c
     const uint32_t total = (uint32_t)my_items * (uint32_t)nkt;               // key tiles this CTA walks
     // Q K^T cursor: runs two key tiles ahead of the P V cursor, across item boundaries
     uint32_t gq = 0, nq_item = 0; int jq = 0;
+    long long m_q = 0, m_kv = 0, m_p0 = 0, m_p1 = 0, m_v = 0, m_oe = 0, m_t0 = 0;
+    const bool mdbg = DBG && lane == 0 && p.dbg != nullptr;
+#define VS_MT() (mdbg ? clock64() : 0LL)
+    if (DBG) m_t0 = VS_MT();
     auto issue_qk = [&](int i) {
       const uint32_t s = gq % C::ST, qb = nq_item % QB;
       if (i == 0) {
+        long long ta = 0;
+        if (DBG) ta = VS_MT();
         if (jq == 0) mbar_wait(q_full(qb), (nq_item / QB) & 1);
+        if (DBG) { const long long tb = VS_MT(); m_q += tb - ta; ta = tb; }
         mbar_wait(kv_full(s), (gq / C::ST) & 1);
+        if (DBG) m_kv += VS_MT() - ta;
         tc_fence_after();
       }
       if (elect_one()) {
@@ -497,29 +513,41 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tcp_kernel(const __grid_c
     };
     for (int a = 0; a < 2 && gq < total; ++a) { issue_qk(0); issue_qk(1); }
     int j = 0;
+    uint32_t n = 0;                                  // item of the P V cursor
     for (uint32_t g = 0; g < total; ++g) {
       const uint32_t s = g % C::ST, sph = (g / C::ST) & 1;
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
+        long long ta = 0;
+        if (DBG) ta = VS_MT();
         mbar_wait(p_full(i, g & 1), (g >> 1) & 1);
+        if (DBG) { const long long tb = VS_MT(); if (i == 0) m_p0 += tb - ta; else m_p1 += tb - ta; ta = tb; }
         if (i == 0) mbar_wait(v_ready(s), sph);      // ones column of this V tile is in place
+        if (DBG) { const long long tb = VS_MT(); m_v += tb - ta; ta = tb; }
+        if (EPIWG && j == 0 && n >= 2) mbar_wait(o_empty(i, n & 1), ((n >> 1) - 1) & 1);   // the epilogue warps drained this O buffer
+        if (DBG) m_oe += VS_MT() - ta;
         tc_fence_after();
         if (elect_one()) {
           const uint32_t pa = p_s + (2 * i + (g & 1)) * C::P_TILE_BYTES;
           const uint32_t va = kv_s + s * C::KV_STAGE_BYTES + C::NCB * C::KV_BLOCK_BYTES;
 #pragma unroll
           for (int k = 0; k < BKV / 16; ++k)
-            tc_mma_f16(tmem + C::O_COL + i * C::O_STRIDE, umma_desc_sw128_kmajor(pa + k * 32),
+            tc_mma_f16(tmem + o_col(i, n), umma_desc_sw128_kmajor(pa + k * 32),
                        umma_desc_sw128_mnmajor(va + k * 16 * 128, C::KV_BLOCK_BYTES), idesc_pv, (j > 0 || k != 0) ? 1u : 0u);
           tc_commit(p_empty(i, g & 1));              // this P buffer consumed, O_i quiescent once this retires
           if (i == 1) tc_commit(kv_empty(s));        // K_j / V_j fully consumed once these MMAs retire
-          if (j == nkt - 1) tc_commit(o_full(i));    // O_i of this item complete
+          if (j == nkt - 1) tc_commit(o_full(i, EPIWG ? (n & 1) : 0));   // O_i of this item complete
         }
         __syncwarp();
         if (gq < total) issue_qk(i);                 // S_{i, g&1} was drained by the softmax before it signalled p_full
       }
-      if (++j == nkt) j = 0;
+      if (++j == nkt) { j = 0; ++n; }
     }
+    if (mdbg) {
+      unsigned long long* d = p.dbg + 16 * blockIdx.x + 8;
+      d[0] = (unsigned long long)(clock64() - m_t0); d[1] = m_q; d[2] = m_kv; d[3] = m_p0; d[4] = m_p1; d[5] = m_v; d[6] = m_oe; d[7] = n;
+    }
+#undef VS_MT
   } else if (warp == 3) {
     // ================================================================ ones column: V[:, D] = 1 for every landed V tile
     constexpr int blk = D / 64, chunk = ((D % 64) * 2) / 16, within = ((D % 64) * 2) % 16;
@@ -538,22 +566,30 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tcp_kernel(const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive(v_ready(s));
     }
-  } else if (warp >= 4) {
-    // ================================================================ softmax warpgroups + epilogue
+  } else if (warp >= 4 && warp < 12) {
+    // ================================================================ softmax warpgroups (+ epilogue unless EPIWG)
     const int i = (warp - 4) >> 2;               // query tile handled by this warpgroup
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;         // query row inside the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    const uint32_t o_addr = tmem + lane_addr + C::O_COL + i * C::O_STRIDE;
     const uint32_t p_row0 = p_s + 2 * i * C::P_TILE_BYTES + row * 128;
     const float sc = p.scale_log2;
+    // DBG: cycle breakdown seen by lane 0 of warp 4: [0] total [1] wait S [2] wait turn [3] wait P buffer / rescale
+    // [4] exponential phase [5] epilogue [6] items [7] key tiles
+    long long t_ws = 0, t_ws0 = 0, t_wt = 0, t_wp = 0, t_ex = 0, t_ep = 0, t0 = 0, tt = 0;
+    const bool dbg = DBG && warp == 4 && lane == 0 && p.dbg != nullptr;
+#define VS_TICK() (dbg ? clock64() : 0LL)
+    if (DBG) t0 = VS_TICK();
     if (i == 1) named_bar_arrive(9 + 0, 256);    // warpgroup 0 goes first on the MUFU pipe
     uint32_t g = 0, n = 0;
     for (int item = item0; item < p.n_items; item += istep, ++n) {
       const int qblk = item % p.n_qblk, bh = item / p.n_qblk, head = bh % p.heads, b = bh / p.heads;
+      const uint32_t o_addr = tmem + lane_addr + o_col(i, n);
       float m_used = -INFINITY;
       for (int j = 0; j < nkt; ++j, ++g) {
+        if (DBG) tt = VS_TICK();
         mbar_wait(s_full(i, g & 1), (g >> 1) & 1);
+        if (DBG) { const long long dt = VS_TICK() - tt; if (j == 0) t_ws0 += dt; else t_ws += dt; }
         tc_fence_after();
         const int kbase = j * BKV;
         uint32_t sv[BKV];
@@ -578,6 +614,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tcp_kernel(const __grid_c
         // lazy rescale: only when the maximum moved by more than 2^8 (always "needed" on the first tile: m_used = -inf,
         // but there O is overwritten by the non-accumulating P V, so nothing is rescaled)
         const bool need = (mx - m_used) * sc > 8.f;
+        if (DBG) tt = VS_TICK();
         if (j > 0 && __any_sync(0xffffffffu, need)) {
           mbar_wait(p_empty(i, (g - 1) & 1), ((g - 1) >> 1) & 1);       // O_i quiescent: the previous P V has retired
           tc_fence_after();
@@ -596,8 +633,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tcp_kernel(const __grid_c
         if (need) m_used = mx;
         const float ms = m_used * sc;
         if (g >= 2) mbar_wait(p_empty(i, g & 1), ((g - 2) >> 1) & 1);   // this P buffer was consumed two key tiles ago
+        if (DBG) { const long long t = VS_TICK(); t_wp += t - tt; tt = t; }
         const uint32_t p_row = p_row0 + (g & 1) * C::P_TILE_BYTES;
         named_bar_sync(9 + i, 256);                                       // my turn on the MUFU pipe
+        if (DBG) { const long long t = VS_TICK(); t_wt += t - tt; tt = t; }
 #pragma unroll
         for (int c8 = 0; c8 < BKV / 8; ++c8) {       // one 16-byte chunk (8 keys) at a time
           // chunks spread evenly over the tile take the FMA-pipe exponential (NPOLY of 8)
@@ -619,9 +658,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tcp_kernel(const __grid_c
         fence_proxy_async();                     // generic-proxy smem writes -> visible to the tensor-core (async) proxy
         tc_fence_before();
         mbar_arrive(p_full(i, g & 1));
+        if (DBG) t_ex += VS_TICK() - tt;
       }
-      // ---- epilogue of this item: O / l -> fp16 -> HBM (the other warpgroup keeps the MUFU pipe busy meanwhile)
-      mbar_wait(o_full(i), n & 1);
+      if (EPIWG) continue;                       // warps 12-15 write O out
+      // ---- epilogue of this item: O / l -> fp16 -> HBM
+      if (DBG) tt = VS_TICK();
+      mbar_wait(o_full(i, 0), n & 1);
       tc_fence_after();
       const int qrow = qblk * 2 * TQ + i * TQ + row;
       float inv;
@@ -652,8 +694,59 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tcp_kernel(const __grid_c
         }
       }
       tc_fence_before();                         // the O reads above are ordered before this warpgroup's next p_full arrive
+      if (DBG) t_ep += VS_TICK() - tt;
     }
     if (i == 0) named_bar_sync(9 + 0, 256);      // absorb the other warpgroup's last hand-over
+    if (dbg) {
+      unsigned long long* d = p.dbg + 16 * blockIdx.x;
+      d[0] = (unsigned long long)(clock64() - t0); d[1] = t_ws; d[2] = t_wt; d[3] = t_wp; d[4] = t_ex; d[5] = t_ep; d[6] = t_ws0; d[7] = g;
+    }
+#undef VS_TICK
+  } else if (EPIWG && warp >= 12) {
+    // ================================================================ epilogue warpgroup: O / l -> fp16 -> HBM
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    uint32_t n = 0;
+    for (int item = item0; item < p.n_items; item += istep, ++n) {
+      const int qblk = item % p.n_qblk, bh = item / p.n_qblk, head = bh % p.heads, b = bh / p.heads;
+#pragma unroll 1
+      for (int i = 0; i < 2; ++i) {
+        mbar_wait(o_full(i, n & 1), (n >> 1) & 1);
+        tc_fence_after();
+        const uint32_t o_addr = tmem + lane_addr + o_col(i, n);
+        const int qrow = qblk * 2 * TQ + i * TQ + row;
+        float inv;
+        {
+          uint32_t v[16];
+          tmem_ld16(o_addr + (D / 16) * 16, v);
+          tmem_ld_wait();
+          inv = 1.f / __uint_as_float(v[D % 16]);
+        }
+        __half* orow = p.o + b * p.o_bs + (long long)qrow * p.ldo + head * D;
+#pragma unroll 1
+        for (int c0 = 0; c0 < C::DPO; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(o_addr + c0, v);
+          tmem_ld_wait();
+          if (qrow < p.nq) {
+#pragma unroll
+            for (int t = 0; t < 16; t += 8) {
+              if (c0 + t < D) {
+                uint4 o4;
+                __half2* h = reinterpret_cast<__half2*>(&o4);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  h[u] = __floats2half2_rn(__uint_as_float(v[t + 2 * u]) * inv, __uint_as_float(v[t + 2 * u + 1]) * inv);
+                *reinterpret_cast<uint4*>(orow + c0 + t) = o4;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(o_empty(i, n & 1));          // this O buffer may be overwritten by the item after next
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -663,15 +756,17 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tcp_kernel(const __grid_c
   }
 }
 
-template <int D, int HO, int NPOLY, bool PERSIST>
+unsigned long long* g_attn_dbg = nullptr;     // 148 x 8 counters (DBG kernels), see vs_debug_read
+
+template <int D, int HO, int NPOLY, bool PERSIST, bool EPIWG = false, bool DBG = false>
 int launch(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv, __half* o, int ldo,
            int batch, int nq, int nk, int heads, long long q_bs, long long kv_bs, long long o_bs, int kv_div) {
   using C = TCfg<D>;
-  constexpr int SMEM_P = C::SMEM + ((D <= 64) ? C::Q_BYTES : 0) + 64;      // persistent: second Q buffer, more barriers
+  constexpr int SMEM_P = C::SMEM + ((D <= 64) ? C::Q_BYTES : 0) + 128;     // persistent: second Q buffer, more barriers
   static_assert(SMEM_P <= 227 * 1024, "shared memory budget (persistent)");
   static bool configured = false;
   if (!configured) {
-    if constexpr (PERSIST) VS_CHECK_CUDA(cudaFuncSetAttribute(attn_tcp_kernel<D, HO, NPOLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_P));
+    if constexpr (PERSIST) VS_CHECK_CUDA(cudaFuncSetAttribute(attn_tcp_kernel<D, HO, NPOLY, EPIWG, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_P));
     else VS_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D, HO>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     configured = true;
   }
@@ -700,7 +795,12 @@ int launch(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, 
   ProfScope prof(st, PC_ATTN, 4.0 * batch * heads * (double)nq * nk * D, 1, nq, nk, D);
   if constexpr (PERSIST) {
     const int ctas = a.n_items < num_sms() ? a.n_items : num_sms();
-    return launch_pdl(attn_tcp_kernel<D, HO, NPOLY>, dim3(ctas), dim3(ATT_THREADS), SMEM_P, st, 1, a);
+    if (DBG) {
+      if (!g_attn_dbg) { VS_CHECK_CUDA(cudaMalloc(&g_attn_dbg, 256 * 16 * sizeof(unsigned long long))); }
+      VS_CHECK_CUDA(cudaMemsetAsync(g_attn_dbg, 0, 256 * 16 * sizeof(unsigned long long), st));
+      a.dbg = g_attn_dbg;
+    }
+    return launch_pdl(attn_tcp_kernel<D, HO, NPOLY, EPIWG, DBG>, dim3(ctas), dim3(EPIWG ? ATT_THREADS + 128 : ATT_THREADS), SMEM_P, st, 1, a);
   }
   else {
     dim3 grid(a.n_qblk, heads, batch);
@@ -709,6 +809,11 @@ int launch(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, 
 }
 
 }  // namespace
+
+int attention_debug_read(unsigned long long* host, int n) {
+  if (!g_attn_dbg) return 1;
+  return cudaMemcpy(host, g_attn_dbg, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 1;
+}
 
 // Returns -1 when the shape is not handled by the tcgen05 kernel (caller falls back to the mma.sync kernel).
 int attention_tc(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv, __half* o,
@@ -722,8 +827,24 @@ int attention_tc(cudaStream_t st, const __half* q, int ldq, const __half* k, int
   const bool early = get_option("attn_handoff") != 0;
   // "attn_persist" (default 1): persistent CTAs; 0 = one CTA per (batch, head, 256 queries) as in round 1 (A/B switch).
   // "attn_poly": how many of the 8 P chunks per key tile take exp2 from the FMA pipe (0, 1, 2, 3; persistent kernel only).
-  if (get_option("attn_persist") != 0) {
+  // 1 (default) = where it measured faster: short key sequences (cross-attention: the per-CTA prologue dominated) and
+  // d = 80; the long d = 40 self-attention keeps one CTA per item (1541 vs 1731 us at N = 4096, profiles/r02_attn_ab_*);
+  // 2 = always, 0 = never.
+  const int pers = get_option("attn_persist");
+  const int nkt_host = (nk + BKV - 1) / BKV;
+  if (pers == 2 || (pers == 1 && (d == 80 || nkt_host <= 8)) || (pers != 0 && get_option("attn_debug") != 0)) {
     const int np = get_option("attn_poly");
+    // "attn_epiwg" (default 1): a dedicated epilogue warpgroup for d = 40 (see attn_tcp_kernel); "attn_debug": cycle counters
+    const bool epiwg = get_option("attn_epiwg") != 0;
+    if (d == 40 && get_option("attn_debug") != 0)
+      return epiwg ? launch<40, 6, 0, true, true, true>(VS_ATT_ARGS) : launch<40, 6, 0, true, false, true>(VS_ATT_ARGS);
+    if (d == 40 && epiwg) {
+      switch (np) {
+        case 0: return launch<40, 6, 0, true, true>(VS_ATT_ARGS);
+        case 1: return launch<40, 6, 1, true, true>(VS_ATT_ARGS);
+        default: return launch<40, 6, 2, true, true>(VS_ATT_ARGS);
+      }
+    }
     if (d == 40) {
       switch (np) {
         case 0: return launch<40, 6, 0, true>(VS_ATT_ARGS);

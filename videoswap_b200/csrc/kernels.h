@@ -75,6 +75,7 @@ int attention(cudaStream_t st, const __half* q, int ldq, const __half* k, int ld
 int attention_tc(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv,
                  __half* o, int ldo, int batch, int nq, int nk, int heads, int d, long long q_bstride,
                  long long kv_bstride, long long o_bstride, int kv_div);
+int attention_debug_read(unsigned long long* host, int n);   // counters of the "attn_debug" kernels (148 x 8)
 // runtime options: "attn_tc" (1 = use the tcgen05 attention kernel where supported, default 1)
 int set_option(const char* name, int value);
 int get_option(const char* name);

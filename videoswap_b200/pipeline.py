@@ -114,28 +114,34 @@ class VideoSwapPipeline:
         return res
 
     @torch.no_grad()
+    def step_sharded(self, latents: torch.Tensor, t, embeds: torch.Tensor, guidance_scale: float, plan,
+                     residuals: Optional[List[torch.Tensor]] = None, coef: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """The loop body on ONE video split over ranks (dist_util.ShardPlan).  `latents` [1,4,F/k,h,w] and
+        `residuals` 4 x [(F/k),C,h,w] hold THIS rank's frames; `embeds` is the full [2,...] (uncond first).  The rank runs the
+        UNet on its CFG half (batch 1; GroupNorm statistics and the motion modules exchange inside the library), the two
+        halves swap their noise predictions, and both compute the same DDIM update for their frames."""
+        from . import dist_util
+        cfg = guidance_scale > 1.0
+        if cfg and plan.cfg_ranks != 2:
+            raise ValueError("frame sharding under CFG needs the CFG split (one batch element per rank)")
+        e = embeds[plan.cfg_index:plan.cfg_index + 1] if cfg else embeds
+        res = [r for r in residuals] if residuals is not None else None
+        eps = self.unet(latents, t, encoder_hidden_states=e, down_block_additional_residuals=res, return_dict=False)[0]
+        if cfg:
+            eps = dist_util.all_gather_cfg(plan, eps)
+        if coef is not None:
+            return ops.cfg_ddim_step(eps, latents, guidance_scale, cfg=cfg, coef=coef)
+        a_t, a_p = self.scheduler.alphas(t)
+        return ops.cfg_ddim_step(eps, latents, guidance_scale, a_t, a_p, cfg=cfg)
+
+    @torch.no_grad()
     def step(self, latents: torch.Tensor, t: int, embeds: torch.Tensor, guidance_scale: float = 7.5,
-             residuals: Optional[List[torch.Tensor]] = None, cfg_group=None) -> torch.Tensor:
+             residuals: Optional[List[torch.Tensor]] = None) -> torch.Tensor:
         """One loop body (pipeline_videoswap.py:556-587): CFG batch duplication -> UNet -> CFG combine -> DDIM step.
         `embeds` is [2,...] (uncond first) when guidance_scale > 1 else [1,...]; `scheduler.set_timesteps` must have
         been called.  Returns the new latents."""
         cfg = guidance_scale > 1.0
         a_t, a_p = self.scheduler.alphas(t)
-        if cfg and cfg_group is not None:
-            # CFG split over two ranks (SURVEY 8e): the uncond / cond halves are independent through the whole UNet
-            # (GroupNorm statistics are per batch element), so rank r runs batch element r only and the two 0.5 MB
-            # noise predictions are exchanged with ONE all-gather (NCCL over NVLink) right before the combine.
-            import torch.distributed as dist
-            r = dist.get_rank(cfg_group)
-            assert dist.get_world_size(cfg_group) == 2, "CFG split needs a process group of exactly two ranks"
-            res_r = None
-            if residuals is not None:
-                res_r = [x.chunk(2, dim=0)[r].contiguous() for x in residuals]
-            eps_r = self.unet(latents, t, encoder_hidden_states=embeds[r:r + 1], down_block_additional_residuals=res_r,
-                              return_dict=False)[0]
-            eps = torch.empty((2,) + tuple(eps_r.shape[1:]), dtype=eps_r.dtype, device=eps_r.device)
-            dist.all_gather_into_tensor(eps, eps_r.contiguous(), group=cfg_group)
-            return _combine(eps, latents, guidance_scale, a_t, a_p, True)
         x_in = torch.cat([latents] * 2) if cfg else latents
         x_in = self.scheduler.scale_model_input(x_in, t)
         eps = self.unet(x_in, t, encoder_hidden_states=embeds, down_block_additional_residuals=residuals, return_dict=False)[0]
@@ -219,10 +225,11 @@ class GraphedStep:
     static.  Removes ~750 kernel-launch gaps per step."""
 
     def __init__(self, pipe: VideoSwapPipeline, latents: torch.Tensor, embeds: torch.Tensor, guidance_scale: float = 7.5,
-                 residuals: Optional[List[torch.Tensor]] = None, inverse: bool = False):
+                 residuals: Optional[List[torch.Tensor]] = None, inverse: bool = False, plan=None):
         """inverse=True: the DDIM-inversion loop body (pipeline_videoswap.py:677-696, no CFG) -- `__call__` then takes the
         inverse scheduler's timesteps and coefficients."""
         self.pipe, self.guidance, self.residuals, self.inverse = pipe, guidance_scale, residuals, inverse
+        self.plan = plan if (plan is not None and plan.world > 1) else None    # sharded: latents / residuals are this rank's frames
         if inverse:
             assert guidance_scale <= 1.0 and residuals is None, "the inversion loop runs without CFG and without adapter residuals"
             if pipe.inverse_scheduler.num_inference_steps is None:
@@ -258,6 +265,9 @@ class GraphedStep:
             pass
 
     def _body(self):
+        if self.plan is not None:      # the NCCL exchanges are captured with the kernels
+            return self.pipe.step_sharded(self.lat, self._d[0:1], self.embeds, self.guidance, self.plan, self.residuals,
+                                          coef=self._d[1:3])
         cfg = self.guidance > 1.0
         x_in = torch.cat([self.lat] * 2) if cfg else self.lat
         res = list(self.residuals) if self.residuals is not None else None
