@@ -94,6 +94,34 @@ int vs_comm_all_gather(vs_comm* c, void* stream, const void* d_send, void* d_rec
 int vs_comm_all_reduce_sum_f32(vs_comm* c, void* stream, float* d_buf, size_t n);
 int vs_unet_set_frame_shard(vs_unet* h, vs_comm* frame_comm, int shard, int nshards);
 
+/* ---- attention controllers (prompt-to-prompt; utils/p2p_utils/attention_register.py:15-97,140-150) ---------------------
+ * The reference swaps a control processor into every attn1 / attn2: layers with fewer than 32^2 queries materialise their
+ * softmax probabilities [(b f), heads, s, t] and pass them through `controller(attn, is_cross, place_in_unet)` before P V.
+ * Here: while a hook is set, vs_unet_forward runs exactly those layers (the 16x16 / 8x8 levels) through the explicit-
+ * probability kernels and calls the hook between the softmax and P V with the DEVICE tensor (fp16, contiguous); the hook
+ * may read it (store) and overwrite it in place (refine / replace) with work enqueued on `stream`.  `layer` = index of the
+ * transformer block in registration order (down -> mid -> up, 0..15), `place` = 0 down / 1 mid / 2 up.  Hook mode runs
+ * eagerly (it cannot be captured in a CUDA graph).  max_queries <= 0 selects the reference's 32^2. */
+typedef void (*vs_attention_hook)(void* user, int layer, int is_cross, int place, void* d_probs, int batch, int heads, int nq,
+                                  int nk, void* stream);
+int vs_unet_set_attention_hook(vs_unet* h, vs_attention_hook hook, void* user, int max_queries);
+/* The two halves of that path as stand-alone entry points (parity tests): probabilities [batch, heads, nq, nk] fp16, then
+ * O = P V.  Same argument conventions as vs_attention. */
+int vs_attention_probs(void* stream, const void* d_q, int ldq, const void* d_k, int ldk, void* d_probs, int batch, int nq, int nk,
+                       int heads, int d, long long q_bstride, long long kv_bstride, int kv_div);
+int vs_attention_apply_probs(void* stream, const void* d_probs, const void* d_v, int ldv, void* d_o, int ldo, int batch, int nq,
+                             int nk, int heads, int d, long long kv_bstride, long long o_bstride, int kv_div);
+/* Latent blend of the controllers (utils/p2p_utils/spatial_blend.py:25-63,141-142) on device.
+ * vs_blend_mask: d_maps = DEVICE array of n_maps * n_prompts pointers (layer-major, prompt 0 = source, 1 = target), each an
+ * fp16 cross-attention map [frames, heads, res_h * res_w, words]; d_alpha [n_prompts, words] fp32 word selector;
+ * mask[p, f, y, x] = (nearest-resize(maxpool3x3(mean_{layer,head} sum_w alpha map)) / max > threshold), and with `both`
+ * mask[p] |= mask[0].  d_mask: [n_prompts, frames, h, w] fp32.
+ * vs_latent_blend: x_tgt = x_src + mask * (x_tgt - x_src), x [channels, frames, h*w] (fp16 or fp32), mask [frames, h*w]. */
+int vs_blend_mask(void* stream, const void* const* d_maps, int n_maps, int n_prompts, int frames, int heads, int res_h, int res_w,
+                  int words, const float* d_alpha, int pool, int h, int w, float threshold, int both, float* d_mask);
+int vs_latent_blend(void* stream, const void* d_x_src, void* d_x_tgt, const float* d_mask, int io_f32, int channels, int frames,
+                    int hw);
+
 /* Debug taps: after the next forward, copies of named intermediate activations (NHWC fp16) can be fetched. */
 int vs_unet_enable_taps(vs_unet* h, int enable);
 int vs_unet_num_taps(const vs_unet* h);

@@ -49,6 +49,12 @@ class OracleConfig:
 Tensor = torch.Tensor
 SD = Dict[str, Tensor]
 
+# Attention controller hook (utils/p2p_utils/attention_register.py:15-97,140-150): when set, every spatial attention with
+# fewer than 32^2 queries passes its probabilities [b, h, s, t] through ATTN_HOOK(probs, is_cross, place_in_unet) between
+# the softmax and P V, exactly where the reference's control processors call `self.controller(...)`.
+ATTN_HOOK = None
+_PLACE = "down"
+
 # False: softmax(q k^T) v spelled out (the arithmetic the oracle is pinned with).  True: F.scaled_dot_product_attention,
 # used only when bench.py runs this same graph in fp16 on the GPU as the "library baseline" (cuDNN / cuBLASLt / SDPA).
 USE_SDPA = False
@@ -102,10 +108,20 @@ def _mha(q: Tensor, k: Tensor, v: Tensor, heads: int) -> Tensor:
     return o.transpose(1, 2).reshape(b, nq, c)
 
 
-def _attn(sd: SD, p: str, x: Tensor, ctx: Tensor, heads: int) -> Tensor:
+def _attn(sd: SD, p: str, x: Tensor, ctx: Tensor, heads: int, is_cross: Optional[bool] = None) -> Tensor:
     q = _lin(sd, p + ".to_q", x)
     k = _lin(sd, p + ".to_k", ctx)
     v = _lin(sd, p + ".to_v", ctx)
+    if ATTN_HOOK is not None and is_cross is not None and q.shape[1] < 32 ** 2:
+        b, nq, c = q.shape
+        d = c // heads
+        qh = q.reshape(b, nq, heads, d).transpose(1, 2)
+        kh = k.reshape(b, k.shape[1], heads, d).transpose(1, 2)
+        vh = v.reshape(b, v.shape[1], heads, d).transpose(1, 2)
+        probs = (torch.matmul(qh, kh.transpose(-1, -2)) * (d ** -0.5)).softmax(dim=-1)       # get_attention_scores
+        probs = ATTN_HOOK(probs, is_cross, _PLACE)
+        o = torch.matmul(probs, vh).transpose(1, 2).reshape(b, nq, c)
+        return _lin(sd, p + ".to_out.0", o)
     return _lin(sd, p + ".to_out.0", _mha(q, k, v, heads))
 
 
@@ -158,8 +174,8 @@ def transformer3d(sd: SD, p: str, x: Tensor, ehs: Tensor, layer_idx: int, cfg: O
     t = t.permute(0, 2, 3, 1).reshape(b * f, h * w, c)
     q = p + ".transformer_blocks.0"
     n1 = _ln(sd, q + ".norm1", t)
-    t = t + _attn(sd, q + ".attn1", n1, n1, cfg.heads)
-    t = t + _attn(sd, q + ".attn2", _ln(sd, q + ".norm2", t), ctx, cfg.heads)
+    t = t + _attn(sd, q + ".attn1", n1, n1, cfg.heads, is_cross=False)
+    t = t + _attn(sd, q + ".attn2", _ln(sd, q + ".norm2", t), ctx, cfg.heads, is_cross=True)
     t = t + _geglu_ff(sd, q + ".ff", _ln(sd, q + ".norm3", t))
     t = t.reshape(b * f, h, w, c).permute(0, 3, 1, 2)
     t = F.conv2d(t, sd[p + ".proj_out.weight"], sd[p + ".proj_out.bias"])
@@ -222,6 +238,8 @@ def unet_forward(sd: SD, cfg: OracleConfig, sample: Tensor, timestep, ehs: Tenso
     skips = [x]
     attn_idx = 0
     nlev = len(boc)
+    global _PLACE
+    _PLACE = "down"
     # down path
     for i in range(nlev):
         cross = i < nlev - 1            # CrossAttn x3 then DownBlock3D (unet.py:47-52)
@@ -244,6 +262,7 @@ def unet_forward(sd: SD, cfg: OracleConfig, sample: Tensor, timestep, ehs: Tenso
         if not cross and res is not None:
             x = _add_residual(x, res)              # after the block; skips unaffected (P6)
     # mid
+    _PLACE = "mid"
     x = resnet_block(sd, "mid_block.resnets.0", x, temb, cfg)
     x = transformer3d(sd, "mid_block.attentions.0", x, ehs, attn_idx, cfg)
     attn_idx += 1
@@ -252,6 +271,7 @@ def unet_forward(sd: SD, cfg: OracleConfig, sample: Tensor, timestep, ehs: Tenso
     x = resnet_block(sd, "mid_block.resnets.1", x, temb, cfg)
     tap("mid_block", x)
     # up path
+    _PLACE = "up"
     for i in range(nlev):
         cross = i > 0                   # UpBlock3D then CrossAttnUp x3
         p = f"up_blocks.{i}"

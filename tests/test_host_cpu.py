@@ -182,3 +182,35 @@ def test_inverse_scheduler_conventions_and_alpha_table():
         assert abs(a_nxt - ac[t]) < 2e-6 and abs(a_cur - (ac[t - 20] if t >= 20 else ac[0])) < 2e-6
     with pytest.raises(ValueError):
         V.DDIMInverseScheduler(convention="0.20")
+
+
+def test_attention_control_registration_and_store_protocol():
+    """SURVEY 8f-2, host side: register_attention_control walks attn1 / attn2 like the reference
+    (attention_register.py:176-211: 16 + 16 layers, ED-LoRA index on the cross layers), and the device-agnostic part of the
+    store follows attention_store.py (only the conditional half under CFG, running sum, per-step list)."""
+    from videoswap_b200 import p2p
+    m = V.AnimateDiffUNet3DModel(init="empty")
+    ctl = p2p.AttentionStore()
+    assert p2p.register_attention_control(m, ctl) == 32 and ctl.num_att_layers == 32
+    a2 = m.up_blocks[1].attentions[0].transformer_blocks[0].attn2.processor
+    assert isinstance(a2, p2p.EDLoRA_AttnControlProcessor) and a2.place_in_unet == "up" and a2.controller is ctl
+    assert a2.cross_attention_idx == 7                       # 6 down + 1 mid before the first up transformer
+    assert m._check_processors() is ctl
+    p2p.register_attention_control(m, None)
+    assert m._check_processors() is None
+    # store protocol on plain tensors
+    ctl = p2p.AttentionStore()
+    for step in range(2):
+        for place, cross in (("down", False), ("down", True), ("up", True)):
+            attn = torch.full((4, 2, 16, 77 if cross else 16), float(step + 1))
+            attn[:2] = -1.0                                  # unconditional half: must never be stored
+            out = ctl(attn, cross, place)
+            assert out is attn
+        big = torch.zeros((4, 2, 1024, 16))
+        ctl(big, False, "up")                                # >= 32^2 queries: passes through, not stored
+        ctl.step_callback(torch.zeros(1, 4, 2, 8, 8))
+    assert ctl.cur_step == 2 and len(ctl.attention_store_all_step) == 2 and len(ctl.latents_store) == 2
+    assert [len(v) for v in ctl.attention_store.values()] == [1, 0, 1, 1, 0, 0]
+    assert float(ctl.attention_store["down_cross"][0].min()) == 3.0 and ctl.attention_store["down_cross"][0].shape[0] == 2
+    assert float(ctl.get_average_attention()["up_cross"][0].mean()) == 1.5
+    assert float(ctl.attention_store_all_step[0]["down_self"][0].max()) == 1.0      # per-step copies are not the running sum

@@ -134,3 +134,34 @@ def test_adapter_matches_reference_golden():
     r = U.adapter_vs_golden()
     for e, ref in zip(r["errs"], r["refs"]):
         assert e <= 2 ** -8 * ref + 2e-3, r
+
+
+# ---------------------------------------------------------------------------------------------------- attention controllers
+def test_explicit_probability_attention():
+    from tests import p2p_checks as P
+    for kw in (dict(B=3, N=256, C=1280), dict(B=4, N=64, C=1280, seed=171), dict(B=4, N=256, NK=77, C=1280, kv_div=2, seed=172),
+               dict(B=2, N=200, NK=77, C=640, seed=173), dict(B=2, N=100, C=320, seed=174)):
+        r = P.explicit_attention_check(**kw)
+        assert r["probs_err"] <= 2e-3 and r["row_sum_err"] <= 4e-3 and r["out_err"] <= 2 ** -8 * r["out_ref"] + 2e-3, (kw, r)
+
+
+def test_attention_hook_delivers_the_reference_maps():
+    """register_attention_control + forward: the 16x16 / 8x8 layers (below 32^2 queries) hand [(b f), 8, s, t] to the
+    controller in the reference's order (down 2 x (self, cross), mid, up 3 x ...), and an in-place edit reaches epsilon."""
+    from tests import p2p_checks as P
+    r = P.unet_hook_vs_oracle(Fr=2, hw=64 // 2)           # 32x32 latent: levels 32^2 (not controlled), 16^2, 8^2, 4^2
+    assert r["registered"] == 32, r
+    assert r["min_map_psnr"] >= PSNR_MIN and r["eps_psnr"] >= PSNR_MIN, r
+    e = P.unet_hook_vs_oracle(Fr=2, hw=16, edit=True)
+    assert e["min_map_psnr"] >= PSNR_MIN and e["eps_psnr"] >= PSNR_MIN, e
+
+
+@pytest.mark.parametrize("kind", ["refine", "replace"])
+def test_device_controllers_match_the_reference_classes(kind):
+    """Store -> refine / replace of the cross maps, masked self-attention replacement, blend mask and latent blend, replayed
+    against the fixture the reference's own classes produced (oracle/make_golden_p2p.py)."""
+    from tests import p2p_checks as P
+    r = P.replay_vs_reference_fixture(kind)
+    assert r["n_masks"][0] == r["n_masks"][1]
+    assert r["map_err"] <= 2e-3 and r["latent_err"] <= 4e-3, r
+    assert r["mask_mismatch"] <= 0.01 * r["mask_pixels"], r      # thresholded masks: fp16 maps vs the fp32 reference

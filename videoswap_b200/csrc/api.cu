@@ -93,6 +93,27 @@ extern "C" int vs_ln_linear(void* stream, const void* d_x, int M, int C, const v
   if (d_pe) { g.rowvec = d_cpe; g.ldrv = N; g.pix_per_batch = hw; g.rv_mod = frames; }
   return gemm_tc(st, g);
 }
+extern "C" int vs_attention_probs(void* stream, const void* d_q, int ldq, const void* d_k, int ldk, void* d_probs, int batch, int nq,
+                                  int nk, int heads, int d, long long q_bstride, long long kv_bstride, int kv_div) {
+  return attention_probs((cudaStream_t)stream, (const __half*)d_q, ldq, (const __half*)d_k, ldk, (__half*)d_probs, batch, nq, nk, heads,
+                         d, q_bstride, kv_bstride, kv_div);
+}
+extern "C" int vs_attention_apply_probs(void* stream, const void* d_probs, const void* d_v, int ldv, void* d_o, int ldo, int batch,
+                                        int nq, int nk, int heads, int d, long long kv_bstride, long long o_bstride, int kv_div) {
+  return attention_apply_probs((cudaStream_t)stream, (const __half*)d_probs, (const __half*)d_v, ldv, (__half*)d_o, ldo, batch, nq, nk,
+                               heads, d, kv_bstride, o_bstride, kv_div);
+}
+extern "C" int vs_blend_mask(void* stream, const void* const* d_maps, int n_maps, int n_prompts, int frames, int heads, int res_h,
+                             int res_w, int words, const float* d_alpha, int pool, int h, int w, float threshold, int both,
+                             float* d_mask) {
+  const int res[2] = {res_h, res_w};
+  return blend_mask((cudaStream_t)stream, (const __half* const*)d_maps, res, n_maps, n_prompts, frames, heads, words, d_alpha, pool, h, w,
+                    threshold, both, d_mask);
+}
+extern "C" int vs_latent_blend(void* stream, const void* d_x_src, void* d_x_tgt, const float* d_mask, int io_f32, int channels,
+                               int frames, int hw) {
+  return latent_blend((cudaStream_t)stream, d_x_src, d_x_tgt, d_mask, io_f32, channels, frames, hw);
+}
 extern "C" int vs_debug_read(unsigned long long* host_out, int n) {
   VS_REQUIRE(host_out && n > 0 && n <= 256 * 16, "vs_debug_read: bad arguments");
   VS_REQUIRE(attention_debug_read(host_out, n) == 0, "vs_debug_read: no debug counters recorded (set option attn_debug)");

@@ -226,6 +226,166 @@ int launch_attn(cudaStream_t st, const AttnParams& p, int batch, int heads) {
   return launch_pdl(attn_kernel<D>, grid, dim3(128), C::SMEM, st, 1, p);
 }
 
+// ================================================================================================ explicit probabilities
+// The prompt-to-prompt controllers of the reference (utils/p2p_utils/attention_register.py:96,140-150) need the softmax
+// probabilities of the small-resolution layers (queries < 32^2) as a tensor [b, h, s, t] they can store and edit between
+// softmax and P V.  Two kernels: probabilities to HBM (two sweeps over K: row max / sum, then the normalised values), and
+// O = P V from (possibly edited) probabilities.  Only the 16x16 / 8x8 levels run here (12 of the 32 attention calls, 0.3 %
+// of the step's FLOPs), so these are plain mma.sync kernels.
+template <int D>
+__global__ void __launch_bounds__(128) attn_probs_kernel(const AttnParams p, __half* __restrict__ probs, int heads) {
+  using C = ACfg<D>;
+  constexpr int DP = C::DP, LDSB = C::LDS * 2, NT = C::BKV / 8;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const uint32_t q_s = smem_u32(smem);
+  const uint32_t k_s0 = q_s + C::BQ * LDSB;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const __half* qp = p.q + b * p.q_bs + h * D;
+  const __half* kp = p.k + (b / p.kv_div) * p.kv_bs + h * D;
+  const int nkt = (p.nk + C::BKV - 1) / C::BKV;
+  load_rows<D>(q_s, qp, p.ldq, qt * C::BQ, p.nq, tid, 128);
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f, i0 = 0.f, i1 = 0.f;
+  const int r0 = qt * C::BQ + warp * 16 + (lane >> 2), r1 = r0 + 8;
+  __half* prow0 = probs + (((long long)b * heads + h) * p.nq + r0) * p.nk;
+  __half* prow1 = prow0 + 8LL * p.nk;
+  for (int pass = 0; pass < 2; ++pass) {
+    load_rows<D>(k_s0, kp, p.ldk, 0, p.nk, tid, 128);
+    cp_async_commit();
+    for (int j = 0; j < nkt; ++j) {
+      cp_async_wait<0>();
+      __syncthreads();
+      if (j + 1 < nkt) {
+        load_rows<D>(k_s0 + ((j + 1) & 1) * C::BKV * LDSB, kp, p.ldk, (j + 1) * C::BKV, p.nk, tid, 128);
+        cp_async_commit();
+      }
+      float s[NT][4];
+      warp_qk<DP, NT>(s, q_s + warp * 16 * LDSB, k_s0 + (j & 1) * C::BKV * LDSB, LDSB, lane);
+      const int kbase = j * C::BKV;
+      if (pass == 0) {
+        float mx0 = m0, mx1 = m1;
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+          const int c = kbase + n * 8 + (lane & 3) * 2;
+          if (c >= p.nk) s[n][0] = s[n][2] = -INFINITY;
+          if (c + 1 >= p.nk) s[n][1] = s[n][3] = -INFINITY;
+          mx0 = fmaxf(mx0, fmaxf(s[n][0], s[n][1]));
+          mx1 = fmaxf(mx1, fmaxf(s[n][2], s[n][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+          rs0 += exp2f((s[n][0] - mx0) * p.scale_log2) + exp2f((s[n][1] - mx0) * p.scale_log2);
+          rs1 += exp2f((s[n][2] - mx1) * p.scale_log2) + exp2f((s[n][3] - mx1) * p.scale_log2);
+        }
+        l0 = l0 * exp2f((m0 - mx0) * p.scale_log2) + rs0;
+        l1 = l1 * exp2f((m1 - mx1) * p.scale_log2) + rs1;
+        m0 = mx0; m1 = mx1;
+      } else {
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+          const int c = kbase + n * 8 + (lane & 3) * 2;
+          if (r0 < p.nq) {
+            if (c < p.nk) prow0[c] = __float2half_rn(exp2f((s[n][0] - m0) * p.scale_log2) * i0);
+            if (c + 1 < p.nk) prow0[c + 1] = __float2half_rn(exp2f((s[n][1] - m0) * p.scale_log2) * i0);
+          }
+          if (r1 < p.nq) {
+            if (c < p.nk) prow1[c] = __float2half_rn(exp2f((s[n][2] - m1) * p.scale_log2) * i1);
+            if (c + 1 < p.nk) prow1[c + 1] = __float2half_rn(exp2f((s[n][3] - m1) * p.scale_log2) * i1);
+          }
+        }
+      }
+      __syncthreads();               // every warp is done with this K buffer before the next sweep / prefetch reuses it
+    }
+    if (pass == 0) {
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+      l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+      l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+      i0 = 1.f / l0; i1 = 1.f / l1;
+    }
+  }
+}
+
+// O[b, q, h*D] = sum_k P[b, h, q, k] V[b / kv_div, k, h*D]   (P fp16 [b, h, nq, nk] row-major)
+template <int D>
+__global__ void __launch_bounds__(128) attn_pv_kernel(const AttnParams p, const __half* __restrict__ probs, int heads) {
+  using C = ACfg<D>;
+  constexpr int DP = C::DP, LDSB = C::LDS * 2, ON = DP / 8, LDP = C::BKV + 8, LDPB = LDP * 2;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const uint32_t p_s = smem_u32(smem);                       // [64 queries][64 keys] fp16, padded rows
+  const uint32_t v_s = p_s + C::BQ * LDPB;                   // [64 keys][DP]
+  __half* p_sm = reinterpret_cast<__half*>(smem);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const __half* vp = p.v + (b / p.kv_div) * p.kv_bs + h * D;
+  const __half* pb = probs + (((long long)b * heads + h) * p.nq) * p.nk;
+  const int nkt = (p.nk + C::BKV - 1) / C::BKV;
+  float o[ON][4];
+#pragma unroll
+  for (int n = 0; n < ON; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+  for (int j = 0; j < nkt; ++j) {
+    __syncthreads();                                         // previous tile consumed
+    load_rows<D>(v_s, vp, p.ldv, j * C::BKV, p.nk, tid, 128);
+    cp_async_commit();
+    for (int e = tid; e < C::BQ * C::BKV; e += 128) {        // P tile (nk may be odd: scalar loads), zero beyond the problem
+      const int r = e / C::BKV, c = e % C::BKV;
+      const int q = qt * C::BQ + r, k = j * C::BKV + c;
+      p_sm[r * LDP + c] = (q < p.nq && k < p.nk) ? pb[(long long)q * p.nk + k] : __float2half(0.f);
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+#pragma unroll
+    for (int kt = 0; kt < C::BKV / 16; ++kt) {
+      uint32_t a[4];
+      ldsm_x4(p_s + (warp * 16 + (lane & 15)) * LDPB + (kt * 16 + (lane >> 4) * 8) * 2, a[0], a[1], a[2], a[3]);
+#pragma unroll
+      for (int n = 0; n < ON; n += 2) {
+        uint32_t b0, b1, b2, b3;
+        const int key = kt * 16 + (lane & 7) + (((lane >> 3) & 1) ? 8 : 0);
+        const int ch = n * 8 + ((lane >> 4) ? 8 : 0);
+        ldsm_x4_t(v_s + key * LDSB + ch * 2, b0, b1, b2, b3);
+        mma16816(o[n], a, b0, b1);
+        mma16816(o[n + 1], a, b2, b3);
+      }
+    }
+  }
+  const int r0 = qt * C::BQ + warp * 16 + (lane >> 2), r1 = r0 + 8;
+  __half* op = p.o + b * p.o_bs + h * D;
+#pragma unroll
+  for (int n = 0; n < ON; ++n) {
+    const int c = n * 8 + (lane & 3) * 2;
+    if (c < D) {
+      if (r0 < p.nq) *reinterpret_cast<__half2*>(op + (long long)r0 * p.ldo + c) = __floats2half2_rn(o[n][0], o[n][1]);
+      if (r1 < p.nq) *reinterpret_cast<__half2*>(op + (long long)r1 * p.ldo + c) = __floats2half2_rn(o[n][2], o[n][3]);
+    }
+  }
+}
+
+template <int D>
+int launch_explicit(cudaStream_t st, const AttnParams& p, __half* probs, int batch, int heads, bool apply) {
+  using C = ACfg<D>;
+  constexpr int SMEM_P = (C::BQ + 2 * C::BKV) * C::LDS * 2;
+  constexpr int SMEM_V = C::BQ * (C::BKV + 8) * 2 + C::BKV * C::LDS * 2;
+  static bool configured = false;
+  if (!configured) {
+    VS_CHECK_CUDA(cudaFuncSetAttribute(attn_probs_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_P));
+    VS_CHECK_CUDA(cudaFuncSetAttribute(attn_pv_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_V));
+    configured = true;
+  }
+  dim3 grid((p.nq + C::BQ - 1) / C::BQ, heads, batch);
+  ProfScope prof(st, PC_ATTN, 2.0 * batch * heads * (double)p.nq * p.nk * D);
+  if (apply) attn_pv_kernel<D><<<grid, 128, SMEM_V, st>>>(p, probs, heads);
+  else attn_probs_kernel<D><<<grid, 128, SMEM_P, st>>>(p, probs, heads);
+  count_launch(1);
+  VS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // ================================================================================================ temporal
 struct TAttnParams {
   const __half* qkv; __half* o;
@@ -345,6 +505,33 @@ int attention(cudaStream_t st, const __half* q, int ldq, const __half* k, int ld
     case 80: return launch_attn<80>(st, p, batch, heads);
     case 160: return launch_attn<160>(st, p, batch, heads);
     default: VS_REQUIRE(false, "attention: unsupported head dim %d (supported: 40, 80, 160)", d);
+  }
+}
+
+// Explicit-probability path (attention controllers): probs [batch, heads, nq, nk] fp16 in HBM.
+int attention_probs(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, __half* probs, int batch, int nq, int nk,
+                    int heads, int d, long long q_bstride, long long kv_bstride, int kv_div) {
+  VS_REQUIRE(nq > 0 && nk > 0 && batch > 0 && probs, "attention_probs: empty problem");
+  VS_REQUIRE((ldq % 8 | ldk % 8) == 0 && d % 8 == 0, "attention_probs: unaligned leading dims");
+  AttnParams p{q, k, nullptr, nullptr, ldq, ldk, 0, 0, q_bstride, kv_bstride, 0, nq, nk, kv_div > 0 ? kv_div : 1,
+               1.4426950408889634f / sqrtf((float)d)};
+  switch (d) {
+    case 40: return launch_explicit<40>(st, p, probs, batch, heads, false);
+    case 80: return launch_explicit<80>(st, p, probs, batch, heads, false);
+    case 160: return launch_explicit<160>(st, p, probs, batch, heads, false);
+    default: VS_REQUIRE(false, "attention_probs: unsupported head dim %d (supported: 40, 80, 160)", d);
+  }
+}
+int attention_apply_probs(cudaStream_t st, const __half* probs, const __half* v, int ldv, __half* o, int ldo, int batch, int nq,
+                          int nk, int heads, int d, long long kv_bstride, long long o_bstride, int kv_div) {
+  VS_REQUIRE(nq > 0 && nk > 0 && batch > 0 && probs, "attention_apply_probs: empty problem");
+  VS_REQUIRE((ldv % 8 | ldo % 2) == 0 && d % 8 == 0, "attention_apply_probs: unaligned leading dims");
+  AttnParams p{nullptr, nullptr, v, o, 0, 0, ldv, ldo, 0, kv_bstride, o_bstride, nq, nk, kv_div > 0 ? kv_div : 1, 0.f};
+  switch (d) {
+    case 40: return launch_explicit<40>(st, p, const_cast<__half*>(probs), batch, heads, true);
+    case 80: return launch_explicit<80>(st, p, const_cast<__half*>(probs), batch, heads, true);
+    case 160: return launch_explicit<160>(st, p, const_cast<__half*>(probs), batch, heads, true);
+    default: VS_REQUIRE(false, "attention_apply_probs: unsupported head dim %d (supported: 40, 80, 160)", d);
   }
 }
 

@@ -75,6 +75,12 @@ int attention(cudaStream_t st, const __half* q, int ldq, const __half* k, int ld
 int attention_tc(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv,
                  __half* o, int ldo, int batch, int nq, int nk, int heads, int d, long long q_bstride,
                  long long kv_bstride, long long o_bstride, int kv_div);
+// Explicit-probability attention for the prompt-to-prompt controllers (small-resolution layers only): softmax
+// probabilities [batch, heads, nq, nk] fp16 to HBM, then O = P V from the (possibly edited) probabilities.
+int attention_probs(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, __half* probs, int batch, int nq, int nk,
+                    int heads, int d, long long q_bstride, long long kv_bstride, int kv_div);
+int attention_apply_probs(cudaStream_t st, const __half* probs, const __half* v, int ldv, __half* o, int ldo, int batch, int nq,
+                          int nk, int heads, int d, long long kv_bstride, long long o_bstride, int kv_div);
 int attention_debug_read(unsigned long long* host, int n);   // counters of the "attn_debug" kernels (148 x 8)
 // runtime options: "attn_tc" (1 = use the tcgen05 attention kernel where supported, default 1)
 int set_option(const char* name, int value);
@@ -116,6 +122,11 @@ int comm_all_reduce_sum_f32(vs_comm* c, cudaStream_t st, float* buf, size_t n); 
 int comm_all_gather(vs_comm* c, cudaStream_t st, const void* send, void* recv, size_t bytes);
 // frames <-> pixels re-sharding: src [n_outer][k][chunk] -> dst [k][n_outer][chunk] (gather = 0) or the inverse (gather = 1)
 int comm_all_to_all_rows(vs_comm* c, cudaStream_t st, const __half* src, __half* dst, int n_outer, size_t chunk, int gather);
+
+// ---- latent blend of the attention controllers (spatial_blend.py): see pointwise.cu
+int blend_mask(cudaStream_t st, const __half* const* maps, const int* map_res, int n_maps, int n_prompts, int frames, int heads,
+               int words, const float* alpha, int pool, int h, int w, float threshold, int both, float* mask);
+int latent_blend(cudaStream_t st, const void* x_src, void* x_tgt, const float* mask, int is_f32, int channels, int frames, int hw);
 
 // ---- weight packing --------------------------------------------------------------------------------------------
 int pack_conv3x3(cudaStream_t st, const __half* w, int cout, int cin, __half* out);   // [co,ci,3,3] -> [co,tap,ci]

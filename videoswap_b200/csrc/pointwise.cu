@@ -273,6 +273,94 @@ __global__ void adapter_splat_kernel(const float* __restrict__ feat, const float
   }
 }
 
+// ---------------------------------------------------------------------------------------------- latent blend (p2p)
+// SpatialBlender.get_mask + __call__ (utils/p2p_utils/spatial_blend.py:25-63,65-145) on device.  One block per frame:
+//   m[p][pix]   = mean over (layers x heads) of sum_w alpha[p][w] * map[layer][p][frame][head][pix][w]
+//   pooled      = 3x3 max pool (stride 1, -inf padding) when `pool`
+//   mask[p]     = nearest-resized(pooled) / max(nearest-resized(pooled)) > threshold
+//   both        : mask[p] |= mask[0]   (the reference's `mask[:1] + mask` on bool tensors)
+// maps: n_maps * n_prompts pointers, each [frames, heads, res_h * res_w, words] fp16.
+constexpr int kBlendMaxRes = 1024;      // the controllers only see layers with fewer than 32^2 queries
+__global__ void __launch_bounds__(256) blend_mask_kernel(const __half* const* __restrict__ maps, int n_maps, int n_prompts, int frames,
+                                                         int heads, int rh, int rw, int words, const float* __restrict__ alpha,
+                                                         int pool, int h, int w, float threshold, int both, float* __restrict__ mask) {
+  __shared__ float m[kBlendMaxRes], pooled[kBlendMaxRes], red[8];
+  const int f = blockIdx.x, res = rh * rw, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float inv = 1.f / (float)(n_maps * heads);
+  for (int pr = 0; pr < n_prompts; ++pr) {
+    // one warp per pixel: lanes stride over the words
+    for (int pix = warp; pix < res; pix += 8) {
+      float acc = 0.f;
+      for (int l = 0; l < n_maps; ++l) {
+        const __half* mp = maps[l * n_prompts + pr] + ((long long)f * heads * res + pix) * words;
+        for (int hd = 0; hd < heads; ++hd)
+          for (int wd = lane; wd < words; wd += 32) {
+            const float a = alpha[pr * words + wd];
+            if (a != 0.f) acc += a * __half2float(mp[(long long)hd * res * words + wd]);
+          }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) m[pix] = acc * inv;
+    }
+    __syncthreads();
+    for (int pix = tid; pix < res; pix += 256) {
+      float v = m[pix];
+      if (pool) {
+        const int y = pix / rw, x = pix % rw;
+        for (int dy = -1; dy <= 1; ++dy)
+          for (int dx = -1; dx <= 1; ++dx) {
+            const int yy = y + dy, xx = x + dx;
+            if (yy >= 0 && yy < rh && xx >= 0 && xx < rw) v = fmaxf(v, m[yy * rw + xx]);
+          }
+      }
+      pooled[pix] = v;
+    }
+    __syncthreads();
+    // F.interpolate(size=(h, w)), mode 'nearest': src = floor(dst * in / out)
+    float mx = -INFINITY;
+    for (int i = tid; i < h * w; i += 256) {
+      const int sy = min((int)floorf((float)(i / w) * ((float)rh / (float)h)), rh - 1);
+      const int sx = min((int)floorf((float)(i % w) * ((float)rw / (float)w)), rw - 1);
+      mx = fmaxf(mx, pooled[sy * rw + sx]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+    float* out = mask + ((long long)pr * frames + f) * h * w;
+    const float* first = mask + (long long)f * h * w;        // prompt 0 of this frame (written by this block earlier)
+    for (int i = tid; i < h * w; i += 256) {
+      const int sy = min((int)floorf((float)(i / w) * ((float)rh / (float)h)), rh - 1);
+      const int sx = min((int)floorf((float)(i % w) * ((float)rw / (float)w)), rw - 1);
+      float bit = (pooled[sy * rw + sx] / mx > threshold) ? 1.f : 0.f;      // 0/0 = NaN -> false, like the reference
+      if (both && pr > 0 && first[i] != 0.f) bit = 1.f;
+      out[i] = bit;
+    }
+    __syncthreads();
+  }
+}
+
+// x_tgt = x_src + mask * (x_tgt - x_src) per (channel, frame, pixel), in fp32 (spatial_blend.py:141-142); mask [frames, hw]
+__global__ void latent_blend_kernel(const void* __restrict__ x_src, void* __restrict__ x_tgt, const float* __restrict__ mask,
+                                    int is_f32, int channels, int frames, int hw) {
+  const long long per_c = (long long)frames * hw, total = per_c * channels;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const float mk = mask[i % per_c];
+    if (is_f32) {
+      const float s = reinterpret_cast<const float*>(x_src)[i];
+      float* t = reinterpret_cast<float*>(x_tgt) + i;
+      *t = s + mk * (*t - s);
+    } else {
+      const float s = __half2float(reinterpret_cast<const __half*>(x_src)[i]);
+      __half* t = reinterpret_cast<__half*>(x_tgt) + i;
+      *t = __float2half_rn(s + mk * (__half2float(*t) - s));
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- packing
 __global__ void pack_conv3x3_kernel(const __half* __restrict__ w, int cout, int cin, __half* __restrict__ out) {
   const long long total = (long long)cout * 9 * cin;
@@ -462,6 +550,22 @@ int adapter_splat(cudaStream_t st, const float* feat, const float* tracks, const
   VS_REQUIRE(C % 8 == 0, "adapter_splat: C %% 8 != 0");
   adapter_splat_kernel<<<capped((size_t)F * h * w * (C / 8)), TPB, 0, st>>>(feat, tracks, point_mask, F, P, C, h, w, rate,
                                                                             coord_fp16, scale, maps);
+  count_launch(1);
+  VS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int blend_mask(cudaStream_t st, const __half* const* maps, const int* map_res, int n_maps, int n_prompts, int frames, int heads,
+               int words, const float* alpha, int pool, int h, int w, float threshold, int both, float* mask) {
+  VS_REQUIRE(maps && map_res && alpha && mask && n_maps >= 1 && n_prompts >= 1 && n_prompts <= 2, "blend_mask: bad arguments");
+  VS_REQUIRE(map_res[0] * map_res[1] <= kBlendMaxRes, "blend_mask: map resolution %dx%d too large", map_res[0], map_res[1]);
+  blend_mask_kernel<<<frames, 256, 0, st>>>(maps, n_maps, n_prompts, frames, heads, map_res[0], map_res[1], words, alpha, pool, h, w,
+                                            threshold, both, mask);
+  count_launch(1);
+  VS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int latent_blend(cudaStream_t st, const void* x_src, void* x_tgt, const float* mask, int is_f32, int channels, int frames, int hw) {
+  latent_blend_kernel<<<capped((size_t)channels * frames * hw), TPB, 0, st>>>(x_src, x_tgt, mask, is_f32, channels, frames, hw);
   count_launch(1);
   VS_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -85,6 +85,11 @@ struct vs_unet {
   vs_comm* fcomm = nullptr;
   int fshard = 0, fnshards = 1;
 
+  // attention controllers: when a hook is set, every spatial attention with fewer than hook_max_q queries
+  // materialises its probabilities [(b f), heads, s, t] in `probs`, hands them to the hook, then applies them to V
+  vs_attention_hook hook = nullptr; void* hook_user = nullptr; int hook_max_q = 0;
+  __half* probs = nullptr; size_t probs_elems = 0;
+
   // debug taps
   bool taps_on = false;
   struct Tap { std::string name; void* p; int n, h, w, c; };
@@ -93,6 +98,7 @@ struct vs_unet {
   ~vs_unet() {
     for (void* p : allocs) cudaFree(p);
     if (ws) cudaFree(ws);
+    if (probs) cudaFree(probs);
     for (auto& t : taps) cudaFree(t.p);
   }
 
@@ -363,6 +369,7 @@ struct Ctx {
   int B, F, NI, H, W;      // W/H are the CURRENT resolution during the walk
   const __half* ehs; int ehs_tokens, ehs_layers;
   int gn_idx = 0;          // GroupNorm call counter: every call owns a slice of F_SUMS, all zeroed by ONE memset per forward
+  int place = 0;           // 0 down / 1 mid / 2 up: the `place_in_unet` the attention controllers are told
   int ln_parts = 0;        // > 0: F_LNP holds that many per-row partial-sum slices of the tensor the last `linear` wrote
 };
 
@@ -468,6 +475,25 @@ int geglu_ff(Ctx& c, const __half* tn, int M, int C, const __half* w1, const flo
   return linear(c, h->HH, M, ff2, t, t);
 }
 
+// Spatial attention with the controller hook: explicit probabilities for the small-resolution layers while a hook is set
+// (attention_register.py:96,140-150: xformers / flash path for >= 32^2 queries, controller path below).
+int attention_hooked(Ctx& c, const Transformer& t, int is_cross, int place, const __half* q, int ldq, const __half* k, int ldk,
+                     const __half* v, int ldv, __half* o, int ldo, int nq, int nk, int heads, int d, long long q_bs, long long kv_bs,
+                     long long o_bs, int kv_div) {
+  vs_unet* h = c.h;
+  if (h->hook == nullptr || nq >= h->hook_max_q)
+    return attention(c.st, q, ldq, k, ldk, v, ldv, o, ldo, c.NI, nq, nk, heads, d, q_bs, kv_bs, o_bs, kv_div);
+  const size_t need = (size_t)c.NI * heads * nq * nk;
+  if (need > h->probs_elems) {          // controller mode runs eagerly (never inside a captured graph)
+    if (h->probs) { VS_CHECK_CUDA(cudaStreamSynchronize(c.st)); cudaFree(h->probs); h->probs = nullptr; }
+    VS_CHECK_CUDA(cudaMalloc(&h->probs, need * sizeof(__half)));
+    h->probs_elems = need;
+  }
+  RUN(attention_probs(c.st, q, ldq, k, ldk, h->probs, c.NI, nq, nk, heads, d, q_bs, kv_bs, kv_div));
+  h->hook(h->hook_user, t.layer, is_cross, place, h->probs, c.NI, heads, nq, nk, (void*)c.st);
+  return attention_apply_probs(c.st, h->probs, v, ldv, o, ldo, c.NI, nq, nk, heads, d, kv_bs, o_bs, kv_div);
+}
+
 int transformer(Ctx& c, const Transformer& t, __half* x) {
   vs_unet* h = c.h;
   const int hw = c.H * c.W, C = t.C, M = c.NI * hw, heads = h->cfg.num_heads, d = C / heads;
@@ -482,8 +508,8 @@ int transformer(Ctx& c, const Transformer& t, __half* x) {
     RUN(layernorm(c.st, h->T, M, C, t.ln1.g, t.ln1.b, nullptr, 1, 1, h->TN));
     GemmArgs g; g.A = h->TN; g.K1 = C; g.lda1 = C; g.Bw = t.wqkv; g.M = M; g.N = 3 * C; g.out = h->QKV; g.ldc = 3 * C; RUN(gemm_tc(c.st, g));
   }
-  RUN(attention(c.st, h->QKV, 3 * C, h->QKV + C, 3 * C, h->QKV + 2 * C, 3 * C, h->ATT, C, c.NI, hw, hw, heads, d,
-                (long long)hw * 3 * C, (long long)hw * 3 * C, (long long)hw * C, 1));
+  RUN(attention_hooked(c, t, 0, c.place, h->QKV, 3 * C, h->QKV + C, 3 * C, h->QKV + 2 * C, 3 * C, h->ATT, C, hw, hw, heads, d,
+                       (long long)hw * 3 * C, (long long)hw * 3 * C, (long long)hw * C, 1));
   RUN(linear(c, h->ATT, M, t.out1, h->T, h->T, use_fold(t.f_q)));
   // cross-attention to the (ED-LoRA layer-selected) text embeddings; K/V were projected once per (batch, layer)
   if (use_fold(t.f_q)) {
@@ -504,8 +530,8 @@ int transformer(Ctx& c, const Transformer& t, __half* x) {
       g.out = h->KV + (long long)b * nk * 2 * C; g.ldc = 2 * C;
       RUN(gemm_tc(c.st, g));
     }
-    RUN(attention(c.st, h->QKV, C, h->KV, 2 * C, h->KV + C, 2 * C, h->ATT, C, c.NI, hw, nk, heads, d, (long long)hw * C,
-                  (long long)nk * 2 * C, (long long)hw * C, c.F));
+    RUN(attention_hooked(c, t, 1, c.place, h->QKV, C, h->KV, 2 * C, h->KV + C, 2 * C, h->ATT, C, hw, nk, heads, d, (long long)hw * C,
+                         (long long)nk * 2 * C, (long long)hw * C, c.F));
   }
   RUN(linear(c, h->ATT, M, t.out2, h->T, h->T, use_fold(t.f_ff)));
   // feed-forward
@@ -645,6 +671,13 @@ extern "C" int vs_unet_set_frame_shard(vs_unet* h, vs_comm* comm, int shard, int
   return 0;
 }
 
+extern "C" int vs_unet_set_attention_hook(vs_unet* h, vs_attention_hook hook, void* user, int max_queries) {
+  VS_REQUIRE(h != nullptr, "vs_unet_set_attention_hook: null handle");
+  VS_REQUIRE(hook == nullptr || h->ws_pinned == 0, "attention hooks run eagerly: release the captured CUDA graph first");
+  h->hook = hook; h->hook_user = user; h->hook_max_q = max_queries > 0 ? max_queries : 32 * 32;
+  return 0;
+}
+
 extern "C" int vs_unet_pin_workspace(vs_unet* h, int pin) {
   VS_REQUIRE(h != nullptr, "vs_unet_pin_workspace: null handle");
   h->ws_pinned += pin ? 1 : -1;
@@ -768,6 +801,7 @@ extern "C" int vs_unet_forward(vs_unet* h, void* stream, const void* d_sample, i
     }
   }
   // ---- mid
+  c.place = 1;
   {
     __half* o = (cur == h->P0) ? h->P1 : h->P0;
     RUN(resnet(c, h->mid0.res, cur, curC, nullptr, 0, o));
@@ -779,6 +813,7 @@ extern "C" int vs_unet_forward(vs_unet* h, void* stream, const void* d_sample, i
     cur = o2;
   }
   // ---- up path
+  c.place = 2;
   for (int i = 0; i < 4; ++i) {
     const Block& blk = h->up[i];
     for (int j = 0; j <= lpb; ++j) {

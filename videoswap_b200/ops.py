@@ -168,6 +168,27 @@ def attention(q, k, v, heads, kv_div=1):
     return out
 
 
+def attention_probs(q, k, heads, kv_div=1):
+    """softmax(q k^T / sqrt(d)) as a tensor [B, heads, Nq, Nk] fp16 (explicit-probability path of the attention controllers)."""
+    B, nq, Cc = q.shape
+    nk = k.shape[1]
+    probs = torch.empty((B, heads, nq, nk), dtype=torch.float16, device=q.device)
+    _lib.call("vs_attention_probs", _stream(), _p(q), q.stride(1), _p(k), k.stride(1), _p(probs), B, nq, nk, heads, Cc // heads,
+              q.stride(0), k.stride(0), kv_div)
+    return probs
+
+
+def attention_apply_probs(probs, v, heads, kv_div=1):
+    """O = P V: probs [B, heads, Nq, Nk] fp16, v [Bk, Nk, heads*d] -> [B, Nq, heads*d]."""
+    _chk16(probs)
+    B, _, nq, nk = probs.shape
+    Cc = v.shape[2]
+    out = torch.empty((B, nq, Cc), dtype=torch.float16, device=probs.device)
+    _lib.call("vs_attention_apply_probs", _stream(), _p(probs), _p(v), v.stride(1), _p(out), Cc, B, nq, nk, heads, Cc // heads,
+              v.stride(0), nq * Cc, kv_div)
+    return out
+
+
 def temporal_attention(qkv, heads):
     """qkv [B, F, HW, 3C] -> [B, F, HW, C]: attention over the F axis for every (b, pixel, head)."""
     _chk16(qkv)

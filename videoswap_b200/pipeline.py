@@ -155,8 +155,6 @@ class VideoSwapPipeline:
                  max_iters: Optional[int] = None):
         """prompt_embeds: [1,77,D] / ED-LoRA [1,16,77,D] (conditional); negative_prompt_embeds same shape (uncond).
         latents [1,4,F,h,w] (e.g. DDIM-inverted).  Mirrors pipeline_videoswap.py:552-601."""
-        if controller is not None:
-            raise NotImplementedError("attention controllers / latent blend (SURVEY 8f-2) are not on the native path yet")
         if output_type != "latent":
             raise NotImplementedError("VAE decode is outside the hot path (SURVEY 8f-4); use output_type='latent'")
         cfg = guidance_scale > 1.0
@@ -189,6 +187,8 @@ class VideoSwapPipeline:
             if adapter_state is not None and len(timesteps) * t2i_start <= i <= len(timesteps) * t2i_end:
                 res = list(adapter_state)        # the UNet pops from this list (no clone needed: it never writes to them)
             latents = self.step(latents, t, embeds, guidance_scale, res)
+            if controller is not None:           # edit the latents using the attention maps (pipeline_videoswap.py:589-593)
+                latents = controller.step_callback(latents).to(latents.dtype)
             if callback is not None and i % callback_steps == 0:
                 callback(i, t, latents)
         # the reference always rearranges 'b c f h w -> (b f) c h w' before returning (pipeline_videoswap.py:603-610)
@@ -203,8 +203,6 @@ class VideoSwapPipeline:
                return_dict: bool = True, controller=None, max_iters: Optional[int] = None):
         """DDIM inversion loop (pipeline_videoswap.py:677-703), guidance_scale = 1 (no CFG).  The UNet is evaluated at
         the inverse scheduler's timestep; which noise levels the step connects is the scheduler's `convention`."""
-        if controller is not None:
-            raise NotImplementedError("attention controllers (SURVEY 8f-2) are not on the native path yet")
         self.inverse_scheduler.set_timesteps(num_inference_steps)
         latents = latents.contiguous()
         for i, t in enumerate(self.inverse_scheduler.timesteps):
@@ -213,6 +211,8 @@ class VideoSwapPipeline:
             eps = self.unet(latents, t, encoder_hidden_states=prompt_embeds, return_dict=False)[0]
             a_cur, a_next = self.inverse_scheduler.alphas(t)
             latents = ops.cfg_ddim_step(eps, latents, 1.0, a_cur, a_next, cfg=False)
+            if controller is not None:           # store the maps / latents of this inversion step (pipeline_videoswap.py:698-702)
+                latents = controller.step_callback(latents).to(latents.dtype)
         if not return_dict:
             return latents
         return TuneAVideoInversionPipelineOutput(latents=latents.detach().clone())

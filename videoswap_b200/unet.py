@@ -431,7 +431,10 @@ class AnimateDiffUNet3DModel(nn.Module):
         self._dirty = False
 
     def _check_processors(self):
+        """Validates the processors the reference's helpers may have swapped in and returns the attention controller the
+        control processors carry (utils/p2p_utils/attention_register.py), or None."""
         idx = 0
+        controller = None
         for blocks in (self.down_blocks, [self.mid_block], self.up_blocks):
             for blk in blocks:
                 for tr in getattr(blk, "attentions", []):
@@ -440,10 +443,14 @@ class AnimateDiffUNet3DModel(nn.Module):
                     if ci is not None and ci != idx:
                         raise NotImplementedError("ED-LoRA cross_attention_idx differs from registration order")
                     for a in (tr.transformer_blocks[0].attn1, tr.transformer_blocks[0].attn2):
-                        if hasattr(a.processor, "controller"):
-                            raise NotImplementedError("attention controllers (prompt-to-prompt maps, SURVEY 8f-2) are not "
-                                                      "implemented on the native path yet")
+                        ctl = getattr(a.processor, "controller", None)
+                        if ctl is not None:
+                            if controller is not None and ctl is not controller:
+                                raise NotImplementedError("all attention layers must share ONE controller (as "
+                                                          "register_attention_control sets them, attention_register.py:176-211)")
+                            controller = ctl
                     idx += 1
+        return controller
 
     def __del__(self):
         try:
@@ -470,7 +477,7 @@ class AnimateDiffUNet3DModel(nn.Module):
         if H % 8 or W % 8:
             raise NotImplementedError("latent H and W must be multiples of 8")
         dev = sample.device
-        self._check_processors()
+        controller = self._check_processors()
         with torch.cuda.device(dev):
             self._sync_weights(dev)
             io_f32 = sample.dtype == torch.float32
@@ -505,8 +512,32 @@ class AnimateDiffUNet3DModel(nn.Module):
             out = torch.empty_like(x)
             if _taps is not None:
                 _lib.call("vs_unet_enable_taps", self._handle, 1)
-            _lib.call("vs_unet_forward", self._handle, torch.cuda.current_stream().cuda_stream, x.data_ptr(), int(io_f32),
-                      B, F, H, W, t.data_ptr(), ehs.data_ptr(), tokens, layers, res_ptrs, 0, 1.0, out.data_ptr())
+            hook_err = []
+            if controller is not None:
+                # attention controllers: the library hands every small-resolution layer's probabilities
+                # [(b f), heads, s, t] to the controller between softmax and P V, as a zero-copy view of its device buffer
+                from . import p2p
+
+                def _hook(user, layer, is_cross, place, ptr, batch, heads, nq, nk, stream):
+                    if hook_err:
+                        return
+                    try:
+                        view = p2p.tensor_view(ptr, (batch, heads, nq, nk), dev)
+                        res = controller(view, bool(is_cross), p2p._PLACES[place])
+                        if res is not None and res.data_ptr() != view.data_ptr():
+                            view.copy_(res.to(device=dev, dtype=torch.float16).reshape(view.shape))
+                    except BaseException as e:  # noqa: BLE001  (ctypes would swallow it: re-raised after the forward)
+                        hook_err.append(e)
+                cb = p2p.HOOK_TYPE(_hook)
+                _lib.call("vs_unet_set_attention_hook", self._handle, cb, None, p2p.MAX_QUERIES)
+            try:
+                _lib.call("vs_unet_forward", self._handle, torch.cuda.current_stream().cuda_stream, x.data_ptr(), int(io_f32),
+                          B, F, H, W, t.data_ptr(), ehs.data_ptr(), tokens, layers, res_ptrs, 0, 1.0, out.data_ptr())
+            finally:
+                if controller is not None:
+                    _lib.call("vs_unet_set_attention_hook", self._handle, None, None, 0)
+            if hook_err:
+                raise hook_err[0]
             if _taps is not None:
                 n = _lib.lib().vs_unet_num_taps(self._handle)
                 for i in range(n):
