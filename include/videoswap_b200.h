@@ -183,6 +183,11 @@ int vs_temporal_attention(void* stream, const void* d_qkv, void* d_o, int B, int
 int vs_conv_in(void* stream, const void* d_x, int nimg, int H, int W, int cin, const void* d_w, const float* d_bias,
                int cout, void* d_out);
 int vs_upsample2x(void* stream, const void* d_x, int nimg, int H, int W, int C, void* d_out);
+/* Upsample3D (resnet.py:21-69): nearest 2x then conv3x3, computed as four 2x2 sub-pixel convolutions on the low-resolution
+ * input (weights pre-summed per output parity; 2.25x fewer FLOPs, no materialised up-sampled tensor).  d_w: [Cout, C, 3, 3]
+ * fp16 as in the state_dict; d_wsub: scratch for the 4 panels, 16 * Cout * C halves; d_out: NHWC [nimg, 2H, 2W, Cout]. */
+int vs_upsample_conv3x3(void* stream, const void* d_x, int nimg, int H, int W, int C, const void* d_w, int Cout,
+                        const float* d_bias, void* d_wsub, void* d_out);
 int vs_conv3x3_s2(void* stream, const void* d_x, int nimg, int H, int W, int C, const void* d_w_packed, int Cout,
                   const float* d_bias, void* d_scratch, void* d_out);
 
@@ -206,6 +211,7 @@ int vs_profile_dump(const char* path);   /* CSV: category, shape (m,n,k), work p
  *   "attn_poly"    0  P chunks (of 8 per key tile) whose exp2 runs on the FMA pipe instead of MUFU.EX2 (0..3)
  *   "ln_fold"      1  LayerNorms folded into the consuming GEMM; 0 = stand-alone LayerNorm kernel
  *   "ln_fuse"      1  row statistics of folded LayerNorms written by the producing GEMM's epilogue; 0 = ln_stats pass
+ *   "subpixel"     1  nearest-2x + conv3x3 as four sub-pixel convs; 0 = materialise the up-sampled tensor, then conv3x3
  *   "pdl"          1  programmatic dependent launch between the hot kernels; 0 = plain stream order */
 int vs_set_option(const char* name, int value);
 /* Cycle counters of the instrumented attention kernel (option "attn_debug" = 1): per CTA 16 values -- softmax warp 4:

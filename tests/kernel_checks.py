@@ -128,6 +128,17 @@ def check_conv_s2(n=2, H=16, W=16, ci=320, co=320, seed=70):
     return _res(out, _conv_ref(x, w, b, stride=2))
 
 
+def check_upsample_conv(n=2, H=8, W=8, ci=640, co=640, seed=75):
+    """Upsample3D: nearest 2x + conv3x3 (resnet.py:54,67) through the sub-pixel decomposition."""
+    x = _rand((n, H, W, ci), seed).half()
+    w = _rand((co, ci, 3, 3), seed + 1, 1 / math.sqrt(9 * ci)).half()
+    b = _rand((co,), seed + 2).float()
+    out = ops.upsample_conv3x3(x, w, bias=b)
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+    ref = F.conv2d(up, w.float(), b, padding=1).permute(0, 2, 3, 1)
+    return _res(out, ref)
+
+
 def check_conv_in(n=4, H=16, W=16, seed=80):
     x = _rand((n, H, W, 4), seed).half()
     w = _rand((320, 4, 3, 3), seed + 1, 1 / 6).half()
@@ -366,6 +377,9 @@ CHECKS = {
     "conv_out": check_conv_out,
     "conv_s2": check_conv_s2,
     "conv_in": check_conv_in,
+    "upsample_conv_subpixel": check_upsample_conv,
+    "upsample_conv_subpixel_odd": lambda: check_upsample_conv(n=3, H=7, W=12, ci=320, co=320, seed=76),
+    "upsample_conv_subpixel_1280": lambda: check_upsample_conv(n=4, H=16, W=16, ci=1280, co=1280, seed=77),
     "upsample": check_upsample,
     "gn5d_silu": lambda: check_groupnorm(),
     "gn5d_concat": lambda: check_groupnorm(c1=640, c2=320),

@@ -84,6 +84,7 @@ _SIGNATURES = {
     "vs_temporal_attention": (_I, [_P, _P, _P, _I, _I, _I, _I, _I]),
     "vs_conv_in": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _I, _P]),
     "vs_upsample2x": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "vs_upsample_conv3x3": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P]),
     "vs_conv3x3_s2": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P]),
 }
 

@@ -93,6 +93,19 @@ extern "C" int vs_ln_linear(void* stream, const void* d_x, int M, int C, const v
   if (d_pe) { g.rowvec = d_cpe; g.ldrv = N; g.pix_per_batch = hw; g.rv_mod = frames; }
   return gemm_tc(st, g);
 }
+extern "C" int vs_upsample_conv3x3(void* stream, const void* d_x, int nimg, int H, int W, int C, const void* d_w, int Cout,
+                                   const float* d_bias, void* d_wsub, void* d_out) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int e = pack_conv_subpixel(st, (const __half*)d_w, Cout, C, (__half*)d_wsub)) return e;
+  for (int par = 0; par < 4; ++par) {
+    GemmArgs g;
+    g.A = (const __half*)d_x; g.K1 = C; g.lda1 = C; g.Bw = (const __half*)d_wsub + (size_t)par * Cout * 4 * C; g.taps = 4;
+    g.sub_py = par >> 1; g.sub_px = par & 1; g.nimg = nimg; g.H = H; g.W = W; g.M = nimg * H * W; g.N = Cout; g.bias = d_bias;
+    g.out = (__half*)d_out; g.ldc = Cout;
+    if (int e = gemm_tc(st, g)) return e;
+  }
+  return 0;
+}
 extern "C" int vs_attention_probs(void* stream, const void* d_q, int ldq, const void* d_k, int ldk, void* d_probs, int batch, int nq,
                                   int nk, int heads, int d, long long q_bstride, long long kv_bstride, int kv_div) {
   return attention_probs((cudaStream_t)stream, (const __half*)d_q, ldq, (const __half*)d_k, ldk, (__half*)d_probs, batch, nq, nk, heads,

@@ -51,6 +51,8 @@ struct GemmParams {
   int taps;
   int a_rank;        // 2 = plain rows, 4 = NHWC conv
   int nimg, H, W, TH, TW, TN, tiles_x, tiles_y;
+  int tap_x0, tap_y0, tap_w;   // conv taps: dy in [tap_y0, tap_y0 + taps / tap_w), dx in [tap_x0, tap_x0 + tap_w)
+  int osy, osx, ooy, oox, OH, OW;   // output pixel of input pixel (y, x): (y * osy + ooy, x * osx + oox) in an OH x OW image
   int tw_log, thw_log;   // log2(TW), log2(TH * TW): the conv tile dims are powers of two
   int m_tiles, n_tiles;
   const float* bias;
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     // =================================================================== TMA producer
     const int num_kb = p.num_kb, kb_per_tap = p.kb_per_tap, kb_src1 = p.kb_src1;
     const bool conv = p.a_rank == 4;
-    const int tap0 = p.taps == 9 ? -1 : 0;
+    const int tap_x0 = p.tap_x0, tap_x1 = p.tap_x0 + p.tap_w;
     uint32_t pr_s = 0, pr_ph = 0;              // ring stage / phase, carried across tiles
     for (int tile = t_begin; tile < total_tiles; tile += t_step) {
       const int mt = tile / p.n_tiles, n_tile = tile - mt * p.n_tiles;
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       const int n0 = n_tile * BN + (PAIR ? (int)crank * (BN / 2) : 0);   // PAIR: this CTA's half of the weight tile
       const int m0 = m_tile * BM;
       int kcoord = 0;                          // K coordinate into the weight panel (kb * 64)
-      int dy = tap0, dx = tap0;                // tap offsets, advanced like an odometer
+      int dy = p.tap_y0, dx = tap_x0;          // tap offsets, advanced like an odometer
       int r = 0;                               // k-block inside the tap
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(empty_bar(pr_s), pr_ph ^ 1);
@@ -207,7 +209,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         kcoord += BK;
         if (++r == kb_per_tap) {               // next tap
           r = 0;
-          if (++dx == 2) { dx = -1; ++dy; }
+          if (++dx == tap_x1) { dx = tap_x0; ++dy; }
         }
         if (++pr_s == (uint32_t)nst) { pr_s = 0; pr_ph ^= 1; }
       }
@@ -275,7 +277,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         const int i0 = (m_tile / (p.tiles_x * p.tiles_y)) * p.TN;
         const int ti = row >> p.thw_log, rem = row & ((1 << p.thw_log) - 1);
         const int y = y0 + (rem >> p.tw_log), x = x0 + (rem & (p.TW - 1)), img = i0 + ti;
-        pix = ((m_tile < p.m_tiles) && (img < p.nimg) && (y < p.H) && (x < p.W)) ? (img * p.H + y) * p.W + x : -1;
+        pix = ((m_tile < p.m_tiles) && (img < p.nimg) && (y < p.H) && (x < p.W))
+                  ? (img * p.OH + y * p.osy + p.ooy) * p.OW + x * p.osx + p.oox : -1;
       } else {
         pix = m_tile * BM + row;
         if (pix >= p.M) pix = -1;
@@ -611,11 +614,11 @@ int gemm_n_tiles(const GemmArgs& a) {
 
 int gemm_tc(cudaStream_t st, const GemmArgs& a) {
   VS_REQUIRE(a.A && a.Bw && a.out, "gemm_tc: null pointer");
-  VS_REQUIRE(a.taps == 1 || a.taps == 9, "gemm_tc: taps must be 1 or 9");
+  VS_REQUIRE(a.taps == 1 || a.taps == 9 || a.taps == 4, "gemm_tc: taps must be 1, 9 (3x3) or 4 (2x2 sub-pixel)");
   VS_REQUIRE(a.K1 % 8 == 0 && a.K2 % 8 == 0, "gemm_tc: K must be a multiple of 8 (TMA 16-byte strides)");
   VS_REQUIRE((long long)a.M * (a.ldc > a.ldr ? a.ldc : a.ldr) < (1LL << 40) && a.M < (1 << 30), "gemm_tc: M too large");
   const bool two = a.A2 != nullptr && a.K2 > 0;
-  if (two || a.taps == 9) VS_REQUIRE(a.K1 % BK == 0 && a.K2 % BK == 0, "gemm_tc: concat/conv sources need C %% 64 == 0 (got %d,%d)", a.K1, a.K2);
+  if (two || a.taps != 1) VS_REQUIRE(a.K1 % BK == 0 && a.K2 % BK == 0, "gemm_tc: concat/conv sources need C %% 64 == 0 (got %d,%d)", a.K1, a.K2);
   GemmParams p;
   memset(&p, 0, sizeof(p));
   const int Ktap = a.K1 + (two ? a.K2 : 0);
@@ -647,9 +650,17 @@ int gemm_tc(cudaStream_t st, const GemmArgs& a) {
   p.ldc = a.ldc;
   p.stages = get_option("gemm_stages");
 
-  if (a.taps == 9) {
+  if (a.taps != 1) {
     VS_REQUIRE(a.nimg > 0 && a.H > 0 && a.W > 0 && a.M == a.nimg * a.H * a.W, "gemm_tc: bad conv geometry");
     p.a_rank = 4;
+    // 3x3: taps (-1..1)^2.  2x2 (one output parity (py, px) of nearest-2x + 3x3, see pack_conv_subpixel): taps
+    // {py - 1, py} x {px - 1, px}, output pixel (2 y + py, 2 x + px) of the 2H x 2W image.
+    if (a.taps == 9) { p.tap_x0 = p.tap_y0 = -1; p.tap_w = 3; p.osy = p.osx = 1; p.ooy = p.oox = 0; p.OH = a.H; p.OW = a.W; }
+    else {
+      VS_REQUIRE((a.sub_py | 1) == 1 && (a.sub_px | 1) == 1, "gemm_tc: sub-pixel parity must be 0 or 1");
+      p.tap_y0 = a.sub_py - 1; p.tap_x0 = a.sub_px - 1; p.tap_w = 2;
+      p.osy = p.osx = 2; p.ooy = a.sub_py; p.oox = a.sub_px; p.OH = 2 * a.H; p.OW = 2 * a.W;
+    }
     const ConvTile t = pick_conv_tile(a.nimg, a.H, a.W);
     p.nimg = a.nimg; p.H = a.H; p.W = a.W; p.TW = t.tw; p.TH = t.th; p.TN = t.tn;
     p.tw_log = ilog2(t.tw);
@@ -715,7 +726,7 @@ int gemm_tc(cudaStream_t st, const GemmArgs& a) {
   if (!p.staged) VS_REQUIRE(a.mode == EPI_LINEAR, "gemm_tc: GEGLU output needs 32-column aligned, 16-byte strided rows");
   if (a.ln_stats || a.ln_parts) VS_REQUIRE(p.staged && (reinterpret_cast<uintptr_t>(a.ln_u) & 15) == 0, "gemm_tc: folded LayerNorm needs the staged epilogue");
   if (a.ln_sums_out) VS_REQUIRE(p.staged, "gemm_tc: row statistics output needs the staged epilogue (N %% 32 == 0, aligned rows)");
-  ProfScope prof(st, a.taps == 9 ? PC_CONV : PC_GEMM, 2.0 * a.M * (double)a.N * Ktot, 1, a.M, a.N, Ktot);
+  ProfScope prof(st, a.taps != 1 ? PC_CONV : PC_GEMM, 2.0 * a.M * (double)a.N * Ktot, 1, a.M, a.N, Ktot);
   if (a.mode == EPI_GEGLU) {
     if (p.ln_stats || p.ln_parts) return pair ? launch<256, EPI_F_GEGLU | EPI_F_LN, true>(st, p) : launch<256, EPI_F_GEGLU | EPI_F_LN, false>(st, p);
     return pair ? launch<256, EPI_F_GEGLU, true>(st, p) : launch<256, EPI_F_GEGLU, false>(st, p);

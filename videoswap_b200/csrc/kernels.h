@@ -20,7 +20,8 @@ struct GemmArgs {
   const __half* A2 = nullptr; int K2 = 0;  int lda2 = 0;
   const __half* Bw = nullptr;                 // [N, taps*(K1+K2)] fp16, K contiguous
   int M = 0, N = 0;
-  int taps = 1;                               // 1 or 9
+  int taps = 1;                               // 1, 9 (3x3, pad 1) or 4 (2x2 sub-pixel phase of nearest-2x + 3x3)
+  int sub_py = 0, sub_px = 0;                 // taps == 4: output parity; writes pixel (2y+py, 2x+px) of the 2H x 2W output
   int nimg = 0, H = 0, W = 0;                 // conv geometry (taps == 9)
   const float* bias = nullptr;                // [N] fp32
   const float* rowvec = nullptr;              // [M / pix_per_batch, ldrv] fp32 (time-embedding add)
@@ -130,6 +131,12 @@ int latent_blend(cudaStream_t st, const void* x_src, void* x_tgt, const float* m
 
 // ---- weight packing --------------------------------------------------------------------------------------------
 int pack_conv3x3(cudaStream_t st, const __half* w, int cout, int cin, __half* out);   // [co,ci,3,3] -> [co,tap,ci]
+// nearest-2x upsampling followed by a 3x3 conv == four 2x2 convs on the LOW-resolution input, one per output parity
+// (py, px): rows 2y+py-1..2y+py+1 of the up-sampled image come from source rows {y-1, y, y} (py = 0) or {y, y, y+1}
+// (py = 1), so the 3 row taps collapse to 2 with weights {w[-1], w[0]+w[1]} / {w[-1]+w[0], w[1]}; same along x.
+// out: [4 parities (py*2+px)][co][2x2 taps][ci] fp16 (weights summed in fp32, rounded once).  2.25x fewer FLOPs and no
+// materialised up-sampled tensor.
+int pack_conv_subpixel(cudaStream_t st, const __half* w, int cout, int cin, __half* out);
 int pack_geglu(cudaStream_t st, const __half* w, const __half* b, int hidden, int K, int granule, __half* wout,
                float* bout);   // rows interleaved value/gate in `granule` blocks; w or b may be null (pack one only)
 int f16_to_f32(cudaStream_t st, const __half* x, size_t n, float* out);

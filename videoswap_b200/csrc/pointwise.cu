@@ -370,6 +370,21 @@ __global__ void pack_conv3x3_kernel(const __half* __restrict__ w, int cout, int 
     out[i] = w[(co * cin + ci) * 9 + tap];
   }
 }
+__global__ void pack_conv_subpixel_kernel(const __half* __restrict__ w, int cout, int cin, __half* __restrict__ out) {
+  const long long per = (long long)cout * 4 * cin, total = 4 * per;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ci = i % cin, tap = (i / cin) % 4;
+    const long long co = (i / (4LL * cin)) % cout;
+    const int par = i / per, py = par >> 1, px = par & 1, ty = tap >> 1, tx = tap & 1;
+    // source-row tap ty of parity py gathers these 3x3 rows: py=0: ty=0 -> {0}, ty=1 -> {1,2};  py=1: ty=0 -> {0,1}, ty=1 -> {2}
+    const int r0 = (py == 0) ? (ty == 0 ? 0 : 1) : (ty == 0 ? 0 : 2), r1 = (py == 0) ? (ty == 0 ? 0 : 2) : (ty == 0 ? 1 : 2);
+    const int c0 = (px == 0) ? (tx == 0 ? 0 : 1) : (tx == 0 ? 0 : 2), c1 = (px == 0) ? (tx == 0 ? 0 : 2) : (tx == 0 ? 1 : 2);
+    float acc = 0.f;
+    for (int r = r0; r <= r1; ++r)
+      for (int c = c0; c <= c1; ++c) acc += __half2float(w[(co * cin + ci) * 9 + r * 3 + c]);
+    out[i] = __float2half_rn(acc);
+  }
+}
 __global__ void pack_geglu_kernel(const __half* __restrict__ w, const __half* __restrict__ b, int hidden, int K,
                                   int gran, __half* __restrict__ wout, float* __restrict__ bout) {
   const long long total = (long long)2 * hidden * K;
@@ -572,6 +587,12 @@ int latent_blend(cudaStream_t st, const void* x_src, void* x_tgt, const float* m
 }
 int pack_conv3x3(cudaStream_t st, const __half* w, int cout, int cin, __half* out) {
   pack_conv3x3_kernel<<<capped((size_t)cout * 9 * cin), TPB, 0, st>>>(w, cout, cin, out);
+  count_launch(1);
+  VS_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+int pack_conv_subpixel(cudaStream_t st, const __half* w, int cout, int cin, __half* out) {
+  pack_conv_subpixel_kernel<<<capped((size_t)cout * 16 * cin), TPB, 0, st>>>(w, cout, cin, out);
   count_launch(1);
   VS_CHECK_CUDA(cudaGetLastError());
   return 0;

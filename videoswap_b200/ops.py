@@ -95,6 +95,18 @@ def conv3x3_s2(x, w_packed, bias=None):
     return out
 
 
+def upsample_conv3x3(x, w, bias=None):
+    """nearest-2x + conv3x3 (pad 1) as four sub-pixel convs: x [N, H, W, C], w [Co, C, 3, 3] (unpacked) -> [N, 2H, 2W, Co]."""
+    _chk16(x, w)
+    _chk32(bias)
+    n, H, W, Ci = x.shape
+    co = w.shape[0]
+    wsub = torch.empty((16 * co * Ci,), dtype=torch.float16, device=x.device)
+    out = torch.empty((n, 2 * H, 2 * W, co), dtype=torch.float16, device=x.device)
+    _lib.call("vs_upsample_conv3x3", _stream(), _p(x), n, H, W, Ci, _p(w), co, _p(bias), _p(wsub), _p(out))
+    return out
+
+
 def groupnorm(x1, gamma, beta, groups, eps, imgs_per_set=1, silu=False, x2=None):
     """x1 [N, H, W, C1] (+ x2) -> normalised [N, H, W, C1+C2]; statistics over imgs_per_set images x (C/groups)."""
     _chk16(x1, x2)
