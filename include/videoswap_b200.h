@@ -204,9 +204,10 @@ int vs_profile_dump(const char* path);   /* CSV: category, shape (m,n,k), work p
  *   "attn_handoff" 1  softmax warpgroups hand the MUFU pipe over after 7 of 8 key chunks; 0 = after the last one
  *   "gemm_pair"    1  CTA pairs (cta_group::2, 256-row tiles) for K >= 768; 0 = never; 2 = whenever >= 2 row tiles
  *   "gemm_stages"  0  limit of the shared-memory ring depth of the GEMM (0 = as many as fit)
- *   "attn_persist" 1  persistent tcgen05 attention (one CTA per SM walks the work items) where it measured faster (key
- *                     sequences <= 512, head dim 80); 2 = always; 0 = one CTA per work item everywhere
+ *   "attn_persist" 1  persistent tcgen05 attention (one CTA per SM walks the work items, Q K^T and P V issued by two
+ *                     warps); 0 = the round-1 kernel (one CTA per work item, one issuer warp)
  *   "attn_epiwg"   1  persistent d = 40 kernel: dedicated epilogue warpgroup, O accumulators double-buffered in TMEM
+ *   "attn_pingpong" 1 persistent kernel: the two softmax warpgroups take turns on the MUFU pipe; 0 = free-running
  *   "attn_debug"   0  1 = the persistent d = 40 kernel records cycle counters (vs_debug_read)
  *   "attn_poly"    0  P chunks (of 8 per key tile) whose exp2 runs on the FMA pipe instead of MUFU.EX2 (0..3)
  *   "ln_fold"      1  LayerNorms folded into the consuming GEMM; 0 = stand-alone LayerNorm kernel
@@ -216,8 +217,8 @@ int vs_profile_dump(const char* path);   /* CSV: category, shape (m,n,k), work p
 int vs_set_option(const char* name, int value);
 /* Cycle counters of the instrumented attention kernel (option "attn_debug" = 1): per CTA 16 values -- softmax warp 4:
  * total, wait for S (tiles > 0), wait for the MUFU turn, wait for the P buffer / rescale, exponential phase, epilogue, wait
- * for S (first tile of an item), key tiles; MMA warp: total, wait Q, wait K/V, wait P(tile 0), wait P(tile 1), wait V ones
- * column, wait O buffer, items.  Synchronises the device.  Diagnostic only. */
+ * for S (first tile of an item), key tiles; issuer warps: P V total, Q K^T wait Q, Q K^T wait K/V, P V wait P(tile 0), P V wait P(tile 1), wait V
+ * ones column, wait O buffer, Q K^T wait for a free S buffer.  Synchronises the device.  Diagnostic only. */
 int vs_debug_read(unsigned long long* host_out, int n);
 
 #ifdef __cplusplus

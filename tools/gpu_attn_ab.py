@@ -70,7 +70,7 @@ for epiwg in (0, 1):
     _lib.call("vs_debug_read", buf, 148 * 16)
     a = torch.tensor(list(buf), dtype=torch.float64).reshape(148, 16)
     names = ["total", "wait_S", "wait_turn", "wait_Pbuf", "exp_phase", "epilogue", "wait_S_first_tile", "tiles",
-             "mma_total", "mma_wait_Q", "mma_wait_KV", "mma_wait_P0", "mma_wait_P1", "mma_wait_Vones", "mma_wait_Obuf", "items"]
+             "mma_total", "mma_wait_Q", "mma_wait_KV", "mma_wait_P0", "mma_wait_P1", "mma_wait_Vones", "mma_wait_Obuf", "qk_wait_Sbuf"]
     mean, mx, mn = a.mean(0), a.max(0).values, a.min(0).values
     out[f"debug_epiwg{epiwg}"] = {nm: {"mean": float(mean[i]), "min": float(mn[i]), "max": float(mx[i])} for i, nm in enumerate(names)}
     print(f"debug epiwg={epiwg}: " + "  ".join(f"{nm}={mean[i]:.0f}[{mn[i]:.0f}..{mx[i]:.0f}]" for i, nm in enumerate(names)), flush=True)

@@ -390,7 +390,7 @@ __device__ __forceinline__ float exp2_fma(float x) {
 // EPIWG (d <= 64, where TMEM has room for a second pair of O accumulators): a fourth warpgroup (warps 12-15) writes the
 // finished O tiles out, so the two softmax warpgroups run one uninterrupted stream of key tiles -- with the epilogue
 // inside the softmax warpgroups the strict MUFU ping-pong stalls both of them at every item boundary.
-template <int D, int HO, int NPOLY, bool EPIWG, bool DBG>
+template <int D, int HO, int NPOLY, bool EPIWG, bool DBG, bool PP = true>
 __global__ void __launch_bounds__(EPIWG ? ATT_THREADS + 128 : ATT_THREADS, 1) attn_tcp_kernel(const __grid_constant__ TAttnArgs p) {
   using C = TCfg<D>;
   static_assert(!EPIWG || C::O_COL + 4 * C::O_STRIDE <= 512, "no TMEM room for double-buffered O");
@@ -474,44 +474,18 @@ __global__ void __launch_bounds__(EPIWG ? ATT_THREADS + 128 : ATT_THREADS, 1) at
       }
     }
   } else if (warp == 1) {
-    // ================================================================ MMA issuer
-    constexpr uint32_t idesc_qk = umma_idesc_f16(TQ, BKV);
+    // ================================================================ P V issuer
+    // The tcgen05.mma issue path of ONE warp (descriptor set-up in uniform registers, ~7 MMAs + 3 commits + 3-4 mbarrier
+    // polls per key tile and query tile) measured ~700 clk per round with the softmax warps waiting ~530 clk per tile for
+    // S (profiles/r02_attn_debug_counters.json): the single issuer, not the MUFU pipe, bounded the steady state.  The two
+    // GEMMs are therefore issued by two warps: this one issues O_i += P_i V, warp 2 issues S_i = Q_i K^T.
     constexpr uint32_t idesc_pv = umma_idesc_f16(TQ, C::DPO) | (1u << 16);   // B operand MN-major
     const int my_items = (p.n_items - item0 + istep - 1) / istep;
     const uint32_t total = (uint32_t)my_items * (uint32_t)nkt;               // key tiles this CTA walks
-    // Q K^T cursor: runs two key tiles ahead of the P V cursor, across item boundaries
-    uint32_t gq = 0, nq_item = 0; int jq = 0;
-    long long m_q = 0, m_kv = 0, m_p0 = 0, m_p1 = 0, m_v = 0, m_oe = 0, m_t0 = 0;
+    long long m_p0 = 0, m_p1 = 0, m_v = 0, m_oe = 0, m_t0 = 0;
     const bool mdbg = DBG && lane == 0 && p.dbg != nullptr;
 #define VS_MT() (mdbg ? clock64() : 0LL)
     if (DBG) m_t0 = VS_MT();
-    auto issue_qk = [&](int i) {
-      const uint32_t s = gq % C::ST, qb = nq_item % QB;
-      if (i == 0) {
-        long long ta = 0;
-        if (DBG) ta = VS_MT();
-        if (jq == 0) mbar_wait(q_full(qb), (nq_item / QB) & 1);
-        if (DBG) { const long long tb = VS_MT(); m_q += tb - ta; ta = tb; }
-        mbar_wait(kv_full(s), (gq / C::ST) & 1);
-        if (DBG) m_kv += VS_MT() - ta;
-        tc_fence_after();
-      }
-      if (elect_one()) {
-        const uint32_t qa = q_s + qb * C::Q_BYTES + i * C::NCB * TQ * 128;
-        const uint32_t ka = kv_s + s * C::KV_STAGE_BYTES;
-#pragma unroll
-        for (int k = 0; k < C::DPK / 16; ++k) {
-          const int cb = (k * 16) / 64, off = ((k * 16) % 64) * 2;
-          tc_mma_f16(tmem + C::S_COL + (2 * i + (gq & 1)) * BKV, umma_desc_sw128_kmajor(qa + cb * TQ * 128 + off),
-                     umma_desc_sw128_kmajor(ka + cb * C::KV_BLOCK_BYTES + off), idesc_qk, k != 0 ? 1u : 0u);
-        }
-        tc_commit(s_full(i, gq & 1));
-        if (i == 1 && jq == nkt - 1) tc_commit(q_empty(qb));     // last Q K^T of this item: its Q buffer may be refilled
-      }
-      __syncwarp();
-      if (i == 1) { ++gq; if (++jq == nkt) { jq = 0; ++nq_item; } }
-    };
-    for (int a = 0; a < 2 && gq < total; ++a) { issue_qk(0); issue_qk(1); }
     int j = 0;
     uint32_t n = 0;                                  // item of the P V cursor
     for (uint32_t g = 0; g < total; ++g) {
@@ -535,17 +509,63 @@ __global__ void __launch_bounds__(EPIWG ? ATT_THREADS + 128 : ATT_THREADS, 1) at
             tc_mma_f16(tmem + o_col(i, n), umma_desc_sw128_kmajor(pa + k * 32),
                        umma_desc_sw128_mnmajor(va + k * 16 * 128, C::KV_BLOCK_BYTES), idesc_pv, (j > 0 || k != 0) ? 1u : 0u);
           tc_commit(p_empty(i, g & 1));              // this P buffer consumed, O_i quiescent once this retires
-          if (i == 1) tc_commit(kv_empty(s));        // K_j / V_j fully consumed once these MMAs retire
+          if (i == 1) tc_commit(kv_empty(s));        // V_j consumed (K_j was consumed by Q K^T of this tile, long retired)
           if (j == nkt - 1) tc_commit(o_full(i, EPIWG ? (n & 1) : 0));   // O_i of this item complete
         }
         __syncwarp();
-        if (gq < total) issue_qk(i);                 // S_{i, g&1} was drained by the softmax before it signalled p_full
       }
       if (++j == nkt) { j = 0; ++n; }
     }
     if (mdbg) {
       unsigned long long* d = p.dbg + 16 * blockIdx.x + 8;
-      d[0] = (unsigned long long)(clock64() - m_t0); d[1] = m_q; d[2] = m_kv; d[3] = m_p0; d[4] = m_p1; d[5] = m_v; d[6] = m_oe; d[7] = n;
+      d[0] = (unsigned long long)(clock64() - m_t0); d[3] = m_p0; d[4] = m_p1; d[5] = m_v; d[6] = m_oe;
+    }
+#undef VS_MT
+  } else if (warp == 2) {
+    // ================================================================ Q K^T issuer (after the TMEM allocation above)
+    // Runs two key tiles ahead of the softmax, across item boundaries: S_{i, g&1} of tile g may be overwritten once the
+    // softmax of tile g-2 has drained it, which it signals with p_full(i, (g-2)&1) (also awaited by the P V issuer).
+    constexpr uint32_t idesc_qk = umma_idesc_f16(TQ, BKV);
+    const int my_items = (p.n_items - item0 + istep - 1) / istep;
+    const uint32_t total = (uint32_t)my_items * (uint32_t)nkt;
+    long long m_q = 0, m_kv = 0, m_pf = 0;
+    const bool mdbg = DBG && lane == 0 && p.dbg != nullptr;
+#define VS_MT() (mdbg ? clock64() : 0LL)
+    uint32_t nq_item = 0; int jq = 0;
+    for (uint32_t gq = 0; gq < total; ++gq) {
+      const uint32_t s = gq % C::ST, qb = nq_item % QB;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        long long ta = 0;
+        if (DBG) ta = VS_MT();
+        if (gq >= 2) mbar_wait(p_full(i, gq & 1), ((gq - 2) >> 1) & 1);
+        if (DBG) { const long long tb = VS_MT(); m_pf += tb - ta; ta = tb; }
+        if (i == 0) {
+          if (jq == 0) mbar_wait(q_full(qb), (nq_item / QB) & 1);
+          if (DBG) { const long long tb = VS_MT(); m_q += tb - ta; ta = tb; }
+          mbar_wait(kv_full(s), (gq / C::ST) & 1);
+          if (DBG) m_kv += VS_MT() - ta;
+        }
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t qa = q_s + qb * C::Q_BYTES + i * C::NCB * TQ * 128;
+          const uint32_t ka = kv_s + s * C::KV_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < C::DPK / 16; ++k) {
+            const int cb = (k * 16) / 64, off = ((k * 16) % 64) * 2;
+            tc_mma_f16(tmem + C::S_COL + (2 * i + (gq & 1)) * BKV, umma_desc_sw128_kmajor(qa + cb * TQ * 128 + off),
+                       umma_desc_sw128_kmajor(ka + cb * C::KV_BLOCK_BYTES + off), idesc_qk, k != 0 ? 1u : 0u);
+          }
+          tc_commit(s_full(i, gq & 1));
+          if (i == 1 && jq == nkt - 1) tc_commit(q_empty(qb));     // last Q K^T of this item: its Q buffer may be refilled
+        }
+        __syncwarp();
+      }
+      if (++jq == nkt) { jq = 0; ++nq_item; }
+    }
+    if (mdbg) {
+      unsigned long long* d = p.dbg + 16 * blockIdx.x + 8;
+      d[1] = m_q; d[2] = m_kv; d[7] = m_pf;          // slots 0, 3..6 belong to the P V issuer; 7 = wait for a free S buffer
     }
 #undef VS_MT
   } else if (warp == 3) {
@@ -580,7 +600,7 @@ __global__ void __launch_bounds__(EPIWG ? ATT_THREADS + 128 : ATT_THREADS, 1) at
     const bool dbg = DBG && warp == 4 && lane == 0 && p.dbg != nullptr;
 #define VS_TICK() (dbg ? clock64() : 0LL)
     if (DBG) t0 = VS_TICK();
-    if (i == 1) named_bar_arrive(9 + 0, 256);    // warpgroup 0 goes first on the MUFU pipe
+    if (PP && i == 1) named_bar_arrive(9 + 0, 256);    // warpgroup 0 goes first on the MUFU pipe
     uint32_t g = 0, n = 0;
     for (int item = item0; item < p.n_items; item += istep, ++n) {
       const int qblk = item % p.n_qblk, bh = item / p.n_qblk, head = bh % p.heads, b = bh / p.heads;
@@ -635,7 +655,7 @@ __global__ void __launch_bounds__(EPIWG ? ATT_THREADS + 128 : ATT_THREADS, 1) at
         if (g >= 2) mbar_wait(p_empty(i, g & 1), ((g - 2) >> 1) & 1);   // this P buffer was consumed two key tiles ago
         if (DBG) { const long long t = VS_TICK(); t_wp += t - tt; tt = t; }
         const uint32_t p_row = p_row0 + (g & 1) * C::P_TILE_BYTES;
-        named_bar_sync(9 + i, 256);                                       // my turn on the MUFU pipe
+        if (PP) named_bar_sync(9 + i, 256);                               // my turn on the MUFU pipe
         if (DBG) { const long long t = VS_TICK(); t_wt += t - tt; tt = t; }
 #pragma unroll
         for (int c8 = 0; c8 < BKV / 8; ++c8) {       // one 16-byte chunk (8 keys) at a time
@@ -653,7 +673,7 @@ __global__ void __launch_bounds__(EPIWG ? ATT_THREADS + 128 : ATT_THREADS, 1) at
           const uint32_t dst = p_row + ((c8 ^ (row & 7)) << 4);
           asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
                        : "memory");
-          if (c8 == HO) named_bar_arrive(9 + (i ^ 1), 256);   // hand the MUFU pipe over a little early (wake-up latency)
+          if (PP && c8 == HO) named_bar_arrive(9 + (i ^ 1), 256);   // hand the MUFU pipe over a little early (wake-up latency)
         }
         fence_proxy_async();                     // generic-proxy smem writes -> visible to the tensor-core (async) proxy
         tc_fence_before();
@@ -696,7 +716,7 @@ __global__ void __launch_bounds__(EPIWG ? ATT_THREADS + 128 : ATT_THREADS, 1) at
       tc_fence_before();                         // the O reads above are ordered before this warpgroup's next p_full arrive
       if (DBG) t_ep += VS_TICK() - tt;
     }
-    if (i == 0) named_bar_sync(9 + 0, 256);      // absorb the other warpgroup's last hand-over
+    if (PP && i == 0) named_bar_sync(9 + 0, 256);      // absorb the other warpgroup's last hand-over
     if (dbg) {
       unsigned long long* d = p.dbg + 16 * blockIdx.x;
       d[0] = (unsigned long long)(clock64() - t0); d[1] = t_ws; d[2] = t_wt; d[3] = t_wp; d[4] = t_ex; d[5] = t_ep; d[6] = t_ws0; d[7] = g;
@@ -758,7 +778,7 @@ __global__ void __launch_bounds__(EPIWG ? ATT_THREADS + 128 : ATT_THREADS, 1) at
 
 unsigned long long* g_attn_dbg = nullptr;     // 148 x 8 counters (DBG kernels), see vs_debug_read
 
-template <int D, int HO, int NPOLY, bool PERSIST, bool EPIWG = false, bool DBG = false>
+template <int D, int HO, int NPOLY, bool PERSIST, bool EPIWG = false, bool DBG = false, bool PP = true>
 int launch(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv, __half* o, int ldo,
            int batch, int nq, int nk, int heads, long long q_bs, long long kv_bs, long long o_bs, int kv_div) {
   using C = TCfg<D>;
@@ -766,7 +786,7 @@ int launch(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, 
   static_assert(SMEM_P <= 227 * 1024, "shared memory budget (persistent)");
   static bool configured = false;
   if (!configured) {
-    if constexpr (PERSIST) VS_CHECK_CUDA(cudaFuncSetAttribute(attn_tcp_kernel<D, HO, NPOLY, EPIWG, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_P));
+    if constexpr (PERSIST) VS_CHECK_CUDA(cudaFuncSetAttribute(attn_tcp_kernel<D, HO, NPOLY, EPIWG, DBG, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_P));
     else VS_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D, HO>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     configured = true;
   }
@@ -800,7 +820,7 @@ int launch(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, 
       VS_CHECK_CUDA(cudaMemsetAsync(g_attn_dbg, 0, 256 * 16 * sizeof(unsigned long long), st));
       a.dbg = g_attn_dbg;
     }
-    return launch_pdl(attn_tcp_kernel<D, HO, NPOLY, EPIWG, DBG>, dim3(ctas), dim3(EPIWG ? ATT_THREADS + 128 : ATT_THREADS), SMEM_P, st, 1, a);
+    return launch_pdl(attn_tcp_kernel<D, HO, NPOLY, EPIWG, DBG, PP>, dim3(ctas), dim3(EPIWG ? ATT_THREADS + 128 : ATT_THREADS), SMEM_P, st, 1, a);
   }
   else {
     dim3 grid(a.n_qblk, heads, batch);
@@ -827,17 +847,20 @@ int attention_tc(cudaStream_t st, const __half* q, int ldq, const __half* k, int
   const bool early = get_option("attn_handoff") != 0;
   // "attn_persist" (default 1): persistent CTAs; 0 = one CTA per (batch, head, 256 queries) as in round 1 (A/B switch).
   // "attn_poly": how many of the 8 P chunks per key tile take exp2 from the FMA pipe (0, 1, 2, 3; persistent kernel only).
-  // 1 (default) = where it measured faster: short key sequences (cross-attention: the per-CTA prologue dominated) and
-  // d = 80; the long d = 40 self-attention keeps one CTA per item (1541 vs 1731 us at N = 4096, profiles/r02_attn_ab_*);
-  // 2 = always, 0 = never.
-  const int pers = get_option("attn_persist");
-  const int nkt_host = (nk + BKV - 1) / BKV;
-  if (pers == 2 || (pers == 1 && (d == 80 || nkt_host <= 8)) || (pers != 0 && get_option("attn_debug") != 0)) {
+  // "attn_persist" (default 1): the persistent kernel with two issuer warps.  With the single issuer of round 1 it only won
+  // on short key sequences (profiles/r02_attn_ab_persistent_v1.json); with Q K^T and P V issued by two warps it wins
+  // everywhere (L0 self 1461 vs 1540 us, L1 self 138 vs 191 us, L0 cross 99 vs 183 us; profiles/r02_attn_ab_split_issuer.json).
+  // 0 = round-1 kernel (one CTA per work item, one issuer warp).
+  if (get_option("attn_persist") != 0) {
     const int np = get_option("attn_poly");
     // "attn_epiwg" (default 1): a dedicated epilogue warpgroup for d = 40 (see attn_tcp_kernel); "attn_debug": cycle counters
     const bool epiwg = get_option("attn_epiwg") != 0;
     if (d == 40 && get_option("attn_debug") != 0)
       return epiwg ? launch<40, 6, 0, true, true, true>(VS_ATT_ARGS) : launch<40, 6, 0, true, false, true>(VS_ATT_ARGS);
+    if (get_option("attn_pingpong") == 0) {        // A/B: softmax warpgroups free-running on the MUFU pipe
+      if (d == 40) return np > 0 ? launch<40, 6, 2, true, true, false, false>(VS_ATT_ARGS) : launch<40, 6, 0, true, true, false, false>(VS_ATT_ARGS);
+      if (d == 80) return launch<80, 6, 0, true, false, false, false>(VS_ATT_ARGS);
+    }
     if (d == 40 && epiwg) {
       switch (np) {
         case 0: return launch<40, 6, 0, true, true>(VS_ATT_ARGS);

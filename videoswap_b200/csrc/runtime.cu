@@ -116,8 +116,9 @@ ProfScope::~ProfScope() {
 struct Option { const char* name; int value; };
 static Option g_options[] = {
     {"attn_tc", 1},        // tcgen05 attention for d = 40 / 80 (0 = mma.sync kernel)
-    {"attn_persist", 1},   // persistent tcgen05 attention: 1 = for short key sequences and d = 80, 2 = always, 0 = never
+    {"attn_persist", 1},   // persistent tcgen05 attention with two issuer warps (0 = round-1 kernel: one CTA per item, one issuer)
     {"attn_epiwg", 1},     // persistent d = 40 attention: dedicated epilogue warpgroup + double-buffered O accumulators
+    {"attn_pingpong", 1},  // persistent attention: MUFU ping-pong of the two softmax warpgroups (0 = free-running, A/B)
     {"attn_debug", 0},     // 1: persistent d = 40 attention records per-CTA cycle counters (vs_debug_read)
     {"attn_poly", 0},      // P chunks (of 8 per key tile) whose exp2 runs on the FMA pipe instead of MUFU (0..3)
     {"attn_handoff", 1},   // 1: the softmax ping-pong hands the MUFU pipe over after 7 of 8 key chunks, 0: after the last
