@@ -209,7 +209,8 @@ int vs_profile_dump(const char* path);   /* CSV: category, shape (m,n,k), work p
  *   "attn_epiwg"   1  persistent d = 40 kernel: dedicated epilogue warpgroup, O accumulators double-buffered in TMEM
  *   "attn_pingpong" 1 persistent kernel: the two softmax warpgroups take turns on the MUFU pipe; 0 = free-running
  *   "attn_debug"   0  1 = the persistent d = 40 kernel records cycle counters (vs_debug_read)
- *   "attn_poly"    0  P chunks (of 8 per key tile) whose exp2 runs on the FMA pipe instead of MUFU.EX2 (0..3)
+ *   "attn_poly"    1  P chunks (of 8 per key tile) whose exp2 runs on the FMA pipe instead of MUFU.EX2 (0..3); 1 of 8 measured
+ *                     neutral at full clocks and -10 % on a power-capped box (profiles/r02_attn_ab_*.json)
  *   "ln_fold"      1  LayerNorms folded into the consuming GEMM; 0 = stand-alone LayerNorm kernel
  *   "ln_fuse"      1  row statistics of folded LayerNorms written by the producing GEMM's epilogue; 0 = ln_stats pass
  *   "subpixel"     1  nearest-2x + conv3x3 as four sub-pixel convs; 0 = materialise the up-sampled tensor, then conv3x3

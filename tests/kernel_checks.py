@@ -346,9 +346,11 @@ CHECKS = {
     "self_attn_d40_nonpersistent": with_option("attn_persist", 0, lambda: check_self_attention(B=2, N=600, C=320, seed=121), 1),
     "self_attn_d80_nonpersistent": with_option("attn_persist", 0, lambda: check_self_attention(B=2, N=300, C=640, seed=123), 1),
     "self_attn_d40_persistent_n4096": with_option("attn_persist", 2, lambda: check_self_attention(B=2, N=4096, C=320, seed=124), 1),
-    "self_attn_d40_poly2": with_option("attn_persist", 2, with_option("attn_poly", 2, lambda: check_self_attention(B=2, N=4096, C=320, seed=124), 0), 1),
-    "self_attn_d40_poly3": with_option("attn_persist", 2, with_option("attn_poly", 3, lambda: check_self_attention(B=3, N=700, C=320, seed=127), 0), 1),
-    "self_attn_d80_poly2": with_option("attn_poly", 2, lambda: check_self_attention(B=2, N=1024, C=640, seed=126), 0),
+    "self_attn_d40_poly2": with_option("attn_persist", 2, with_option("attn_poly", 2, lambda: check_self_attention(B=2, N=4096, C=320, seed=124), 1), 1),
+    "self_attn_d40_poly3": with_option("attn_persist", 2, with_option("attn_poly", 3, lambda: check_self_attention(B=3, N=700, C=320, seed=127), 1), 1),
+    "self_attn_d80_poly2": with_option("attn_poly", 2, lambda: check_self_attention(B=2, N=1024, C=640, seed=126), 1),
+    "self_attn_d40_mufu_only": with_option("attn_poly", 0, lambda: check_self_attention(B=2, N=1024, C=320, seed=122), 1),
+    "self_attn_d40_free_running": with_option("attn_pingpong", 0, lambda: check_self_attention(B=2, N=1024, C=320, seed=122), 1),
     "self_attn_d40_softmax_epilogue": with_option("attn_persist", 2, with_option("attn_epiwg", 0, lambda: check_self_attention(B=2, N=4096, C=320, seed=124), 1), 1),
     "cross_attn_d40_softmax_epilogue": with_option("attn_epiwg", 0, lambda: check_cross_attention(B=2, Fr=4, N=1024, C=320, seed=134), 1),
     "self_attn_d40_many_items": with_option("attn_persist", 2, lambda: check_self_attention(B=2, N=6144, C=320, seed=128), 1),

@@ -35,7 +35,7 @@ for label, (B, N, NK, C, kvdiv) in shapes.items():
     for r in range(reps + 2):
         for ci, c in enumerate(cfgs):
             for n in names:
-                ops.set_option(n, c.get(n, {"attn_persist": 1, "attn_poly": 0, "attn_handoff": 1, "attn_tc": 1, "attn_epiwg": 1}.get(n, 0)))
+                ops.set_option(n, c.get(n, {"attn_persist": 1, "attn_poly": 1, "attn_handoff": 1, "attn_tc": 1, "attn_epiwg": 1}.get(n, 0)))
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             o = ops.attention(q, k, v, 8, kv_div=kvdiv)
@@ -62,7 +62,7 @@ qkv = torch.randn(32, 4096, 960, device=dev).half()
 q, k, v = qkv[..., :320], qkv[..., 320:640], qkv[..., 640:]
 for epiwg in (0, 1):
     for n in ("attn_persist", "attn_debug", "attn_epiwg", "attn_poly"):
-        ops.set_option(n, {"attn_persist": 2, "attn_debug": 1, "attn_epiwg": epiwg, "attn_poly": 0}[n])
+        ops.set_option(n, {"attn_persist": 2, "attn_debug": 1, "attn_epiwg": epiwg, "attn_poly": 1}[n])
     for _ in range(2):
         ops.attention(q, k, v, 8)
     torch.cuda.synchronize()

@@ -120,7 +120,7 @@ static Option g_options[] = {
     {"attn_epiwg", 1},     // persistent d = 40 attention: dedicated epilogue warpgroup + double-buffered O accumulators
     {"attn_pingpong", 1},  // persistent attention: MUFU ping-pong of the two softmax warpgroups (0 = free-running, A/B)
     {"attn_debug", 0},     // 1: persistent d = 40 attention records per-CTA cycle counters (vs_debug_read)
-    {"attn_poly", 0},      // P chunks (of 8 per key tile) whose exp2 runs on the FMA pipe instead of MUFU (0..3)
+    {"attn_poly", 1},      // P chunks (of 8 per key tile) whose exp2 runs on the FMA pipe instead of MUFU (0..3)
     {"attn_handoff", 1},   // 1: the softmax ping-pong hands the MUFU pipe over after 7 of 8 key chunks, 0: after the last
     {"gemm_pair", 1},      // CTA pairs (cta_group::2, 256-row tiles): 1 = for K >= 768, 0 = never, 2 = whenever possible
     {"gemm_stages", 0},    // smem ring depth limit (0 = all)

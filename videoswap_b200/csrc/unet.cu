@@ -627,7 +627,13 @@ int ensure_workspace(vs_unet* h, int B, int F, int H, int W) {
   want(&h->XIN, NI * hw[0] * 8);
   want(&h->XN, maxCat);
   want(&h->T, maxC); want(&h->TN, maxC); want(&h->QKV, 3 * maxC); want(&h->ATT, maxC); want(&h->HH, 4 * maxC);
-  want(&h->SC, maxC); want(&h->P0, maxC); want(&h->P1, maxC);
+  // P0 / P1 ping-pong the running sample of the mid / up path, including the up-samplers' outputs, which carry the channel
+  // count of the COARSER level at the finer resolution (e.g. 640 channels at 64x64: twice the largest block tensor).
+  // (Round 1 sized them with maxC: the last up-sampler's output overran its buffer into the neighbouring one -- harmless
+  // only while that neighbour happened to be dead; caught by the 64x64 reference fixture once the sub-pixel conv read it.)
+  size_t maxP = maxC;
+  for (int l = 0; l < 3; ++l) maxP = std::max(maxP, NI * hw[l] * (size_t)boc[l + 1]);
+  want(&h->SC, maxC); want(&h->P0, maxP); want(&h->P1, maxP);
   want(&h->SCR, std::max(std::max(NI * hw[1] * 9 * boc[0], 4 * maxC), (NI * hw[0] + boc[0]) * 64));   // im2col (stride-2) /
                 // nearest-upsample scratch / conv_in patch rows
   want(&h->KV, (size_t)B * 128 * 2 * boc[3]);
