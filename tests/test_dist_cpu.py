@@ -123,6 +123,23 @@ def test_plan_layout():
     assert torch.equal(p[2].shard_frames(x, 2), x[:, :, 8:12])
 
 
+def test_every_communicator_gets_its_own_unique_id():
+    """A ncclUniqueId serves exactly ONE communicator (the 4-GPU run of round 2 failed in ncclCommInitRank because rank 0 is
+    the first rank of a frame group AND of a CFG pair and both groups took 'the id of their first rank')."""
+    from videoswap_b200.dist_util import select_comm_ids
+    for world, cfg in ((2, True), (4, True), (8, True), (4, False)):
+        ids = [[f"frame-id-of-{r}".encode(), f"cfg-id-of-{r}".encode()] for r in range(world)]
+        used = {}                                   # id -> (kind, group)
+        for r in range(world):
+            for name, (group, idb) in select_comm_ids(make_plan(world, r, cfg=cfg), ids).items():
+                assert r in group
+                key = (name, tuple(group))
+                assert used.setdefault(idb, key) == key, f"id {idb} shared by {used[idb]} and {key}"
+        groups = {v for v in used.values()}
+        expect = {2: 1, 4: 4, 8: 6}[world] if cfg else 1        # CFG pairs + frame groups with more than one rank
+        assert len(groups) == len(used) == expect, (world, cfg, groups)
+
+
 def test_shard_jobs_covers_everything():
     for n in (0, 1, 7, 16):
         for w in (1, 2, 4, 8):

@@ -36,7 +36,10 @@ def main():
     boc = model.cfg.block_out_channels
     out = {"world": world, "cases": {}}
     ok = True
-    for name, Fr, hw in (("16f_32x32", 16, 32), ("16f_64x64_C2", 16, 64)):
+    cases = (("16f_32x32", 16, 32), ("16f_64x64_C2", 16, 64))
+    if os.environ.get("SHARD_CHECK_ONLY_C2"):
+        cases = cases[1:]
+    for name, Fr, hw in cases:
         g = torch.Generator(device=dev).manual_seed(100)
         lat = torch.randn((1, 4, Fr, hw, hw), device=dev, generator=g).half()
         embeds = torch.randn((2, 16, 77, 768), device=dev, generator=g).half()

@@ -83,23 +83,34 @@ def max_over_ranks(value: float, device=None) -> float:
 
 
 def create_comms(plan: ShardPlan) -> ShardPlan:
-    """Creates the NCCL communicators of the plan inside libvideoswap_b200 (one per exchange group).  Every rank draws an
-    id, one all_gather_object spreads them, each group uses the id of its first rank."""
+    """Creates the NCCL communicators of the plan inside libvideoswap_b200 (one per exchange group).  Every rank draws one
+    id PER KIND of group (a ncclUniqueId serves exactly one communicator: rank 0 is the first rank of a frame group AND of
+    a CFG pair), one all_gather_object spreads them, each group uses the id its first rank drew for that kind."""
     from . import _lib
     if plan.world == 1:
         return plan
-    buf = (C.c_char * 128)()
-    _lib.call("vs_comm_unique_id", buf)
-    ids: List[Optional[bytes]] = [None] * plan.world
-    dist.all_gather_object(ids, bytes(buf.raw))
-    for name, group in (("frame_comm", plan.frame_group), ("cfg_comm", plan.cfg_group)):
-        if len(group) == 1:
-            continue
+    mine = []
+    for _ in range(2):
+        buf = (C.c_char * 128)()
+        _lib.call("vs_comm_unique_id", buf)
+        mine.append(bytes(buf.raw))
+    ids: List[Optional[List[bytes]]] = [None] * plan.world
+    dist.all_gather_object(ids, mine)
+    for name, (group, idb) in select_comm_ids(plan, ids).items():
         h = C.c_void_p()
-        idb = (C.c_char * 128).from_buffer_copy(ids[group[0]])
-        _lib.call("vs_comm_create", idb, group.index(plan.rank), len(group), C.byref(h))
+        _lib.call("vs_comm_create", (C.c_char * 128).from_buffer_copy(idb), group.index(plan.rank), len(group), C.byref(h))
         setattr(plan, name, h)
     return plan
+
+
+def select_comm_ids(plan: ShardPlan, ids):
+    """ids[rank] = [id for a frame group, id for a CFG pair] as drawn by `rank`.  Returns {attribute: (group, id)} for the
+    groups of more than one rank this rank belongs to: the id its group's first rank drew for that kind."""
+    out = {}
+    for kind, (name, group) in enumerate((("frame_comm", plan.frame_group), ("cfg_comm", plan.cfg_group))):
+        if len(group) > 1:
+            out[name] = (group, ids[group[0]][kind])
+    return out
 
 
 def attach(unet, plan: ShardPlan) -> None:
