@@ -208,6 +208,8 @@ int vs_profile_dump(const char* path);   /* CSV: category, shape (m,n,k), work p
  *                     warps); 0 = the round-1 kernel (one CTA per work item, one issuer warp)
  *   "attn_epiwg"   1  persistent d = 40 kernel: dedicated epilogue warpgroup, O accumulators double-buffered in TMEM
  *   "attn_pingpong" 1 persistent kernel: the two softmax warpgroups take turns on the MUFU pipe; 0 = free-running
+ *   "attn_ptmem"   1  persistent kernel: the probabilities reach the P V MMA through tensor memory (tcgen05.st, A operand
+ *                     from TMEM); 0 = through 128B-swizzled shared memory + generic->async proxy fence
  *   "attn_debug"   0  1 = the persistent d = 40 kernel records cycle counters (vs_debug_read)
  *   "attn_poly"    1  P chunks (of 8 per key tile) whose exp2 runs on the FMA pipe instead of MUFU.EX2 (0..3); 1 of 8 measured
  *                     neutral at full clocks and -10 % on a power-capped box (profiles/r02_attn_ab_*.json)

@@ -349,6 +349,13 @@ CHECKS = {
     "self_attn_d40_poly2": with_option("attn_persist", 2, with_option("attn_poly", 2, lambda: check_self_attention(B=2, N=4096, C=320, seed=124), 1), 1),
     "self_attn_d40_poly3": with_option("attn_persist", 2, with_option("attn_poly", 3, lambda: check_self_attention(B=3, N=700, C=320, seed=127), 1), 1),
     "self_attn_d80_poly2": with_option("attn_poly", 2, lambda: check_self_attention(B=2, N=1024, C=640, seed=126), 1),
+    # P handed to the P V MMA through tensor memory (tcgen05.st, A operand from TMEM) instead of shared memory
+    # (default since r02k; the shared-memory P path stays behind "attn_ptmem" = 0)
+    "self_attn_d40_psmem": with_option("attn_ptmem", 0, lambda: check_self_attention(B=2, N=4096, C=320, seed=124), 1),
+    "self_attn_d40_psmem_ragged": with_option("attn_ptmem", 0, lambda: check_self_attention(B=3, N=700, C=320, seed=127), 1),
+    "self_attn_d80_psmem": with_option("attn_ptmem", 0, lambda: check_self_attention(B=2, N=1100, C=640, seed=129), 1),
+    "cross_attn_d40_psmem": with_option("attn_ptmem", 0, lambda: check_cross_attention(B=2, Fr=4, N=1024, C=320, seed=134), 1),
+    "cross_attn_d80_psmem": with_option("attn_ptmem", 0, lambda: check_cross_attention(B=2, Fr=8, N=1024, C=640, seed=133), 1),
     "self_attn_d40_mufu_only": with_option("attn_poly", 0, lambda: check_self_attention(B=2, N=1024, C=320, seed=122), 1),
     "self_attn_d40_free_running": with_option("attn_pingpong", 0, lambda: check_self_attention(B=2, N=1024, C=320, seed=122), 1),
     "self_attn_d40_softmax_epilogue": with_option("attn_persist", 2, with_option("attn_epiwg", 0, lambda: check_self_attention(B=2, N=4096, C=320, seed=124), 1), 1),

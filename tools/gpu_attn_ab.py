@@ -35,7 +35,7 @@ for label, (B, N, NK, C, kvdiv) in shapes.items():
     for r in range(reps + 2):
         for ci, c in enumerate(cfgs):
             for n in names:
-                ops.set_option(n, c.get(n, {"attn_persist": 1, "attn_poly": 1, "attn_handoff": 1, "attn_tc": 1, "attn_epiwg": 1}.get(n, 0)))
+                ops.set_option(n, c.get(n, {"attn_persist": 1, "attn_poly": 1, "attn_handoff": 1, "attn_tc": 1, "attn_epiwg": 1, "attn_pingpong": 1, "attn_ptmem": 0}.get(n, 0)))
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             o = ops.attention(q, k, v, 8, kv_div=kvdiv)

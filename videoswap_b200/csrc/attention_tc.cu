@@ -67,6 +67,16 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (here the fp16 probabilities, lane = query row, two K elements per
+// 32-bit column) comes straight from tensor memory, so P never takes the shared-memory round trip
+__device__ __forceinline__ void tc_mma_f16_ta(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -390,7 +400,7 @@ __device__ __forceinline__ float exp2_fma(float x) {
 // EPIWG (d <= 64, where TMEM has room for a second pair of O accumulators): a fourth warpgroup (warps 12-15) writes the
 // finished O tiles out, so the two softmax warpgroups run one uninterrupted stream of key tiles -- with the epilogue
 // inside the softmax warpgroups the strict MUFU ping-pong stalls both of them at every item boundary.
-template <int D, int HO, int NPOLY, bool EPIWG, bool DBG, bool PP = true>
+template <int D, int HO, int NPOLY, bool EPIWG, bool DBG, bool PP = true, bool PTMEM = false>
 __global__ void __launch_bounds__(EPIWG ? ATT_THREADS + 128 : ATT_THREADS, 1) attn_tcp_kernel(const __grid_constant__ TAttnArgs p) {
   using C = TCfg<D>;
   static_assert(!EPIWG || C::O_COL + 4 * C::O_STRIDE <= 512, "no TMEM room for double-buffered O");
@@ -505,9 +515,14 @@ __global__ void __launch_bounds__(EPIWG ? ATT_THREADS + 128 : ATT_THREADS, 1) at
           const uint32_t pa = p_s + (2 * i + (g & 1)) * C::P_TILE_BYTES;
           const uint32_t va = kv_s + s * C::KV_STAGE_BYTES + C::NCB * C::KV_BLOCK_BYTES;
 #pragma unroll
-          for (int k = 0; k < BKV / 16; ++k)
-            tc_mma_f16(tmem + o_col(i, n), umma_desc_sw128_kmajor(pa + k * 32),
-                       umma_desc_sw128_mnmajor(va + k * 16 * 128, C::KV_BLOCK_BYTES), idesc_pv, (j > 0 || k != 0) ? 1u : 0u);
+          for (int k = 0; k < BKV / 16; ++k) {
+            if (PTMEM)      // P_{i, g&1} lives in the first 32 columns of the S buffer it was computed from (8 columns per k16)
+              tc_mma_f16_ta(tmem + o_col(i, n), tmem + C::S_COL + (2 * i + (g & 1)) * BKV + k * 8,
+                            umma_desc_sw128_mnmajor(va + k * 16 * 128, C::KV_BLOCK_BYTES), idesc_pv, (j > 0 || k != 0) ? 1u : 0u);
+            else
+              tc_mma_f16(tmem + o_col(i, n), umma_desc_sw128_kmajor(pa + k * 32),
+                         umma_desc_sw128_mnmajor(va + k * 16 * 128, C::KV_BLOCK_BYTES), idesc_pv, (j > 0 || k != 0) ? 1u : 0u);
+          }
           tc_commit(p_empty(i, g & 1));              // this P buffer consumed, O_i quiescent once this retires
           if (i == 1) tc_commit(kv_empty(s));        // V_j consumed (K_j was consumed by Q K^T of this tile, long retired)
           if (j == nkt - 1) tc_commit(o_full(i, EPIWG ? (n & 1) : 0));   // O_i of this item complete
@@ -538,7 +553,9 @@ __global__ void __launch_bounds__(EPIWG ? ATT_THREADS + 128 : ATT_THREADS, 1) at
       for (int i = 0; i < 2; ++i) {
         long long ta = 0;
         if (DBG) ta = VS_MT();
-        if (gq >= 2) mbar_wait(p_full(i, gq & 1), ((gq - 2) >> 1) & 1);
+        // S_{i, gq&1} is free once the softmax of tile gq-2 drained it (p_full) -- or, when P lives in that same TMEM region
+        // (PTMEM), once P V of tile gq-2 has consumed it (p_empty)
+        if (gq >= 2) mbar_wait(PTMEM ? p_empty(i, gq & 1) : p_full(i, gq & 1), ((gq - 2) >> 1) & 1);
         if (DBG) { const long long tb = VS_MT(); m_pf += tb - ta; ta = tb; }
         if (i == 0) {
           if (jq == 0) mbar_wait(q_full(qb), (nq_item / QB) & 1);
@@ -652,11 +669,13 @@ __global__ void __launch_bounds__(EPIWG ? ATT_THREADS + 128 : ATT_THREADS, 1) at
         }
         if (need) m_used = mx;
         const float ms = m_used * sc;
-        if (g >= 2) mbar_wait(p_empty(i, g & 1), ((g - 2) >> 1) & 1);   // this P buffer was consumed two key tiles ago
+        if (!PTMEM && g >= 2) mbar_wait(p_empty(i, g & 1), ((g - 2) >> 1) & 1);   // this P buffer was consumed two key tiles ago
+        // (PTMEM: P aliases the S buffer just read; Q K^T of this tile already waited for P V of tile g-2)
         if (DBG) { const long long t = VS_TICK(); t_wp += t - tt; tt = t; }
         const uint32_t p_row = p_row0 + (g & 1) * C::P_TILE_BYTES;
         if (PP) named_bar_sync(9 + i, 256);                               // my turn on the MUFU pipe
         if (DBG) { const long long t = VS_TICK(); t_wt += t - tt; tt = t; }
+        uint32_t pt[16];
 #pragma unroll
         for (int c8 = 0; c8 < BKV / 8; ++c8) {       // one 16-byte chunk (8 keys) at a time
           // chunks spread evenly over the tile take the FMA-pipe exponential (NPOLY of 8)
@@ -670,12 +689,18 @@ __global__ void __launch_bounds__(EPIWG ? ATT_THREADS + 128 : ATT_THREADS, 1) at
             const __half2 h = __floats2half2_rn(e0, e1);   // the row sum is formed by the MMA from these rounded values
             pk[u] = *reinterpret_cast<const uint32_t*>(&h);
           }
-          const uint32_t dst = p_row + ((c8 ^ (row & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
-                       : "memory");
+          if (PTMEM) {                           // P -> TMEM (fp16 pairs, 4 columns per chunk), 16 columns per store
+            pt[(c8 & 3) * 4 + 0] = pk[0]; pt[(c8 & 3) * 4 + 1] = pk[1]; pt[(c8 & 3) * 4 + 2] = pk[2]; pt[(c8 & 3) * 4 + 3] = pk[3];
+            if ((c8 & 3) == 3) tmem_st16(s_addr + (c8 >> 2) * 16, pt);
+          } else {
+            const uint32_t dst = p_row + ((c8 ^ (row & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3])
+                         : "memory");
+          }
           if (PP && c8 == HO) named_bar_arrive(9 + (i ^ 1), 256);   // hand the MUFU pipe over a little early (wake-up latency)
         }
-        fence_proxy_async();                     // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+        if (PTMEM) tmem_st_wait();               // P is in tensor memory: no shared-memory round trip, no proxy fence
+        else fence_proxy_async();                // generic-proxy smem writes -> visible to the tensor-core (async) proxy
         tc_fence_before();
         mbar_arrive(p_full(i, g & 1));
         if (DBG) t_ex += VS_TICK() - tt;
@@ -778,7 +803,7 @@ __global__ void __launch_bounds__(EPIWG ? ATT_THREADS + 128 : ATT_THREADS, 1) at
 
 unsigned long long* g_attn_dbg = nullptr;     // 148 x 8 counters (DBG kernels), see vs_debug_read
 
-template <int D, int HO, int NPOLY, bool PERSIST, bool EPIWG = false, bool DBG = false, bool PP = true>
+template <int D, int HO, int NPOLY, bool PERSIST, bool EPIWG = false, bool DBG = false, bool PP = true, bool PTMEM = false>
 int launch(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, const __half* v, int ldv, __half* o, int ldo,
            int batch, int nq, int nk, int heads, long long q_bs, long long kv_bs, long long o_bs, int kv_div) {
   using C = TCfg<D>;
@@ -786,7 +811,7 @@ int launch(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, 
   static_assert(SMEM_P <= 227 * 1024, "shared memory budget (persistent)");
   static bool configured = false;
   if (!configured) {
-    if constexpr (PERSIST) VS_CHECK_CUDA(cudaFuncSetAttribute(attn_tcp_kernel<D, HO, NPOLY, EPIWG, DBG, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_P));
+    if constexpr (PERSIST) VS_CHECK_CUDA(cudaFuncSetAttribute(attn_tcp_kernel<D, HO, NPOLY, EPIWG, DBG, PP, PTMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_P));
     else VS_CHECK_CUDA(cudaFuncSetAttribute(attn_tc_kernel<D, HO>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
     configured = true;
   }
@@ -820,7 +845,7 @@ int launch(cudaStream_t st, const __half* q, int ldq, const __half* k, int ldk, 
       VS_CHECK_CUDA(cudaMemsetAsync(g_attn_dbg, 0, 256 * 16 * sizeof(unsigned long long), st));
       a.dbg = g_attn_dbg;
     }
-    return launch_pdl(attn_tcp_kernel<D, HO, NPOLY, EPIWG, DBG, PP>, dim3(ctas), dim3(EPIWG ? ATT_THREADS + 128 : ATT_THREADS), SMEM_P, st, 1, a);
+    return launch_pdl(attn_tcp_kernel<D, HO, NPOLY, EPIWG, DBG, PP, PTMEM>, dim3(ctas), dim3(EPIWG ? ATT_THREADS + 128 : ATT_THREADS), SMEM_P, st, 1, a);
   }
   else {
     dim3 grid(a.n_qblk, heads, batch);
@@ -845,19 +870,24 @@ int attention_tc(cudaStream_t st, const __half* q, int ldq, const __half* k, int
   // "attn_handoff" (A/B switch): 1 = the softmax ping-pong hands the MUFU pipe over after key chunk 6 of 8 (L0 self-
   // attention 1549 us), 0 = after the last exponential (1607 us; interleaved repetitions on one box).
   const bool early = get_option("attn_handoff") != 0;
-  // "attn_persist" (default 1): persistent CTAs; 0 = one CTA per (batch, head, 256 queries) as in round 1 (A/B switch).
-  // "attn_poly": how many of the 8 P chunks per key tile take exp2 from the FMA pipe (0, 1, 2, 3; persistent kernel only).
   // "attn_persist" (default 1): the persistent kernel with two issuer warps.  With the single issuer of round 1 it only won
   // on short key sequences (profiles/r02_attn_ab_persistent_v1.json); with Q K^T and P V issued by two warps it wins
   // everywhere (L0 self 1461 vs 1540 us, L1 self 138 vs 191 us, L0 cross 99 vs 183 us; profiles/r02_attn_ab_split_issuer.json).
   // 0 = round-1 kernel (one CTA per work item, one issuer warp).
+  // Shipped configuration of the persistent kernel: P through tensor memory ("attn_ptmem" 1: L0 self 1422 vs 1458 us, L1
+  // self 134 vs 141 us, profiles/r02_attn_ab_ptmem.json), epilogue warpgroup for d = 40 ("attn_epiwg" 1), MUFU ping-pong
+  // ("attn_pingpong" 1), one FMA-pipe exp2 chunk of eight ("attn_poly" 1).  Any other setting of those switches selects
+  // the corresponding shared-memory-P A/B variant below.
   if (get_option("attn_persist") != 0) {
     const int np = get_option("attn_poly");
-    // "attn_epiwg" (default 1): a dedicated epilogue warpgroup for d = 40 (see attn_tcp_kernel); "attn_debug": cycle counters
-    const bool epiwg = get_option("attn_epiwg") != 0;
-    if (d == 40 && get_option("attn_debug") != 0)
+    const bool epiwg = get_option("attn_epiwg") != 0, pingpong = get_option("attn_pingpong") != 0;
+    if (d == 40 && get_option("attn_debug") != 0)           // cycle counters (vs_debug_read)
       return epiwg ? launch<40, 6, 0, true, true, true>(VS_ATT_ARGS) : launch<40, 6, 0, true, false, true>(VS_ATT_ARGS);
-    if (get_option("attn_pingpong") == 0) {        // A/B: softmax warpgroups free-running on the MUFU pipe
+    if (get_option("attn_ptmem") != 0 && pingpong && epiwg && np <= 1) {
+      if (d == 40) return np > 0 ? launch<40, 6, 1, true, true, false, true, true>(VS_ATT_ARGS) : launch<40, 6, 0, true, true, false, true, true>(VS_ATT_ARGS);
+      if (d == 80) return launch<80, 6, 0, true, false, false, true, true>(VS_ATT_ARGS);
+    }
+    if (!pingpong) {                               // A/B: softmax warpgroups free-running on the MUFU pipe
       if (d == 40) return np > 0 ? launch<40, 6, 2, true, true, false, false>(VS_ATT_ARGS) : launch<40, 6, 0, true, true, false, false>(VS_ATT_ARGS);
       if (d == 80) return launch<80, 6, 0, true, false, false, false>(VS_ATT_ARGS);
     }
@@ -876,7 +906,7 @@ int attention_tc(cudaStream_t st, const __half* q, int ldq, const __half* k, int
         default: return launch<40, 6, 2, true>(VS_ATT_ARGS);
       }
     }
-    if (d == 80) return np > 0 ? launch<80, 6, 2, true>(VS_ATT_ARGS) : launch<80, 6, 0, true>(VS_ATT_ARGS);
+    if (d == 80) return np > 1 ? launch<80, 6, 2, true>(VS_ATT_ARGS) : launch<80, 6, 0, true>(VS_ATT_ARGS);
     return -1;
   }
   if (d == 40) return early ? launch<40, 6, 0, false>(VS_ATT_ARGS) : launch<40, 7, 0, false>(VS_ATT_ARGS);

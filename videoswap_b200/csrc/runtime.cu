@@ -119,6 +119,7 @@ static Option g_options[] = {
     {"attn_persist", 1},   // persistent tcgen05 attention with two issuer warps (0 = round-1 kernel: one CTA per item, one issuer)
     {"attn_epiwg", 1},     // persistent d = 40 attention: dedicated epilogue warpgroup + double-buffered O accumulators
     {"attn_pingpong", 1},  // persistent attention: MUFU ping-pong of the two softmax warpgroups (0 = free-running, A/B)
+    {"attn_ptmem", 1},     // persistent attention: P handed to the P V MMA through tensor memory instead of shared memory
     {"attn_debug", 0},     // 1: persistent d = 40 attention records per-CTA cycle counters (vs_debug_read)
     {"attn_poly", 1},      // P chunks (of 8 per key tile) whose exp2 runs on the FMA pipe instead of MUFU (0..3)
     {"attn_handoff", 1},   // 1: the softmax ping-pong hands the MUFU pipe over after 7 of 8 key chunks, 0: after the last
