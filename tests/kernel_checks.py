@@ -397,6 +397,9 @@ CHECKS = {
     # headline sizes: one statistics set = 16 frames x 64 x 64 x 10 channels = 655 360 elements with a mean 2-4x the spread
     "gn5d_c2_l0_mean3": lambda: check_groupnorm(B=2, Fr=16, H=64, W=64, c1=320, mean=3.0, seed=101),
     "gn5d_c2_l0_concat": lambda: check_groupnorm(B=1, Fr=16, H=64, W=64, c1=320, c2=320, mean=-6.0, seed=102),
+    "gn5d_silu_stats_v2": with_option("gn_stats_v2", 1, lambda: check_groupnorm(), 0),
+    "gn5d_concat_stats_v2": with_option("gn_stats_v2", 1, lambda: check_groupnorm(c1=640, c2=320), 0),
+    "gn5d_c2_l0_mean3_stats_v2": with_option("gn_stats_v2", 1, lambda: check_groupnorm(B=2, Fr=16, H=64, W=64, c1=320, mean=3.0, seed=101), 0),
     "gn_frame_l0": lambda: check_groupnorm(B=2, Fr=4, H=64, W=64, c1=320, per_frame=True, silu=False, eps=1e-6, mean=2.0, seed=103),
     "ln_fold_qkv_320": lambda: check_ln_linear(),
     "ln_fold_qkv_pe_640": lambda: check_ln_linear(rows=1280, C=640, N=1920, pe=True, seed=116, hw=64),   # one frame per warp

@@ -214,3 +214,52 @@ def test_attention_control_registration_and_store_protocol():
     assert float(ctl.attention_store["down_cross"][0].min()) == 3.0 and ctl.attention_store["down_cross"][0].shape[0] == 2
     assert float(ctl.get_average_attention()["up_cross"][0].mean()) == 1.5
     assert float(ctl.attention_store_all_step[0]["down_self"][0].max()) == 1.0      # per-step copies are not the running sum
+
+
+def test_on_disk_formats_of_the_callers_load_unchanged(tmp_path):
+    """SURVEY 8f-4, the UNet-side file formats: (i) AnimateDiff motion checkpoints after test.py:63's key remap
+    ('.pos_encoder' -> '.processor.pos_encoder') match our keys exactly; (ii) adapter.pth is the SparsePointAdapter
+    state_dict; (iii) TAP.pth is the dict frame_point_dataset.py:66-70 turns into `conditions`; (iv) an ED-LoRA '.pth'
+    ({'params': {'unet': {...lora_down / lora_up...}}}) merges through state_dict()/load_state_dict() exactly like
+    convert_edlora_to_diffusers.py:70-76 (run with the reference's own function when /root/reference is present)."""
+    m = V.AnimateDiffUNet3DModel(init="empty")
+    keys = set(m.state_dict().keys())
+    motion = {k for k in keys if ".motion_modules." in k}
+    as_shipped = {k.replace(".processor.pos_encoder", ".pos_encoder") for k in motion}          # AnimateDiff's own naming
+    remapped = {k.replace(".pos_encoder", ".processor.pos_encoder") for k in as_shipped}          # test.py:63
+    assert remapped == motion and len(motion) == 560
+    sd = {k: torch.zeros_like(v) for k, v in m.state_dict().items() if k in motion}
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all(".motion_modules." not in k for k in missing)
+    # adapter.pth / TAP.pth
+    ad = V.SparsePointAdapter(init="seeded")
+    torch.save(ad.state_dict(), tmp_path / "adapter.pth")
+    ad2 = V.SparsePointAdapter(init="empty")
+    ad2.load_state_dict(torch.load(tmp_path / "adapter.pth"))
+    assert sorted(ad2.state_dict()) == sorted(f"model_list.{l}.mlp.{i}.{p}" for l in range(4) for i in (0, 2) for p in ("weight", "bias"))
+    tap = {"pred_tracks": torch.rand(16, 5, 2) * 512, "point_name2id": {"nose": 0, "tail": 4}, "point_embedding": torch.randn(5, 1280)}
+    torch.save(tap, tmp_path / "TAP.pth")
+    t = torch.load(tmp_path / "TAP.pth")
+    cond = {"pred_tracks": t["pred_tracks"], "point_embedding": t["point_embedding"], "point_name2id": t["point_name2id"],
+            "img_size": (512, 512), "index_list": [t["point_name2id"]["nose"]]}
+    assert cond["pred_tracks"].shape == (16, 5, 2) and cond["point_embedding"].shape[1] == 1280
+    # ED-LoRA merge on two layers (rank 4), restated and -- when available -- through the reference's own function
+    k1 = "down_blocks.0.attentions.0.transformer_blocks.0.attn2.to_k.weight"
+    k2 = "down_blocks.0.attentions.0.proj_in.weight"                       # 4-D 1x1 conv weight
+    base = {k1: torch.randn(320, 768), k2: torch.randn(320, 320, 1, 1)}
+    lora = {k1.replace("to_k.weight", "to_k.lora_down.weight"): torch.randn(4, 768), k1.replace("to_k.weight", "to_k.lora_up.weight"): torch.randn(320, 4),
+            k2.replace("proj_in.weight", "proj_in.lora_down.weight"): torch.randn(4, 320, 1, 1),
+            k2.replace("proj_in.weight", "proj_in.lora_up.weight"): torch.randn(320, 4, 1, 1)}
+    want = {k1: base[k1] + 0.6 * lora[k1.replace("to_k.weight", "to_k.lora_up.weight")] @ lora[k1.replace("to_k.weight", "to_k.lora_down.weight")],
+            k2: base[k2] + 0.6 * (lora[k2.replace("proj_in.weight", "proj_in.lora_up.weight")].squeeze() @
+                                  lora[k2.replace("proj_in.weight", "proj_in.lora_down.weight")].squeeze())[..., None, None]}
+    from oracle.ref_loader import reference_available
+    if reference_available():
+        import importlib
+        from oracle.ref_loader import load_reference
+        load_reference()
+        conv = importlib.import_module("videoswap.utils.convert_edlora_to_diffusers")
+        got = conv.merge_lora_into_weight(base, lora, model_type="unet", alpha=0.6)
+        assert all(torch.allclose(got[k], want[k], atol=1e-5) for k in want)
+    m.load_state_dict(want, strict=False)                                   # the merged dict goes back through load_state_dict
+    assert torch.allclose(m.state_dict()[k1], want[k1]) and m._dirty       # ... and marks the packed weights stale
