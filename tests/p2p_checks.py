@@ -127,3 +127,148 @@ def replay_vs_reference_fixture(kind="refine"):
         mask_mismatch += int((a != b).sum().item())
     return {"map_err": map_err, "latent_err": lat_err, "mask_mismatch": mask_mismatch, "mask_pixels": sum(m.numel() for m in masks),
             "n_masks": (len(masks), len(g["latent_masks"]))}
+
+
+# ---------------------------------------------------------------------------------------------------- whole flow
+class _RecordingBlender(p2p.SpatialBlender):
+    """The product blender, remembering every mask it computed (in call order)."""
+
+    def _mask(self, maps, target_h, target_w):
+        m = super()._mask(maps, target_h, target_w)
+        self.__dict__.setdefault("all_masks", []).append(m.float().cpu())
+        return m
+
+
+class _TorchBlender(p2p.SpatialBlender):
+    """Checker-side restatement of SpatialBlender.get_mask / the blend in plain torch (spatial_blend.py:25-63,141-142), so the
+    oracle loop below does not execute the CUDA blend kernels it is checking.  A mask is a THRESHOLDED quantity: a pixel
+    within fp16 noise of the threshold may flip between the fp16 device maps and the fp32 oracle maps and would then send the
+    two (chaotic) denoising trajectories apart.  So the checker counts its disagreements with the masks the product computed
+    (`forced`, in call order) and continues with the product's mask: mask computation and everything downstream of it are
+    checked separately."""
+    forced = None
+    mismatch = 0
+    pixels = 0
+
+    def _mask(self, maps, target_h, target_w):
+        own = self._own_mask(maps, target_h, target_w)
+        if self.forced is None:
+            return own
+        given = self.forced.pop(0).to(own)
+        type(self).mismatch += int((own != given).sum())
+        type(self).pixels += own.numel()
+        return given
+
+    def _own_mask(self, maps, target_h, target_w):
+        import torch.nn.functional as F
+        items = [m[None] if m.dim() == 4 else m for m in maps]
+        p, frames, heads, r, words = items[0].shape
+        res_h = int((r * (target_h / target_w)) ** 0.5)
+        res_w = int(r / res_h)
+        n_prompts = 1 if self.prompt_choose == "source" else p
+        cat = torch.cat([it[:n_prompts].float().reshape(n_prompts, frames, heads, res_h, res_w, words).permute(0, 2, 1, 3, 4, 5)
+                         for it in items], dim=1)                                    # p (layers heads) c h w words
+        alpha = self.alpha_layers[:n_prompts].float().reshape(n_prompts, 1, 1, 1, 1, words)
+        mm = (cat * alpha).sum(-1).mean(1)
+        mm = F.max_pool2d(mm, (3, 3), (1, 1), padding=(1, 1))
+        mask = F.interpolate(mm, size=(target_h, target_w))
+        mask = mask / mask.max(-2, keepdims=True)[0].max(-1, keepdims=True)[0]
+        mask = mask.gt(self.th[0])
+        if self.prompt_choose == "both":
+            mask = mask[:1] + mask
+        return mask.float()
+
+    def __call__(self, attention_store, step_in_store=None, target_h=None, target_w=None, x_t=None):
+        if target_h is None and target_w is None and x_t is not None:
+            target_h, target_w = x_t.shape[-2:]
+        self.counter += 1
+        mask = self._mask(attention_store["down_cross"][2:4] + attention_store["up_cross"][:3], target_h, target_w)
+        self.mask_list.append(mask[0][:, None])
+        if x_t is None:
+            return mask
+        if self.start_blend < self.counter < self.end_blend:
+            x_t = x_t[:1] + mask[:, None] * (x_t - x_t[:1])
+        return x_t
+
+
+def _edit_controller(store, blender_cls, n_steps):
+    """AttentionRefine with everything switched on for all steps: cross refine (a new word at position 3, the others mapped
+    1:1), masked self-attention replacement and latent blend from the first callback on."""
+    mapper = torch.arange(77)[None].clone()
+    mapper[0, 3] = -1
+    alphas = torch.ones(1, 77)
+    alphas[0, 3] = 0.0
+    words = torch.zeros(2, 77)
+    words[:, 2] = 1.0
+    words[1, 3] = 1.0
+
+    def blender(choose, start, end):
+        # threshold 0.92: with seeded random weights the normalised maps live in [0.85, 1] (median 0.92) -> ~half the pixels
+        b = blender_cls(words, th=(0.92, 0.92), NUM_DDIM_STEPS=n_steps, prompt_choose=choose)
+        b.start_blend, b.end_blend = start, end
+        return b
+    ctl = p2p.AttentionRefine(mapper, alphas, num_steps=n_steps, cross_replace_alpha=p2p.time_words_alpha(n_steps, 1.0),
+                              self_replace_steps=1.0, latent_blend=blender("both", 0, 10 ** 6), additional_attention_store=store,
+                              attention_blend=blender("source", 0, 10 ** 6), image_height=512, image_width=512)
+    return ctl
+
+
+def edit_flow_vs_oracle(n_steps=2, Fr=2, hw=64):
+    """The `use_blend: true` loop of a shipped config, shortened to n_steps: DDIM inversion with an AttentionStore registered
+    (no CFG), then the CFG editing loop with AttentionRefine + masked self-attention replacement + latent blend, through the
+    product surface (pipe.invert / pipe.__call__ with `controller=`) at the shipped resolution (64x64 latents: only the
+    16x16 / 8x8 levels are controlled and the blend reads up_cross[:3], all 16x16 -- at other input sizes the reference's own
+    SpatialBlender concatenates maps of different resolutions and fails) against the same flow on the CPU oracle (oracle UNet
+    with its attention hook, p2p's device-agnostic controller logic on CPU tensors -- itself pinned to the reference's
+    classes by replay_vs_reference_fixture -- and the torch restatement of the blend above)."""
+    from videoswap_b200 import DDIMInverseScheduler, DDIMScheduler, VideoSwapPipeline
+    m, sd = U.get_model()
+    lat0 = U.randn((1, 4, Fr, hw, hw), 91).half()
+    src = U.randn((1, 16, 77, 768), 92).half()
+    tgt = U.randn((1, 16, 77, 768), 93).half()
+    neg = U.randn((1, 16, 77, 768), 94).half()
+    # ---- native
+    pipe = VideoSwapPipeline(m, DDIMScheduler(), inverse_scheduler=DDIMInverseScheduler())
+    store = p2p.AttentionStore()
+    store.LOW_RESOURCE = True
+    p2p.register_attention_control(pipe, store)
+    try:
+        inv = pipe.invert(src.cuda(), lat0.cuda(), num_inference_steps=50, controller=store, max_iters=n_steps).latents
+        ctl = _edit_controller(store, _RecordingBlender, n_steps)
+        p2p.register_attention_control(pipe, ctl)
+        out = pipe(tgt.cuda(), inv, negative_prompt_embeds=neg.cuda(), num_inference_steps=50, guidance_scale=7.5, controller=ctl,
+                   max_iters=n_steps).videos
+        torch.cuda.synchronize()
+    finally:
+        p2p.register_attention_control(pipe, None)
+    # ---- oracle
+    ostore = p2p.AttentionStore()
+    ostore.LOW_RESOURCE = True
+    sched = O.DDIM()
+    x = lat0.float()
+    with torch.no_grad():
+        O.ATTN_HOOK = ostore
+        try:
+            for i, t in enumerate(sched.inverse_timesteps(50)[:n_steps]):
+                x = sched.inverse_step(O.unet_forward(sd, O.OracleConfig(), x, t, src.float()), t, x, 50)
+                x = ostore.step_callback(x)
+            oinv = x
+            octl = _edit_controller(ostore, _TorchBlender, n_steps)
+            # the two blenders of the native controller were called in this order: attention blend per controlled self-attention
+            # layer, latent blend once per step -- the oracle's blenders are called in the same order
+            octl.attention_blend.forced = list(ctl.attention_blend.all_masks)
+            octl.latent_blend.forced = list(ctl.latent_blend.all_masks)
+            _TorchBlender.mismatch = _TorchBlender.pixels = 0
+            O.ATTN_HOOK = octl
+            ehs2 = torch.cat([neg, tgt]).float()
+            for i, t in enumerate(sched.timesteps(50)[:n_steps]):
+                x = O.denoise_step(sd, O.OracleConfig(), sched, x, t, 50, ehs2, 7.5)
+                x = octl.step_callback(x)
+        finally:
+            O.ATTN_HOOK = None
+    ref = x.permute(0, 2, 1, 3, 4).reshape(Fr, 4, hw, hw)
+    fill = torch.stack([mm.float().cpu() for mm in ctl.latent_blend.mask_list]).mean().item()
+    return {"inversion_psnr": U.psnr(inv, oinv), "edit_psnr": U.psnr(out, ref), "stored_maps": sum(len(v) for v in store.attention_store.values()),
+            "mask_mismatch": _TorchBlender.mismatch, "mask_pixels": _TorchBlender.pixels, "mask_fill": fill,
+            "masks_checked": (len(ctl.attention_blend.all_masks), len(ctl.latent_blend.all_masks)),
+            "unused_forced": (len(octl.attention_blend.forced), len(octl.latent_blend.forced)), "steps": (store.cur_step, ctl.cur_step)}

@@ -165,3 +165,15 @@ def test_device_controllers_match_the_reference_classes(kind):
     assert r["n_masks"][0] == r["n_masks"][1]
     assert r["map_err"] <= 2e-3 and r["latent_err"] <= 4e-3, r
     assert r["mask_mismatch"] <= 0.01 * r["mask_pixels"], r      # thresholded masks: fp16 maps vs the fp32 reference
+
+
+def test_use_blend_flow_matches_oracle():
+    """Inversion with the store registered, then the editing loop with cross refine + masked self replacement + latent blend
+    (the `use_blend: true` body of the shipped configs at 512x512, 2 + 2 steps) through pipe.invert / pipe(..., controller=)."""
+    from tests import p2p_checks as P
+    r = P.edit_flow_vs_oracle(n_steps=2)
+    assert r["steps"] == (2, 2) and r["stored_maps"] == 12, r
+    assert r["inversion_psnr"] >= PSNR_MIN and r["edit_psnr"] >= PSNR_MIN, r
+    assert 0.05 < r["mask_fill"] < 0.95, r                               # the blend really mixes source and target latents
+    assert r["unused_forced"] == (0, 0) and r["masks_checked"][1] == 2, r # both sides computed the same number of masks
+    assert r["mask_mismatch"] <= 0.03 * r["mask_pixels"], r              # thresholded maps: fp16 device maps vs fp32 oracle
