@@ -73,6 +73,10 @@ extern "C" int vs_groupnorm(void* stream, const void* d_x1, int c1, const void* 
                             int imgs_per_set, int groups, float eps, const float* d_gamma, const float* d_beta, int silu,
                             float* d_sums, void* d_out) {
   cudaStream_t st = (cudaStream_t)stream;
+  if (imgs_per_set == 1 && c2 == 0) {     // per-frame norm of one tensor: the single-pass cluster kernel, as in the UNet forward
+    const int e = groupnorm_frame_fused(st, (const __half*)d_x1, c1, nimg, hw, groups, eps, d_gamma, d_beta, silu != 0, (__half*)d_out);
+    if (e >= 0) return e;
+  }
   if (int e = groupnorm_stats(st, (const __half*)d_x1, c1, (const __half*)d_x2, c2, nimg, hw, imgs_per_set, groups, d_sums)) return e;
   return groupnorm_apply(st, (const __half*)d_x1, c1, (const __half*)d_x2, c2, nimg, hw, imgs_per_set, groups, d_sums, eps,
                          d_gamma, d_beta, silu != 0, (__half*)d_out);

@@ -56,6 +56,9 @@ int groupnorm_apply(cudaStream_t st, const __half* x1, int c1, const __half* x2,
                     int imgs_per_set, int groups, const float* sums, float eps, const float* gamma,
                     const float* beta, bool silu, __half* out, int count_scale = 1);   // count_scale: `sums` cover that many
                     // times the local elements (frame-sharded 5-D GroupNorm after the all-reduce of the sums)
+// Per-frame GroupNorm in ONE pass (image resident in the shared memory of a thread-block cluster); -1 = shape not supported
+int groupnorm_frame_fused(cudaStream_t st, const __half* x, int C, int nimg, int hw, int groups, float eps, const float* gamma,
+                          const float* beta, bool silu, __half* out);
 // LayerNorm over the last dim of [rows, C]; optional temporal positional encoding pe[(row / hw) % F, :] added after.
 int layernorm(cudaStream_t st, const __half* x, int rows, int C, const float* gamma, const float* beta,
               const float* pe, int hw, int F, __half* out);

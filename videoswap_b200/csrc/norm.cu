@@ -135,6 +135,110 @@ __global__ void gn_apply_kernel(const GnParams p) {
   for (; i < p1; i += step) apply(gn_load(p, base + i, cv), base + i);
 }
 
+// ---------------------------------------------------------------------------------------------- per-frame GroupNorm, one pass
+// Transformer3DModel.norm / the motion module's norm (attention.py:108, motion_module.py:146) normalise every frame on its
+// own: one image is 2.6 MB at the 64x64 level, 1.3 MB / 0.66 MB / 0.16 MB below -- it fits the shared memory of a thread-block
+// CLUSTER (16 / 8 / 4 / 1 CTAs x 164 KB).  So each image is read ONCE: the CTAs of a cluster stage their pixel slices in
+// shared memory while accumulating (sum, sum of squares) per group, exchange the 64 partial sums through distributed shared
+// memory (ld.shared::cluster) between two cluster barriers, and normalise straight from shared memory.  Replaces the
+// statistics kernel + apply kernel pair (two reads, two launches, global atomics) for 36 of the 81 GroupNorms; deterministic
+// (fixed summation order).
+constexpr int kGnFusedThreads = 480;          // CV * rows with CV = C / 8 in {40, 80, 160}: 12 / 6 / 3 pixel rows
+__global__ void __launch_bounds__(kGnFusedThreads, 1) gn_frame_fused_kernel(const GnParams p, int ncta, int ppc) {
+  extern __shared__ __align__(16) uint8_t gsm[];
+  float* part = reinterpret_cast<float*>(gsm);                   // [64]: this CTA's (sum, sumsq) per group
+  float* tot = part + 64;                                         // [64]: cluster totals
+  uint4* tile = reinterpret_cast<uint4*>(gsm + 512);              // [ppc][CV] 16-byte vectors
+  const int rank = (int)cluster_ctarank();
+  const int img = blockIdx.x / ncta;
+  const int cv = threadIdx.x % p.CV, r = threadIdx.x / p.CV, rows = blockDim.x / p.CV;
+  if (threadIdx.x < 64) part[threadIdx.x] = 0.f;
+  __syncthreads();
+  pdl_trigger();
+  pdl_wait();
+  const int ga = (cv * 8) / p.cpg, gb = (cv * 8 + 7) / p.cpg;
+  const int split = (ga == gb) ? 8 : (gb * p.cpg - cv * 8);
+  const uint4* src = reinterpret_cast<const uint4*>(p.x1) + ((long long)img * p.hw + (long long)rank * ppc) * p.CV + cv;
+  float ps[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, pq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  auto accum = [&](const uint4& v) {
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      ps[2 * j] += f.x; pq[2 * j] = fmaf(f.x, f.x, pq[2 * j]);
+      ps[2 * j + 1] += f.y; pq[2 * j + 1] = fmaf(f.y, f.y, pq[2 * j + 1]);
+    }
+  };
+  int i = r;
+  for (; i + 3 * rows < ppc; i += 4 * rows) {                     // 4 independent 16-byte loads in flight per thread
+    const uint4 v0 = src[(long long)i * p.CV], v1 = src[(long long)(i + rows) * p.CV];
+    const uint4 v2 = src[(long long)(i + 2 * rows) * p.CV], v3 = src[(long long)(i + 3 * rows) * p.CV];
+    tile[i * p.CV + cv] = v0; tile[(i + rows) * p.CV + cv] = v1; tile[(i + 2 * rows) * p.CV + cv] = v2; tile[(i + 3 * rows) * p.CV + cv] = v3;
+    accum(v0); accum(v1); accum(v2); accum(v3);
+  }
+  for (; i < ppc; i += rows) {
+    const uint4 v = src[(long long)i * p.CV];
+    tile[i * p.CV + cv] = v;
+    accum(v);
+  }
+  float sa = 0.f, qa = 0.f, sb = 0.f, qb = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (j < split) { sa += ps[j]; qa += pq[j]; } else { sb += ps[j]; qb += pq[j]; }
+  }
+  atomicAdd(&part[ga * 2], sa);
+  atomicAdd(&part[ga * 2 + 1], qa);
+  if (gb != ga) {
+    atomicAdd(&part[gb * 2], sb);
+    atomicAdd(&part[gb * 2 + 1], qb);
+  }
+  __syncthreads();
+  if (ncta > 1) cluster_sync_all();                               // every CTA's partial sums are complete
+  if (threadIdx.x < 64) {
+    float t = 0.f;
+    if (ncta > 1) {
+      const uint32_t mine = smem_u32(&part[threadIdx.x]);
+      for (int c = 0; c < ncta; ++c) {                             // fixed order: deterministic
+        float v;
+        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(mapa_shared(mine, (uint32_t)c)));
+        t += v;
+      }
+    } else {
+      t = part[threadIdx.x];
+    }
+    tot[threadIdx.x] = t;
+  }
+  __syncthreads();
+  float a[8], b[8];
+  const float inv_n = 1.f / ((float)p.hw * p.cpg);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cv * 8 + j;
+    const int g = c / p.cpg;
+    const float mean = tot[g * 2] * inv_n;
+    const float var = fmaxf(tot[g * 2 + 1] * inv_n - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + p.eps);
+    a[j] = rstd * p.gamma[c];
+    b[j] = p.beta[c] - mean * a[j];
+  }
+  uint4* dst = reinterpret_cast<uint4*>(p.out) + ((long long)img * p.hw + (long long)rank * ppc) * p.CV + cv;
+  for (i = r; i < ppc; i += rows) {
+    const uint4 v = tile[i * p.CV + cv];
+    const __half2* h = reinterpret_cast<const __half2*>(&v);
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(h[j]);
+      float y0 = f.x * a[2 * j] + b[2 * j], y1 = f.y * a[2 * j + 1] + b[2 * j + 1];
+      if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); }
+      oh[j] = __floats2half2_rn(y0, y1);
+    }
+    dst[(long long)i * p.CV] = o;
+  }
+  if (ncta > 1) cluster_sync_all();                               // nobody leaves while a peer may still read its partial sums
+}
+
 int gn_fill(GnParams& p, dim3& grid, int& threads, const __half* x1, int c1, const __half* x2, int c2, int nimg, int hw,
             int imgs_per_set, int groups) {
   const int C = c1 + c2;
@@ -381,6 +485,34 @@ int ln_rowstats(cudaStream_t st, const __half* x, long long rows, int C, float* 
   if (lpr == 8) return launch_pdl(ln_stats_kernel<8>, dim3(grid), dim3(256), 0, st, 1, x, rows, s2);
   if (lpr == 16) return launch_pdl(ln_stats_kernel<16>, dim3(grid), dim3(256), 0, st, 1, x, rows, s2);
   return launch_pdl(ln_stats_kernel<32>, dim3(grid), dim3(256), 0, st, 1, x, rows, s2);
+}
+
+// Single-pass per-frame GroupNorm (see gn_frame_fused_kernel).  Returns -1 when the shape does not fit (caller falls back to
+// the statistics + apply pair): one source tensor, C / 8 dividing 480 threads, an image slice per CTA <= 164 KB with a
+// cluster of <= 16 CTAs.
+int groupnorm_frame_fused(cudaStream_t st, const __half* x, int C, int nimg, int hw, int groups, float eps, const float* gamma,
+                          const float* beta, bool silu, __half* out) {
+  if (get_option("gn_fused") == 0) return -1;
+  if (C % 8 != 0 || C % groups != 0 || C / groups < 8 || groups > 32) return -1;
+  const int CV = C / 8;
+  if (kGnFusedThreads % CV != 0) return -1;
+  const size_t img_bytes = (size_t)hw * C * 2, cap = 160 * 1024;
+  int ncta = 1;
+  while ((img_bytes + ncta - 1) / ncta > cap && ncta < 16) ncta *= 2;
+  if ((img_bytes + ncta - 1) / ncta > cap || hw % ncta != 0) return -1;
+  const int ppc = hw / ncta;
+  const size_t smem = 512 + (size_t)ppc * C * 2;
+  static bool configured = false;
+  if (!configured) {
+    VS_CHECK_CUDA(cudaFuncSetAttribute(gn_frame_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 + (int)cap));
+    VS_CHECK_CUDA(cudaFuncSetAttribute(gn_frame_fused_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    configured = true;
+  }
+  GnParams p{};
+  p.x1 = x; p.c1 = C; p.C = C; p.CV = CV; p.hw = hw; p.imgs_per_set = 1; p.groups = groups; p.cpg = C / groups;
+  p.pix_per_set = hw; p.gamma = gamma; p.beta = beta; p.eps = eps; p.silu = silu ? 1 : 0; p.out = out; p.count_scale = 1;
+  ProfScope prof(st, PC_GROUPNORM, 4.0 * nimg * (double)hw * C, 1, (long long)nimg * hw, C, 1);   // read once + write once
+  return launch_pdl(gn_frame_fused_kernel, dim3((unsigned)(nimg * ncta)), dim3(kGnFusedThreads), smem, st, ncta, p, ncta, ppc);
 }
 
 int groupnorm_stats(cudaStream_t st, const __half* x1, int c1, const __half* x2, int c2, int nimg, int hw,

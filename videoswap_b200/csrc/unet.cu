@@ -510,8 +510,14 @@ int transformer(Ctx& c, const Transformer& t, __half* x) {
   vs_unet* h = c.h;
   const int hw = c.H * c.W, C = t.C, M = c.NI * hw, heads = h->cfg.num_heads, d = C / heads;
   NEXT_SUMS(sums);
-  RUN(groupnorm_stats(c.st, x, C, nullptr, 0, c.NI, hw, 1, h->cfg.norm_num_groups, sums, false));
-  RUN(groupnorm_apply(c.st, x, C, nullptr, 0, c.NI, hw, 1, h->cfg.norm_num_groups, sums, 1e-6f, t.norm.g, t.norm.b, false, h->XN));
+  {
+    const int e = groupnorm_frame_fused(c.st, x, C, c.NI, hw, h->cfg.norm_num_groups, 1e-6f, t.norm.g, t.norm.b, false, h->XN);
+    if (e > 0) return e;
+    if (e < 0) {
+      RUN(groupnorm_stats(c.st, x, C, nullptr, 0, c.NI, hw, 1, h->cfg.norm_num_groups, sums, false));
+      RUN(groupnorm_apply(c.st, x, C, nullptr, 0, c.NI, hw, 1, h->cfg.norm_num_groups, sums, 1e-6f, t.norm.g, t.norm.b, false, h->XN));
+    }
+  }
   RUN(linear(c, h->XN, M, t.proj_in, nullptr, h->T, use_fold(t.f_qkv)));
   // self-attention
   if (use_fold(t.f_qkv)) {
@@ -570,8 +576,14 @@ int motion(Ctx& c, const Motion& m, int level, __half* x) {
   VS_REQUIRE(Ft <= h->cfg.pe_max_len, "video_length %d exceeds temporal_position_encoding_max_len %d", Ft, h->cfg.pe_max_len);
   if (k > 1) VS_REQUIRE(c.B == 1 && hw_all % k == 0, "frame sharding needs batch 1 per rank and h*w (%d) divisible by the %d shards", hw_all, k);
   NEXT_SUMS(sums);
-  RUN(groupnorm_stats(c.st, x, C, nullptr, 0, c.NI, hw_all, 1, 32, sums, false));
-  RUN(groupnorm_apply(c.st, x, C, nullptr, 0, c.NI, hw_all, 1, 32, sums, 1e-6f, m.norm.g, m.norm.b, false, h->XN));
+  {
+    const int e = groupnorm_frame_fused(c.st, x, C, c.NI, hw_all, 32, 1e-6f, m.norm.g, m.norm.b, false, h->XN);
+    if (e > 0) return e;
+    if (e < 0) {
+      RUN(groupnorm_stats(c.st, x, C, nullptr, 0, c.NI, hw_all, 1, 32, sums, false));
+      RUN(groupnorm_apply(c.st, x, C, nullptr, 0, c.NI, hw_all, 1, 32, sums, 1e-6f, m.norm.g, m.norm.b, false, h->XN));
+    }
+  }
   const __half* xin = h->XN;
   if (k > 1) {
     RUN(comm_all_to_all_rows(h->fcomm, c.st, h->XN, h->SC, c.F, (size_t)hw * C, 0));    // [F/k, k, hw C] -> [k, F/k, hw C] = [F, hw, C]
