@@ -216,7 +216,8 @@ int vs_profile_dump(const char* path);   /* CSV: category, shape (m,n,k), work p
  *   "ln_fold"      1  LayerNorms folded into the consuming GEMM; 0 = stand-alone LayerNorm kernel
  *   "ln_fuse"      1  row statistics of folded LayerNorms written by the producing GEMM's epilogue; 0 = ln_stats pass
  *   "gn_fused"     1  per-frame GroupNorms (Transformer3DModel.norm, motion-module norm) as ONE pass with the image resident
- *                     in the shared memory of a thread-block cluster (<= 16 CTAs x 160 KB); 0 = statistics + apply kernels
+ *                     in the shared memory of a thread-block cluster where that measured faster (<= 4 CTAs x 160 KB: the
+ *                     16x16 / 8x8 levels); 2 = up to 16 CTAs; 0 = statistics + apply kernels everywhere
  *   "subpixel"     1  nearest-2x + conv3x3 as four sub-pixel convs; 0 = materialise the up-sampled tensor, then conv3x3
  *   "pdl"          1  programmatic dependent launch between the hot kernels; 0 = plain stream order */
 int vs_set_option(const char* name, int value);

@@ -402,7 +402,8 @@ CHECKS = {
     "gn5d_c2_l0_mean3_stats_v2": with_option("gn_stats_v2", 1, lambda: check_groupnorm(B=2, Fr=16, H=64, W=64, c1=320, mean=3.0, seed=101), 0),
     # per-frame GroupNorm, single pass in a thread-block cluster: 16 / 8 / 4 / 1 CTAs per image, SiLU variant, and the
     # two-kernel path behind "gn_fused" = 0 (also taken when an image does not fit: 96x96 at 320 channels = 5.9 MB)
-    "gn_frame_fused_l1": lambda: check_groupnorm(B=2, Fr=3, H=32, W=32, c1=640, per_frame=True, silu=False, eps=1e-6, mean=-1.0, seed=104),
+    "gn_frame_fused_l1": with_option("gn_fused", 2, lambda: check_groupnorm(B=2, Fr=3, H=32, W=32, c1=640, per_frame=True, silu=False, eps=1e-6, mean=-1.0, seed=104), 1),
+    "gn_frame_fused_l0_cluster16": with_option("gn_fused", 2, lambda: check_groupnorm(B=2, Fr=4, H=64, W=64, c1=320, per_frame=True, silu=False, eps=1e-6, mean=2.0, seed=103), 1),
     "gn_frame_fused_l2": lambda: check_groupnorm(B=2, Fr=3, H=16, W=16, c1=1280, per_frame=True, silu=False, eps=1e-6, mean=0.5, seed=105),
     "gn_frame_fused_l3_silu": lambda: check_groupnorm(B=2, Fr=3, H=8, W=8, c1=1280, per_frame=True, silu=True, eps=1e-6, seed=106),
     "gn_frame_fused_odd": lambda: check_groupnorm(B=1, Fr=3, H=7, W=12, c1=320, per_frame=True, silu=False, eps=1e-6, seed=107),
