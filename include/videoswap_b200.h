@@ -215,6 +215,7 @@ int vs_profile_dump(const char* path);   /* CSV: category, shape (m,n,k), work p
  *                     neutral at full clocks and -10 % on a power-capped box (profiles/r02_attn_ab_*.json)
  *   "ln_fold"      1  LayerNorms folded into the consuming GEMM; 0 = stand-alone LayerNorm kernel
  *   "ln_fuse"      1  row statistics of folded LayerNorms written by the producing GEMM's epilogue; 0 = ln_stats pass
+ *   "tattn_vst"    1  temporal attention writes its outputs with 16-byte stores from a shared-memory stage; 0 = 4-byte stores
  *   "gn_fused"     1  per-frame GroupNorms (Transformer3DModel.norm, motion-module norm) as ONE pass with the image resident
  *                     in the shared memory of a thread-block cluster where that measured faster (<= 4 CTAs x 160 KB: the
  *                     16x16 / 8x8 levels); 2 = up to 16 CTAs; 0 = statistics + apply kernels everywhere

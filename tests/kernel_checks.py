@@ -440,6 +440,8 @@ CHECKS = {
     "cross_attn_d40": lambda: check_cross_attention(B=2, Fr=2, N=300, C=320, seed=131),
     "cross_attn": check_cross_attention,
     "temporal_attn_d40": lambda: check_temporal_attention(C=320),
+    "temporal_attn_d40_scalar_stores": with_option("tattn_vst", 0, lambda: check_temporal_attention(C=320), 1),
+    "temporal_attn_d80_f16": lambda: check_temporal_attention(B=2, Fr=16, HW=33, C=640, seed=141),
     "temporal_attn_d160_f3": lambda: check_temporal_attention(B=1, Fr=3, HW=7, C=1280),
     "temporal_attn_f24": lambda: check_temporal_attention(B=1, Fr=24, HW=5, C=640),
     "cfg_ddim_f16": lambda: check_cfg_ddim(torch.float16),

@@ -394,7 +394,7 @@ struct TAttnParams {
   long long items;
 };
 
-template <int D, int FP>   // FP = frames padded to 16 or 32
+template <int D, int FP, bool VST = true>   // FP = frames padded to 16 or 32; VST: outputs staged in shared memory, 16-byte stores
 __global__ void __launch_bounds__(128) tattn_kernel(const TAttnParams p) {
   pdl_trigger();
   pdl_wait();
@@ -461,12 +461,31 @@ __global__ void __launch_bounds__(128) tattn_kernel(const TAttnParams p) {
     warp_pv<NT, ON>(o, s, v_s, LDSB, lane);
     const float i0 = 1.f / l0, i1 = 1.f / l1;
     const int f0 = mt * 16 + (lane >> 2), f1 = f0 + 8;
+    if (VST) {
+      // the 16 query rows of this m-tile were read (ldmatrix, above) by this warp only and are dead now: stage the outputs
+      // there and write each 80 / 160 / 320-byte head row with 16-byte stores instead of 4-byte fragments
+      __syncwarp();
+      __half* stage = reinterpret_cast<__half*>(smem) + (size_t)warp * (3 * FP * LDS) + (size_t)mt * 16 * LDS;
 #pragma unroll
-    for (int n = 0; n < ON; ++n) {
-      const int c = n * 8 + (lane & 3) * 2;
-      if (c < D) {
-        if (f0 < p.F) *reinterpret_cast<__half2*>(dst + f0 * orow + c) = __floats2half2_rn(o[n][0] * i0, o[n][1] * i0);
-        if (f1 < p.F) *reinterpret_cast<__half2*>(dst + f1 * orow + c) = __floats2half2_rn(o[n][2] * i1, o[n][3] * i1);
+      for (int n = 0; n < ON; ++n) {
+        const int c = n * 8 + (lane & 3) * 2;
+        *reinterpret_cast<__half2*>(stage + (lane >> 2) * LDS + c) = __floats2half2_rn(o[n][0] * i0, o[n][1] * i0);
+        *reinterpret_cast<__half2*>(stage + ((lane >> 2) + 8) * LDS + c) = __floats2half2_rn(o[n][2] * i1, o[n][3] * i1);
+      }
+      __syncwarp();
+      constexpr int VCH = D / 8;                       // 16-byte chunks per head row
+      for (int e = lane; e < 16 * VCH; e += 32) {
+        const int fr = e / VCH, ch = e % VCH, f = mt * 16 + fr;
+        if (f < p.F) *reinterpret_cast<uint4*>(dst + f * orow + ch * 8) = *reinterpret_cast<const uint4*>(stage + fr * LDS + ch * 8);
+      }
+    } else {
+#pragma unroll
+      for (int n = 0; n < ON; ++n) {
+        const int c = n * 8 + (lane & 3) * 2;
+        if (c < D) {
+          if (f0 < p.F) *reinterpret_cast<__half2*>(dst + f0 * orow + c) = __floats2half2_rn(o[n][0] * i0, o[n][1] * i0);
+          if (f1 < p.F) *reinterpret_cast<__half2*>(dst + f1 * orow + c) = __floats2half2_rn(o[n][2] * i1, o[n][3] * i1);
+        }
       }
     }
   }
@@ -478,12 +497,14 @@ int launch_tattn(cudaStream_t st, const TAttnParams& p) {
   constexpr int SMEM = 4 * 3 * FP * (DP + 8) * 2;
   static bool configured = false;
   if (!configured) {
-    VS_CHECK_CUDA(cudaFuncSetAttribute(tattn_kernel<D, FP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    VS_CHECK_CUDA(cudaFuncSetAttribute(tattn_kernel<D, FP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    VS_CHECK_CUDA(cudaFuncSetAttribute(tattn_kernel<D, FP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
   const long long blocks = (p.items + 3) / 4;
   ProfScope prof(st, PC_TATTN, 8.0 * p.B * p.F * (double)p.HW * p.C);   // bytes: read 3C + write C fp16 per token
-  return launch_pdl(tattn_kernel<D, FP>, dim3((unsigned)blocks), dim3(128), SMEM, st, 1, p);
+  if (get_option("tattn_vst") == 0) return launch_pdl(tattn_kernel<D, FP, false>, dim3((unsigned)blocks), dim3(128), SMEM, st, 1, p);
+  return launch_pdl(tattn_kernel<D, FP, true>, dim3((unsigned)blocks), dim3(128), SMEM, st, 1, p);
 }
 
 }  // namespace

@@ -127,6 +127,7 @@ static Option g_options[] = {
     {"gemm_stages", 0},    // smem ring depth limit (0 = all)
     {"ln_fold", 1},        // LayerNorms folded into the GEMM that consumes them (0 = stand-alone LayerNorm kernel)
     {"ln_fuse", 1},        // row statistics of folded LayerNorms come from the producing GEMM's epilogue (0 = ln_stats_kernel pass)
+    {"tattn_vst", 1},      // temporal attention: outputs staged in shared memory and written with 16-byte stores (0 = 4-byte)
     {"gn_fused", 1},       // per-frame GroupNorms as one cluster-resident pass (0 = statistics kernel + apply kernel)
     {"gn_stats_v2", 0},    // GroupNorm statistics with per-position accumulators (no per-element group select); A/B
     {"subpixel", 1},       // nearest-2x + 3x3 conv as four 2x2 sub-pixel convs on the low-resolution input (0 = materialise)
