@@ -363,6 +363,13 @@ CHECKS = {
     "self_attn_d40_many_items": with_option("attn_persist", 2, lambda: check_self_attention(B=2, N=6144, C=320, seed=128), 1),
     "self_attn_d80_many_items_odd_tiles": lambda: check_self_attention(B=6, N=1100, C=640, seed=129),     # nkt = 18, 5 q blocks
     "cross_attn_d80_many_items": lambda: check_cross_attention(B=2, Fr=8, N=1024, C=640, seed=133),
+    # epilogue with the TMEM load of the next sub-tile in flight ("epi_prefetch" = 1)
+    "gemm_bn160_prefetch": with_option("epi_prefetch", 1, lambda: check_gemm(512, 320, 320), 0),
+    "gemm_residual_prefetch": with_option("epi_prefetch", 1, lambda: check_gemm(128 * 150 + 9, 1280, 320, residual=True, seed=8), 0),
+    "gemm_pair_prefetch": with_option("epi_prefetch", 1, lambda: check_gemm(128 * 5 + 9, 1280, 1024, seed=13), 0),
+    "conv3x3_epi_prefetch": with_option("epi_prefetch", 1, lambda: check_conv3x3(rowvec=True, residual=True), 0),
+    "ln_fuse_res_prefetch": with_option("epi_prefetch", 1, lambda: check_linear_ln_linear(rows=128 * 150 + 37, residual=True, N=320, seed=161, mean=2.0), 0),
+    "gemm_bn128_tail_prefetch": with_option("epi_prefetch", 1, lambda: check_gemm(300, 768, 320, bn=128), 0),
     "gemm_bn160": lambda: check_gemm(512, 320, 320),
     "gemm_bn128_tail": lambda: check_gemm(300, 768, 320, bn=128),
     "gemm_bn64": lambda: check_gemm(130, 64, 128, bn=64),

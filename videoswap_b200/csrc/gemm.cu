@@ -70,6 +70,7 @@ struct GemmParams {
   int ldr;
   __half* out;
   int ldc;
+  int epi_prefetch;  // 1 = the accumulator columns of sub-tile s+1 are loaded from TMEM while sub-tile s is processed
   int staged;        // 1 = smem-transposed coalesced epilogue; 0 = direct stores for tiny / unaligned N
   int stages;        // 0 = all, else limits the smem ring depth (pipeline-depth experiments)
 };
@@ -360,10 +361,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         }
         mbar_wait(tfull_bar(acc), aph);
         tc_fence_after();
+        // Linear epilogues prefetch the next 32 accumulator columns (tcgen05.ld is asynchronous until tcgen05.wait::ld), so the
+        // TMEM round trip of sub-tile s+1 overlaps the bias / transpose / store work of sub-tile s.
+        uint32_t vn[32];
+        const bool prefetch = !GEGLU && p.epi_prefetch != 0;
+        if (prefetch) tmem_ld32(taddr, vn);
 #pragma unroll 1
         for (int s = 0; s < nsub; ++s) {
           float f[32];
-          {
+          if (prefetch) {
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(vn[j]);
+            if (s + 1 < nsub) tmem_ld32(taddr + (s + 1) * EPI_COLS, vn);
+          } else {
             uint32_t v[32];
             tmem_ld32(taddr + s * EPI_COLS, v);
             if (GEGLU) {
@@ -649,6 +660,7 @@ int gemm_tc(cudaStream_t st, const GemmArgs& a) {
   p.out = a.out;
   p.ldc = a.ldc;
   p.stages = get_option("gemm_stages");
+  p.epi_prefetch = get_option("epi_prefetch");
 
   if (a.taps != 1) {
     VS_REQUIRE(a.nimg > 0 && a.H > 0 && a.W > 0 && a.M == a.nimg * a.H * a.W, "gemm_tc: bad conv geometry");
