@@ -220,6 +220,9 @@ int vs_profile_dump(const char* path);   /* CSV: category, shape (m,n,k), work p
  *                     in the shared memory of a thread-block cluster where that measured faster (<= 4 CTAs x 160 KB: the
  *                     16x16 / 8x8 levels); 2 = up to 16 CTAs; 0 = statistics + apply kernels everywhere
  *   "subpixel"     1  nearest-2x + conv3x3 as four sub-pixel convs; 0 = materialise the up-sampled tensor, then conv3x3
+ *   "gn_stats_v2"  0  1 = GroupNorm statistics kernel with per-position accumulators instead of a per-element group select (no gain)
+ *   "epi_prefetch" 0  1 = GEMM / conv epilogue issues the TMEM load of sub-tile s+1 while sub-tile s is processed
+ *                     (measured: GEMM time 21.6 -> 21.9 ms, no gain)
  *   "pdl"          1  programmatic dependent launch between the hot kernels; 0 = plain stream order */
 int vs_set_option(const char* name, int value);
 /* Cycle counters of the instrumented attention kernel (option "attn_debug" = 1): per CTA 16 values -- softmax warp 4:
