@@ -177,3 +177,12 @@ def test_use_blend_flow_matches_oracle():
     assert 0.05 < r["mask_fill"] < 0.95, r                               # the blend really mixes source and target latents
     assert r["unused_forced"] == (0, 0) and r["masks_checked"][1] == 2, r # both sides computed the same number of masks
     assert r["mask_mismatch"] <= 0.03 * r["mask_pixels"], r              # thresholded maps: fp16 device maps vs fp32 oracle
+
+
+def test_edlora_merge_in_place_and_restore():
+    """SURVEY 8f-4 (ED-LoRA file -> UNet weights, convert_edlora_to_diffusers.py:36-96): the in-place merge reaches the kernels
+    (lazy re-pack), matches the oracle on independently merged weights, and restore is bit-exact."""
+    r = U.edlora_merge_vs_oracle()
+    assert r["pairs"] == r["touched"] > 20, r
+    assert r["psnr"] >= 40.0 and r["psnr_unmerged_vs_merged_ref"] < r["psnr"] - 15.0, r      # the merge really changed the output
+    assert r["restored_bit_exact"], r

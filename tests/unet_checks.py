@@ -212,3 +212,38 @@ def adapter_vs_golden():
     errs = [(m.float().cpu() - r).abs().max().item() for m, r in zip(maps, g["maps"])]
     refs = [r.abs().max().item() for r in g["maps"]]
     return {"errs": errs, "refs": refs}
+
+
+def edlora_merge_vs_oracle(Fr=2, hw=8, alpha=0.6, rank=4):
+    """formats.merge_edlora_into_unet on the NATIVE model (parameters on the GPU, re-packed lazily) vs the oracle run on
+    independently merged weights; then restore_unet brings the pre-merge output back bit for bit."""
+    from videoswap_b200 import formats
+    m, sd = get_model()
+    g = torch.Generator().manual_seed(77)
+    lora = {}
+    for k, w in sd.items():
+        dn = formats.lora_down_name(k)
+        if dn == k or "motion_modules" in k or not any(s in k for s in ("down_blocks.0.", "mid_block.", "up_blocks.3.attentions.2.")):
+            continue
+        down, up = 0.1 * torch.randn((rank, w.shape[1]), generator=g), 0.1 * torch.randn((w.shape[0], rank), generator=g)
+        if w.dim() == 4:
+            down, up = down[:, :, None, None], up[:, :, None, None]
+        lora[dn], lora[dn.replace("lora_down", "lora_up")] = down, up
+    merged = dict(sd)
+    for dn in [k for k in lora if "lora_down" in k]:
+        k = dn.replace("lora_down.", "")
+        d = lora[dn.replace("lora_down", "lora_up")].squeeze() @ lora[dn].squeeze()
+        merged[k] = (sd[k] + alpha * d.reshape(sd[k].shape)).half().float()
+    x, ehs = randn((1, 4, Fr, hw, hw), 2).half(), randn((1, 16, 77, 768), 3).half()
+    before = m(x.cuda(), 981, ehs.cuda(), return_dict=False)[0].clone()
+    backup = formats.merge_edlora_into_unet(m, lora, alpha, strict=True)
+    try:
+        out = m(x.cuda(), 981, ehs.cuda(), return_dict=False)[0].clone()
+        with torch.no_grad():
+            ref = O.unet_forward(merged, O.OracleConfig(), x.float(), 981, ehs.float(), None)
+    finally:
+        formats.restore_unet(m, backup)
+    after = m(x.cuda(), 981, ehs.cuda(), return_dict=False)[0]
+    torch.cuda.synchronize()
+    return {"pairs": len(lora) // 2, "touched": len(backup), "psnr": psnr(out, ref), "psnr_unmerged_vs_merged_ref": psnr(before, ref),
+            "restored_bit_exact": bool(torch.equal(before, after))}

@@ -1,6 +1,7 @@
 """videoswap_b200: B200-native (sm_100a) implementation of the denoising hot path of showlab/VideoSwap -- the
 `AnimateDiffUNet3DModel` forward + classifier-free guidance + DDIM step -- behind the reference's own Python surface.
 See DESIGN.md / INTEGRATION.md.  Importing this package never touches `oracle/` and there is no CPU fallback."""
+from . import formats  # noqa: F401
 from .pipeline import (SparsePointAdapter, TuneAVideoPipeline, TuneAVideoPipelineOutput, VideoSwapPipeline)  # noqa: F401
 from .scheduler import DDIMInverseScheduler, DDIMScheduler  # noqa: F401
 from .spec import UNetConfig, adapter_param_shapes, unet_param_shapes  # noqa: F401
