@@ -216,7 +216,8 @@ def adapter_vs_golden():
 
 def edlora_merge_vs_oracle(Fr=2, hw=8, alpha=0.6, rank=4):
     """formats.merge_edlora_into_unet on the NATIVE model (parameters on the GPU, re-packed lazily) vs the oracle run on
-    independently merged weights; then restore_unet brings the pre-merge output back bit for bit."""
+    independently merged weights; then restore_unet brings the parameters back bit for bit (the OUTPUT is compared in dB: the
+    GroupNorm statistics use float atomics, so two forwards of the same weights differ in the last bits)."""
     from videoswap_b200 import formats
     m, sd = get_model()
     g = torch.Generator().manual_seed(77)
@@ -236,6 +237,7 @@ def edlora_merge_vs_oracle(Fr=2, hw=8, alpha=0.6, rank=4):
         merged[k] = (sd[k] + alpha * d.reshape(sd[k].shape)).half().float()
     x, ehs = randn((1, 4, Fr, hw, hw), 2).half(), randn((1, 16, 77, 768), 3).half()
     before = m(x.cuda(), 981, ehs.cuda(), return_dict=False)[0].clone()
+    saved = {k: p.detach().clone() for k, p in m.named_parameters() if k in {d.replace("lora_down.", "") for d in lora}}
     backup = formats.merge_edlora_into_unet(m, lora, alpha, strict=True)
     try:
         out = m(x.cuda(), 981, ehs.cuda(), return_dict=False)[0].clone()
@@ -246,4 +248,5 @@ def edlora_merge_vs_oracle(Fr=2, hw=8, alpha=0.6, rank=4):
     after = m(x.cuda(), 981, ehs.cuda(), return_dict=False)[0]
     torch.cuda.synchronize()
     return {"pairs": len(lora) // 2, "touched": len(backup), "psnr": psnr(out, ref), "psnr_unmerged_vs_merged_ref": psnr(before, ref),
-            "restored_bit_exact": bool(torch.equal(before, after))}
+            "restored_params_bit_exact": all(torch.equal(p, saved[k]) for k, p in m.named_parameters() if k in saved) and len(saved) == len(backup),
+            "psnr_restored_vs_before": psnr(after, before)}
