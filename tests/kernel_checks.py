@@ -370,6 +370,18 @@ CHECKS = {
     "conv3x3_epi_prefetch": with_option("epi_prefetch", 1, lambda: check_conv3x3(rowvec=True, residual=True), 0),
     "ln_fuse_res_prefetch": with_option("epi_prefetch", 1, lambda: check_linear_ln_linear(rows=128 * 150 + 37, residual=True, N=320, seed=161, mean=2.0), 0),
     "gemm_bn128_tail_prefetch": with_option("epi_prefetch", 1, lambda: check_gemm(300, 768, 320, bn=128), 0),
+    # residual rows of the next tile prefetched into L2 ("res_prefetch": 1 = prefetch.global.L2, 2 = cp.async.bulk.prefetch.L2);
+    # ragged M (rows outside the problem must not be touched), partial last column tile, conv geometry, CTA pairs
+    "gemm_residual_respf1": with_option("res_prefetch", 1, lambda: check_gemm(128 * 150 + 9, 1280, 320, residual=True, seed=8), 0),
+    "gemm_residual_respf2": with_option("res_prefetch", 2, lambda: check_gemm(128 * 150 + 9, 1280, 320, residual=True, seed=8), 0),
+    "gemm_residual_k320_respf1": with_option("res_prefetch", 1, lambda: check_gemm(128 * 301 + 77, 320, 320, residual=True, seed=21), 0),
+    "gemm_residual_k320_respf2": with_option("res_prefetch", 2, lambda: check_gemm(128 * 301 + 77, 320, 320, residual=True, seed=21), 0),
+    "gemm_residual_n96_respf2": with_option("res_prefetch", 2, lambda: check_gemm(128 * 3 + 5, 96, 320, residual=True, seed=22), 0),
+    "gemm_pair_residual_respf1": with_option("res_prefetch", 1, lambda: check_gemm(128 * 5 + 9, 1280, 1024, residual=True, seed=13), 0),
+    "gemm_pair_residual_respf2": with_option("res_prefetch", 2, lambda: check_gemm(128 * 5 + 9, 1280, 1024, residual=True, seed=13), 0),
+    "conv3x3_respf1": with_option("res_prefetch", 1, lambda: check_conv3x3(rowvec=True, residual=True), 0),
+    "conv3x3_respf2": with_option("res_prefetch", 2, lambda: check_conv3x3(rowvec=True, residual=True), 0),
+    "ln_fuse_res_respf2": with_option("res_prefetch", 2, lambda: check_linear_ln_linear(rows=128 * 150 + 37, residual=True, N=320, seed=161, mean=2.0), 0),
     "gemm_bn160": lambda: check_gemm(512, 320, 320),
     "gemm_bn128_tail": lambda: check_gemm(300, 768, 320, bn=128),
     "gemm_bn64": lambda: check_gemm(130, 64, 128, bn=64),

@@ -185,4 +185,4 @@ def test_edlora_merge_in_place_and_restore():
     r = U.edlora_merge_vs_oracle()
     assert r["pairs"] == r["touched"] > 20, r
     assert r["psnr"] >= 40.0 and r["psnr_unmerged_vs_merged_ref"] < r["psnr"] - 15.0, r      # the merge really changed the output
-    assert r["restored_params_bit_exact"] and r["psnr_restored_vs_before"] >= 80.0, r
+    assert r["restored_params_bit_exact"] and r["psnr_restored_vs_before"] >= 60.0, r

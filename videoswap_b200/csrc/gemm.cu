@@ -71,6 +71,8 @@ struct GemmParams {
   __half* out;
   int ldc;
   int epi_prefetch;  // 1 = the accumulator columns of sub-tile s+1 are loaded from TMEM while sub-tile s is processed
+  int res_prefetch;  // residual rows of this epilogue group's NEXT tile are prefetched into L2 while the current tile is
+                     // drained: 1 = prefetch.global.L2 per 128 bytes, 2 = one cp.async.bulk.prefetch.L2 per row, 0 = off
   int staged;        // 1 = smem-transposed coalesced epilogue; 0 = direct stores for tiny / unaligned N
   int stages;        // 0 = all, else limits the smem ring depth (pipeline-depth experiments)
 };
@@ -268,22 +270,47 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN;
     uint32_t aph = 0;
     const uint32_t tempty_arrive = PAIR ? mapa_shared(tempty_bar(acc), 0) : tempty_bar(acc);   // PAIR: the leader's barrier
-    for (int tile = t_begin + grp * t_step; tile < total_tiles; tile += 2 * t_step, aph ^= 1) {
-      const int mt = tile / p.n_tiles, n_tile = tile - mt * p.n_tiles;
+    // output pixel (row of the GEMM) this thread owns in `tile`, -1 = outside the problem
+    auto tile_pixel = [&](int tile, int& n_tile) -> int {
+      const int mt = tile / p.n_tiles;
+      n_tile = tile - mt * p.n_tiles;
       const int m_tile = PAIR ? 2 * mt + (int)crank : mt;
-      int pix;                              // output pixel (row of the GEMM) of this thread, -1 = outside the problem
       if (p.a_rank == 4) {
         const int x0 = (m_tile % p.tiles_x) * p.TW;
         const int y0 = ((m_tile / p.tiles_x) % p.tiles_y) * p.TH;
         const int i0 = (m_tile / (p.tiles_x * p.tiles_y)) * p.TN;
         const int ti = row >> p.thw_log, rem = row & ((1 << p.thw_log) - 1);
         const int y = y0 + (rem >> p.tw_log), x = x0 + (rem & (p.TW - 1)), img = i0 + ti;
-        pix = ((m_tile < p.m_tiles) && (img < p.nimg) && (y < p.H) && (x < p.W))
-                  ? (img * p.OH + y * p.osy + p.ooy) * p.OW + x * p.osx + p.oox : -1;
-      } else {
-        pix = m_tile * BM + row;
-        if (pix >= p.M) pix = -1;
+        return ((m_tile < p.m_tiles) && (img < p.nimg) && (y < p.H) && (x < p.W))
+                   ? (img * p.OH + y * p.osy + p.ooy) * p.OW + x * p.osx + p.oox : -1;
       }
+      const int px = m_tile * BM + row;
+      return px < p.M ? px : -1;
+    };
+    // The residual add made the K <= 640 epilogues DRAM-latency-bound: each 32-column sub-tile waited for residual rows
+    // requested only one sub-tile earlier (ncu: the top stall of the epilogue warps was the long scoreboard on those loads,
+    // DRAM at 46 %, tensor pipe at 22 %).  The rows of the group's NEXT tile are therefore pulled into L2 a whole tile ahead.
+    auto prefetch_residual = [&](int tile) {
+      if (tile >= total_tiles) return;
+      int nt;
+      const int px = tile_pixel(tile, nt);
+      if (px < 0) return;
+      const int n0p = nt * BN;
+      const int bytes = (p.N - n0p < BN ? p.N - n0p : BN) * 2;
+      const char* src = reinterpret_cast<const char*>(p.residual + (long long)px * p.ldr + n0p);
+      if (p.res_prefetch == 2) {
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+      } else {
+        for (int o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + o));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(src + bytes - 1));
+      }
+    };
+    const bool res_pf = HAS_RES && !GEGLU && staged && p.res_prefetch != 0;
+    if (res_pf) prefetch_residual(t_begin + grp * t_step);
+    for (int tile = t_begin + grp * t_step; tile < total_tiles; tile += 2 * t_step, aph ^= 1) {
+      int n_tile;
+      const int pix = tile_pixel(tile, n_tile);
+      if (res_pf) prefetch_residual(tile + 2 * t_step);
       const int n0 = n_tile * BN;
 
       if (staged) {
@@ -329,14 +356,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         int tpix[4];                        // pixels of the rows this lane stores after the transpose
 #pragma unroll
         for (int i = 0; i < 4; ++i) tpix[i] = __shfl_sync(0xffffffffu, pix, i * 8 + tr);
-        uint4 rres[4];
-        auto load_res = [&](int s) {        // coalesced residual rows of sub-tile s (one sub-tile ahead of its use)
+        // Row pointers of the 4 rows this lane stores, computed once per tile: the sub-tile loop below is fully unrolled for
+        // the linear epilogues, so every access becomes [pointer + immediate].  (Computed per access inside a rolled loop --
+        // 64-bit multiplies, constant-bank reloads after every asm volatile, one branch per row, register copies for the
+        // residual double buffer -- the sub-tile body was ~290 instructions per warp, and with two epilogue warps per
+        // scheduler the K <= 640 GEMMs were bound by exactly that instruction stream: ncu, profiles/r02_ncu_proj.json.)
+        // Rows outside the problem point at row 0 (loads are harmless, stores are predicated).
+        __half* orow[4];
+        const __half* rrow[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            rres[i] = tpix[i] >= 0 ? __ldg(reinterpret_cast<const uint4*>(p.residual + (long long)tpix[i] * p.ldr + oc0 + s * EPI_COLS + tch * 8))
-                                   : make_uint4(0, 0, 0, 0);
+        for (int i = 0; i < 4; ++i) {
+          const long long px = tpix[i] >= 0 ? tpix[i] : 0;
+          orow[i] = p.out + px * p.ldc + oc0 + tch * 8;
+          rrow[i] = HAS_RES ? p.residual + px * p.ldr + oc0 + tch * 8 : nullptr;
+        }
+        // Residual rows are requested one sub-tile ahead of their use into the OTHER of two register sets (the sub-tile loop is
+        // unrolled by two so the sets alternate without copies).
+        uint4 res_a[4], res_b[4];
+        auto load_res = [&](int s, uint4 (&dst)[4]) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dst[i] = __ldg(reinterpret_cast<const uint4*>(rrow[i] + s * EPI_COLS));
         };
-        if (HAS_RES) load_res(0);
+        if (HAS_RES) load_res(0, res_a);
         // The tile's bias vector goes to this warp's own shared-memory slice while the accumulator is still being
         // computed; the sub-tiles then read it as broadcast LDS.  (Read with __ldg inside the sub-tile loop, the epilogue
         // warps of the K = 320 GEMMs spent 31% of their time waiting for those loads.)
@@ -366,8 +407,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         uint32_t vn[32];
         const bool prefetch = !GEGLU && p.epi_prefetch != 0;
         if (prefetch) tmem_ld32(taddr, vn);
-#pragma unroll 1
-        for (int s = 0; s < nsub; ++s) {
+        auto subtile = [&](const int s, uint4 (&rcur)[4], uint4 (&rnext)[4]) {
           float f[32];
           if (prefetch) {
             tmem_ld_wait();
@@ -412,12 +452,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             if (PAIR) mbar_arrive_cluster(tempty_arrive);
             else mbar_arrive(tempty_bar(acc));
           }
-          uint4 rcur[4];
-          if (HAS_RES) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) rcur[i] = rres[i];
-            if (s + 1 < nsub) load_res(s + 1);
-          }
+          if (HAS_RES && s + 1 < nsub) load_res(s + 1, rnext);
           if (!GEGLU) {
             if (LN) {                         // rstd * acc + (-mean rstd) * u + c in two FMAs per element
               const uint32_t up = u_stage + s * EPI_COLS * 4, bp = bias_stage + s * EPI_COLS * 4;
@@ -459,7 +494,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                          "r"(pk[2]), "r"(pk[3]) : "memory");
           }
           __syncwarp();
-          const int col = oc0 + s * EPI_COLS + tch * 8;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {       // 8 rows x 64 contiguous bytes per store instruction
             uint4 o;
@@ -471,7 +505,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
               for (int u = 0; u < 4; ++u) oh[u] = __hadd2(oh[u], rh[u]);
             }
-            if (tpix[i] >= 0) *reinterpret_cast<uint4*>(p.out + (long long)tpix[i] * p.ldc + col) = o;
+            if (tpix[i] >= 0) *reinterpret_cast<uint4*>(orow[i] + s * EPI_COLS) = o;
             if (LNOUT) {                      // off the store's critical path: 8 values of row i*8+tr
               const __half2* oh = reinterpret_cast<const __half2*>(&o);
               const float2 a = __half22float2(oh[0]), b = __half22float2(oh[1]), c = __half22float2(oh[2]), d = __half22float2(oh[3]);
@@ -481,6 +515,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
               rq[i] += (q0 + q1) + (q2 + q3);
             }
           }
+        };
+#pragma unroll 1
+        for (int s = 0; s < nsub; s += 2) {
+          subtile(s, res_a, res_b);
+          if (s + 1 < nsub) subtile(s + 1, res_b, res_a);
         }
         if (LNOUT) {                          // the 4 column chunks of a row sit in 4 adjacent lanes
 #pragma unroll
@@ -661,6 +700,7 @@ int gemm_tc(cudaStream_t st, const GemmArgs& a) {
   p.ldc = a.ldc;
   p.stages = get_option("gemm_stages");
   p.epi_prefetch = get_option("epi_prefetch");
+  p.res_prefetch = get_option("res_prefetch");
 
   if (a.taps != 1) {
     VS_REQUIRE(a.nimg > 0 && a.H > 0 && a.W > 0 && a.M == a.nimg * a.H * a.W, "gemm_tc: bad conv geometry");
