@@ -221,6 +221,11 @@ int vs_profile_dump(const char* path);   /* CSV: category, shape (m,n,k), work p
  *                     16x16 / 8x8 levels); 2 = up to 16 CTAs; 0 = statistics + apply kernels everywhere
  *   "subpixel"     1  nearest-2x + conv3x3 as four sub-pixel convs; 0 = materialise the up-sampled tensor, then conv3x3
  *   "gn_stats_v2"  0  1 = GroupNorm statistics kernel with per-position accumulators instead of a per-element group select (no gain)
+ *   "res_stage"    1  single-CTA linear layers with a residual and K <= 320 (proj_out / to_out at the 64x64 level): the epilogue
+ *                     keeps the residual rows of a whole tile in shared memory, copied in with cp.async one tile ahead
+ *                     (-8 % at M = 131072; deeper K loses more to the shorter operand ring than it gains); 0 = registers only
+ *   "res_prefetch" 0  1 / 2 = residual rows of the next tile prefetched into L2 (prefetch.global.L2 / cp.async.bulk.prefetch.L2);
+ *                     measured: no gain
  *   "epi_prefetch" 0  1 = GEMM / conv epilogue issues the TMEM load of sub-tile s+1 while sub-tile s is processed
  *                     (measured: GEMM time 21.6 -> 21.9 ms, no gain)
  *   "pdl"          1  programmatic dependent launch between the hot kernels; 0 = plain stream order */

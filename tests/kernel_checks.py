@@ -382,6 +382,22 @@ CHECKS = {
     "conv3x3_respf1": with_option("res_prefetch", 1, lambda: check_conv3x3(rowvec=True, residual=True), 0),
     "conv3x3_respf2": with_option("res_prefetch", 2, lambda: check_conv3x3(rowvec=True, residual=True), 0),
     "ln_fuse_res_respf2": with_option("res_prefetch", 2, lambda: check_linear_ln_linear(rows=128 * 150 + 37, residual=True, N=320, seed=161, mean=2.0), 0),
+    # whole-tile residual stage in shared memory ("res_stage" = 1, default; single-CTA linear layers with K <= 320): many tiles
+    # per CTA (refill of consumed chunks with the next tile's rows), ragged M, a partial last column tile (different sub-tile
+    # counts of consecutive tiles), every BN that takes the path, the K boundary, and the register path kept for A/B
+    "gemm_resst_l0_full": lambda: check_gemm(131072, 320, 320, residual=True, seed=31),
+    "gemm_resst_ragged_many_tiles": lambda: check_gemm(128 * 901 + 77, 320, 320, residual=True, seed=32),
+    "gemm_resst_n96_partial_tile": lambda: check_gemm(128 * 40 + 5, 96, 320, residual=True, seed=33),
+    "gemm_resst_n224_bn160_partial": lambda: check_gemm(128 * 333 + 1, 224, 256, residual=True, bn=160, seed=34),
+    "gemm_resst_bn128": lambda: check_gemm(128 * 300 + 9, 640, 320, residual=True, bn=128, seed=35),
+    "gemm_resst_bn64": lambda: check_gemm(128 * 300 + 9, 320, 320, residual=True, bn=64, seed=36),
+    "gemm_resst_k64": lambda: check_gemm(32768, 320, 64, residual=True, seed=37),
+    "gemm_res_k384_register_path": lambda: check_gemm(4096, 320, 384, residual=True, seed=38),
+    "gemm_res_k1280_register_path": lambda: check_gemm(32768, 320, 1280, residual=True, seed=40),
+    "gemm_res_pair_k1024_register_path": lambda: check_gemm(128 * 64 + 9, 1280, 1024, residual=True, seed=39),
+    "gemm_resst_off_register_path": with_option("res_stage", 0, lambda: check_gemm(128 * 301 + 77, 320, 320, residual=True, seed=21), 1),
+    "ln_fuse_res_resst_many_tiles": lambda: check_linear_ln_linear(rows=128 * 700 + 37, residual=True, N=320, seed=162, mean=2.0),
+    "ln_fuse_res_resst_off": with_option("res_stage", 0, lambda: check_linear_ln_linear(rows=128 * 150 + 37, residual=True, N=320, seed=161, mean=2.0), 1),
     "gemm_bn160": lambda: check_gemm(512, 320, 320),
     "gemm_bn128_tail": lambda: check_gemm(300, 768, 320, bn=128),
     "gemm_bn64": lambda: check_gemm(130, 64, 128, bn=64),

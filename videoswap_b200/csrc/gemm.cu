@@ -40,7 +40,7 @@ constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int EPI_COLS = 32;                        // output columns per epilogue sub-tile (64 B of fp16: SWIZZLE_64B)
 constexpr int EPI_WARP_BYTES = 4096;                // per epilogue warp: 2 KB transpose staging + 1 KB bias + 1 KB LN-fold slice
 constexpr int EPI_BYTES = 8 * EPI_WARP_BYTES;
-enum { EPI_F_GEGLU = 1, EPI_F_RES = 2, EPI_F_RV = 4, EPI_F_LN = 8, EPI_F_LNOUT = 16 };   // compile-time epilogue features
+enum { EPI_F_GEGLU = 1, EPI_F_RES = 2, EPI_F_RV = 4, EPI_F_LN = 8, EPI_F_LNOUT = 16, EPI_F_RESST = 32 };   // compile-time epilogue features
 
 struct GemmParams {
   CUtensorMap tmA, tmA2, tmB;
@@ -71,25 +71,45 @@ struct GemmParams {
   __half* out;
   int ldc;
   int epi_prefetch;  // 1 = the accumulator columns of sub-tile s+1 are loaded from TMEM while sub-tile s is processed
+  int res_stage;     // 1 = linear layers with a residual and K <= 320 keep the residual tile in shared memory (EPI_F_RESST)
   int res_prefetch;  // residual rows of this epilogue group's NEXT tile are prefetched into L2 while the current tile is
                      // drained: 1 = prefetch.global.L2 per 128 bytes, 2 = one cp.async.bulk.prefetch.L2 per row, 0 = off
   int staged;        // 1 = smem-transposed coalesced epilogue; 0 = direct stores for tiny / unaligned N
   int stages;        // 0 = all, else limits the smem ring depth (pipeline-depth experiments)
 };
 
-template <int BN, bool PAIR = false>
+// RESST: the epilogue keeps the residual rows of a whole tile in shared memory (one private [32 rows x BN] slice per epilogue
+// warp, filled with cp.async a whole tile ahead); it costs ring stages, so only tiles up to BN = 160 take it.
+template <int BN, bool PAIR = false, bool RESST = false>
 struct Cfg {
   static constexpr int B_STAGE_BYTES = (PAIR ? BN / 2 : BN) * BK * 2;   // a CTA pair splits the weight tile along N
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES_RAW = (SMEM_LIMIT - 2048 - EPI_BYTES) / STAGE_BYTES;
+  // row stride of a residual slice: 64 B of padding when the row would be a multiple of 128 B, so that the two rows a
+  // quarter-warp reads per LDS.128 phase fall into different bank halves
+  static constexpr int RES_ROW_BYTES = BN * 2 + ((BN * 2) % 128 == 0 ? 64 : 0);
+  static constexpr int RES_WARP_BYTES = RESST ? 32 * RES_ROW_BYTES : 0;
+  static constexpr int RES_BYTES = 8 * RES_WARP_BYTES;
+  static constexpr int STAGES_RAW = (SMEM_LIMIT - 2048 - EPI_BYTES - RES_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + RES_BYTES;
   static_assert(2 * BN <= 512, "two accumulator stages must fit TMEM");
   static_assert(B_STAGE_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment for SWIZZLE_128B");
   static_assert(STAGES >= 3, "pipeline too shallow");
 };
 
+__host__ __device__ constexpr bool residual_staged(int BN, int EPI) {
+  return (EPI & EPI_F_RESST) != 0 && (EPI & EPI_F_RES) != 0 && (EPI & EPI_F_GEGLU) == 0 && BN <= 160;
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -104,7 +124,8 @@ __device__ __forceinline__ uint32_t sw64_off(int row, int chunk) {   // byte off
 // third (BN = 256: 32 KB instead of 48 KB per 512 tensor cycles and CTA).
 template <int BN, int EPI, bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-  using C = Cfg<BN, PAIR>;
+  constexpr bool RESST = residual_staged(BN, EPI);
+  using C = Cfg<BN, PAIR, RESST>;
   constexpr bool GEGLU = (EPI & EPI_F_GEGLU) != 0, HAS_RES = (EPI & EPI_F_RES) != 0, HAS_RV = (EPI & EPI_F_RV) != 0;
   // LN: the A operand is the RAW input of a LayerNorm whose affine map is folded into the weights:
   //   LN(x) W^T = rstd (x W'^T) - rstd mean u + c,  W' = W * gamma, u[n] = sum_k W'[n,k], c = beta W^T + bias (the `bias`)
@@ -305,12 +326,54 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         asm volatile("prefetch.global.L2 [%0];" ::"l"(src + bytes - 1));
       }
     };
-    const bool res_pf = HAS_RES && !GEGLU && staged && p.res_prefetch != 0;
+    const bool res_pf = HAS_RES && !GEGLU && !RESST && staged && p.res_prefetch != 0;
     if (res_pf) prefetch_residual(t_begin + grp * t_step);
+    // RESST -- whole-tile residual stage.  With the residual rows requested one 32-column sub-tile ahead (register double
+    // buffer, below) every epilogue warp sat out one full memory latency per sub-tile: 5 x ~1.2 us + work = the 8.6 us a
+    // BN = 160 tile took (64 us vs 42 us without the residual at M = 131072, N = K = 320; fewer instructions or an L2
+    // prefetch did not move it; this stage brings it to 58 us -- it costs ring stages, see launch_linear for where it is used).  Now each lane owns the sixteen-byte
+    // chunks it will add after the transpose -- rows i*8 + tr, chunk tch of every sub-tile -- in a private shared-memory
+    // slice: it copies them in with cp.async, one commit group per sub-tile, and refills a sub-tile's chunks with the NEXT
+    // tile's rows right after it has consumed them.  A chunk is written and read by the same lane only, so no barrier is
+    // involved: program order covers write-after-read, cp.async.wait_group covers read-after-write.  Every tile commits
+    // exactly MAXSUB groups (empty ones for missing sub-tiles or a missing next tile), so when sub-tile s is consumed the
+    // groups younger than its own are always MAXSUB - 1: (MAXSUB - 1 - s) of this tile + s refills.
+    constexpr int MAXSUB_T = (GEGLU ? BN / 2 : BN) / EPI_COLS;
+    const uint32_t res_lane = bar_base + 256u + (uint32_t)((warp - 4) * C::RES_WARP_BYTES + tr * C::RES_ROW_BYTES + tch * 16);
+    const __half* rnext[4] = {nullptr, nullptr, nullptr, nullptr};   // this lane's 4 residual rows of the group's next tile
+    int nsub_next = 0;
+    auto residual_rows = [&](int tile) {
+      nsub_next = 0;
+      if (tile < total_tiles) {               // warp-uniform
+        int nt;
+        const int px = tile_pixel(tile, nt);
+        const int n0p = nt * BN;
+        nsub_next = (p.N - n0p < BN ? p.N - n0p : BN) / EPI_COLS;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int tp = __shfl_sync(0xffffffffu, px, i * 8 + tr);
+          rnext[i] = tp >= 0 ? p.residual + (long long)tp * p.ldr + n0p + tch * 8 : nullptr;
+        }
+      }
+    };
+    auto stage_residual = [&](int s) {       // this lane's chunks of sub-tile s of the next tile; always exactly one group
+      if (s < nsub_next) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (rnext[i] != nullptr) cp_async16(res_lane + (uint32_t)(i * 8 * C::RES_ROW_BYTES + s * 64), rnext[i] + s * EPI_COLS);
+      }
+      cp_async_commit();
+    };
+    if (RESST && staged) {
+      residual_rows(t_begin + grp * t_step);
+#pragma unroll 1
+      for (int s = 0; s < MAXSUB_T; ++s) stage_residual(s);
+    }
     for (int tile = t_begin + grp * t_step; tile < total_tiles; tile += 2 * t_step, aph ^= 1) {
       int n_tile;
       const int pix = tile_pixel(tile, n_tile);
       if (res_pf) prefetch_residual(tile + 2 * t_step);
+      if (RESST && staged) residual_rows(tile + 2 * t_step);
       const int n0 = n_tile * BN;
 
       if (staged) {
@@ -359,8 +422,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         // Row pointers of the 4 rows this lane stores, computed once per tile: the sub-tile loop below is fully unrolled for
         // the linear epilogues, so every access becomes [pointer + immediate].  (Computed per access inside a rolled loop --
         // 64-bit multiplies, constant-bank reloads after every asm volatile, one branch per row, register copies for the
-        // residual double buffer -- the sub-tile body was ~290 instructions per warp, and with two epilogue warps per
-        // scheduler the K <= 640 GEMMs were bound by exactly that instruction stream: ncu, profiles/r02_ncu_proj.json.)
+        // residual double buffer -- the sub-tile body was ~300 instructions per warp; the diet to ~210 bought 2 % of the GEMM
+        // time, the residual latency above was the larger term: profiles/r02_ncu_proj.json, r02_epilogue_shapes_ab.json.)
         // Rows outside the problem point at row 0 (loads are harmless, stores are predicated).
         __half* orow[4];
         const __half* rrow[4];
@@ -368,7 +431,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         for (int i = 0; i < 4; ++i) {
           const long long px = tpix[i] >= 0 ? tpix[i] : 0;
           orow[i] = p.out + px * p.ldc + oc0 + tch * 8;
-          rrow[i] = HAS_RES ? p.residual + px * p.ldr + oc0 + tch * 8 : nullptr;
+          rrow[i] = (HAS_RES && !RESST) ? p.residual + px * p.ldr + oc0 + tch * 8 : nullptr;
         }
         // Residual rows are requested one sub-tile ahead of their use into the OTHER of two register sets (the sub-tile loop is
         // unrolled by two so the sets alternate without copies).
@@ -377,7 +440,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
           for (int i = 0; i < 4; ++i) dst[i] = __ldg(reinterpret_cast<const uint4*>(rrow[i] + s * EPI_COLS));
         };
-        if (HAS_RES) load_res(0, res_a);
+        if (HAS_RES && !RESST) load_res(0, res_a);
         // The tile's bias vector goes to this warp's own shared-memory slice while the accumulator is still being
         // computed; the sub-tiles then read it as broadcast LDS.  (Read with __ldg inside the sub-tile loop, the epilogue
         // warps of the K = 320 GEMMs spent 31% of their time waiting for those loads.)
@@ -407,7 +470,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         uint32_t vn[32];
         const bool prefetch = !GEGLU && p.epi_prefetch != 0;
         if (prefetch) tmem_ld32(taddr, vn);
-        auto subtile = [&](const int s, uint4 (&rcur)[4], uint4 (&rnext)[4]) {
+        auto subtile = [&](const int s, uint4 (&rcur)[4], uint4 (&rnxt)[4]) {
           float f[32];
           if (prefetch) {
             tmem_ld_wait();
@@ -452,7 +515,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             if (PAIR) mbar_arrive_cluster(tempty_arrive);
             else mbar_arrive(tempty_bar(acc));
           }
-          if (HAS_RES && s + 1 < nsub) load_res(s + 1, rnext);
+          if (HAS_RES && !RESST && s + 1 < nsub) load_res(s + 1, rnxt);
           if (!GEGLU) {
             if (LN) {                         // rstd * acc + (-mean rstd) * u + c in two FMAs per element
               const uint32_t up = u_stage + s * EPI_COLS * 4, bp = bias_stage + s * EPI_COLS * 4;
@@ -494,6 +557,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                          "r"(pk[2]), "r"(pk[3]) : "memory");
           }
           __syncwarp();
+          if (RESST) cp_async_wait<MAXSUB_T - 1>();   // this lane's residual chunks of sub-tile s have landed
 #pragma unroll
           for (int i = 0; i < 4; ++i) {       // 8 rows x 64 contiguous bytes per store instruction
             uint4 o;
@@ -501,7 +565,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                          : "r"(out_stage + sw64_off(i * 8 + tr, tch)));
             if (HAS_RES) {                    // fp16 add: the rounding order of the reference's `linear(x) + residual`
               __half2* oh = reinterpret_cast<__half2*>(&o);
-              const __half2* rh = reinterpret_cast<const __half2*>(&rcur[i]);
+              uint4 rr;
+              if (RESST) {
+                asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(rr.x), "=r"(rr.y), "=r"(rr.z), "=r"(rr.w)
+                             : "r"(res_lane + (uint32_t)(i * 8 * C::RES_ROW_BYTES + s * 64)));
+              } else {
+                rr = rcur[i];
+              }
+              const __half2* rh = reinterpret_cast<const __half2*>(&rr);
 #pragma unroll
               for (int u = 0; u < 4; ++u) oh[u] = __hadd2(oh[u], rh[u]);
             }
@@ -515,11 +586,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
               rq[i] += (q0 + q1) + (q2 + q3);
             }
           }
+          if (RESST) stage_residual(s);       // the chunks just consumed are refilled with the next tile's rows
         };
 #pragma unroll 1
         for (int s = 0; s < nsub; s += 2) {
           subtile(s, res_a, res_b);
           if (s + 1 < nsub) subtile(s + 1, res_b, res_a);
+        }
+        if (RESST) {
+#pragma unroll 1
+          for (int s = nsub; s < MAXSUB_T; ++s) stage_residual(s);   // keep the group count per tile constant
         }
         if (LNOUT) {                          // the 4 column chunks of a row sit in 4 adjacent lanes
 #pragma unroll
@@ -560,6 +636,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         else mbar_arrive(tempty_bar(acc));
       }
     }
+    if (RESST) cp_async_wait<0>();             // only empty groups can be left; nothing in flight when the CTA exits
   }
 
   tc_fence_before();
@@ -593,7 +670,7 @@ ConvTile pick_conv_tile(int nimg, int H, int W) {
 
 template <int BN, int EPI, bool PAIR>
 int launch(cudaStream_t st, const GemmParams& p) {
-  using C = Cfg<BN, PAIR>;
+  using C = Cfg<BN, PAIR, residual_staged(BN, EPI)>;
   static bool configured = false;
   if (!configured) {
     VS_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -612,8 +689,20 @@ int launch(cudaStream_t st, const GemmParams& p) {
 
 template <int BN, bool PAIR>
 int launch_linear(cudaStream_t st, const GemmParams& p) {
-  const int epi = (p.residual ? EPI_F_RES : 0) | (p.rowvec ? EPI_F_RV : 0) | ((p.ln_stats || p.ln_parts) ? EPI_F_LN : 0) |
-                  (p.ln_sums_out ? EPI_F_LNOUT : 0);
+  int epi = (p.residual ? EPI_F_RES : 0) | (p.rowvec ? EPI_F_RV : 0) | ((p.ln_stats || p.ln_parts) ? EPI_F_LN : 0) |
+            (p.ln_sums_out ? EPI_F_LNOUT : 0);
+  // Whole-tile residual stage in shared memory: pays only where the epilogue, not the main loop, sets the tile time AND a
+  // 3-stage operand ring is deep enough -- measured: K = 320 (5 k-blocks) at M = 131072 -8 %; K = 640 +7 %, K = 1280 +20 %,
+  // CTA pairs +15 % (profiles/r02_resst_shapes.json).  So: single-CTA linear layers with K <= 320 only.
+  if constexpr (BN <= 160 && !PAIR) {
+    if ((epi == EPI_F_RES || epi == (EPI_F_LNOUT | EPI_F_RES)) && p.res_stage != 0 && p.staged != 0 && p.a_rank != 4 && p.num_kb <= 5)
+      epi |= EPI_F_RESST;
+    switch (epi) {
+      case EPI_F_RES | EPI_F_RESST: return launch<BN, EPI_F_RES | EPI_F_RESST, PAIR>(st, p);
+      case EPI_F_LNOUT | EPI_F_RES | EPI_F_RESST: return launch<BN, EPI_F_LNOUT | EPI_F_RES | EPI_F_RESST, PAIR>(st, p);
+      default: break;
+    }
+  }
   switch (epi) {
     case EPI_F_LNOUT: return launch<BN, EPI_F_LNOUT, PAIR>(st, p);
     case EPI_F_LNOUT | EPI_F_RES: return launch<BN, EPI_F_LNOUT | EPI_F_RES, PAIR>(st, p);
@@ -701,6 +790,7 @@ int gemm_tc(cudaStream_t st, const GemmArgs& a) {
   p.stages = get_option("gemm_stages");
   p.epi_prefetch = get_option("epi_prefetch");
   p.res_prefetch = get_option("res_prefetch");
+  p.res_stage = get_option("res_stage");
 
   if (a.taps != 1) {
     VS_REQUIRE(a.nimg > 0 && a.H > 0 && a.W > 0 && a.M == a.nimg * a.H * a.W, "gemm_tc: bad conv geometry");

@@ -124,6 +124,7 @@ static Option g_options[] = {
     {"attn_poly", 1},      // P chunks (of 8 per key tile) whose exp2 runs on the FMA pipe instead of MUFU (0..3)
     {"attn_handoff", 1},   // 1: the softmax ping-pong hands the MUFU pipe over after 7 of 8 key chunks, 0: after the last
     {"gemm_pair", 1},      // CTA pairs (cta_group::2, 256-row tiles): 1 = for K >= 768, 0 = never, 2 = whenever possible
+    {"res_stage", 1},      // linear layers with a residual, K <= 320: residual tile staged in shared memory a whole tile ahead
     {"res_prefetch", 0},   // GEMM epilogue: residual rows of the next tile prefetched into L2 (1 = per 128 B, 2 = bulk per row)
     {"epi_prefetch", 0},   // GEMM epilogue: TMEM load of sub-tile s+1 issued while sub-tile s is processed (A/B)
     {"gemm_stages", 0},    // smem ring depth limit (0 = all)
