@@ -109,6 +109,20 @@ def test_cfg_split_times_frame_shards_reproduce_the_step_world4():
     assert torch.equal(by[0], by[2]) and torch.equal(by[1], by[3])
 
 
+def test_cfg_split_times_four_frame_shards_reproduce_the_step_world8():
+    """8 ranks = CFG pair x 4 frame shards (the layout `bench.py --gpus 8` runs): one frame per rank, so every temporal
+    attention works purely on re-sharded pixels and every GroupNorm statistic is an all-reduce of four single-frame partials."""
+    from oracle import unet3d_oracle as O
+    sd, oc, lat, ehs2, res = _tiny_problem()
+    with torch.no_grad():
+        ref = O.denoise_step(sd, oc, O.DDIM(), lat, 981, 50, ehs2, 7.5, res)
+    got = _run(8, True, 37500)
+    assert sorted(r for r, _, _ in got) == list(range(8))
+    for rank, frames, out in got:
+        assert len(frames) == 1 and frames[0] == rank % 4
+        assert torch.allclose(out, ref[:, :, frames[0]:frames[0] + 1], atol=2e-5), (rank, (out - ref[:, :, frames[0]:frames[0] + 1]).abs().max())
+
+
 def test_plan_layout():
     p = [make_plan(8, r) for r in range(8)]
     assert [x.cfg_index for x in p] == [0, 0, 0, 0, 1, 1, 1, 1] and [x.frame_shard for x in p] == [0, 1, 2, 3] * 2
